@@ -1,0 +1,157 @@
+// common.cuh — shared declarations of the B200 ICP engine (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "icp_b200.h"
+
+namespace icpb {
+
+typedef unsigned long long u64;
+
+// ---- K1 (brute-force matching) geometry ------------------------------------------------------
+// Targets live in HBM re-tiled as [tile][X|Y|Z][K1_TT] floats so that one 1-D TMA bulk copy brings
+// one tile (12 KB) into shared memory. Correspondence tracking is done per sub-tile of K1_TRK
+// targets: the inner loop only keeps a running minimum; the winning index is recovered afterwards
+// by re-scanning one sub-tile per source.
+constexpr int K1_TT     = 1024;   // targets per shared-memory tile
+constexpr int K1_TRK    = 128;    // targets per tracking sub-tile
+constexpr int K1_STAGES = 3;      // TMA ring depth
+constexpr int K1_TILE_BYTES = 3 * K1_TT * 4;
+constexpr u64 KEY_UNMATCHED = ~0ull;
+
+// ---- device-resident control block of a registration ----------------------------------------
+struct IterState {
+	int    done;          // set on the device when the reference's loop would `break` / hit MAX_ITER
+	int    iteration;     // the reference's `iteration` counter
+	int    iters_run;     // loop bodies executed
+	int    numeric_error; // 6x6 system not SPD
+	int    ticket_a;      // last-block tickets of the two reduction kernels
+	int    ticket_b;
+	int    max_iter;
+	int    stop_early;
+	double tol;
+	double n_total;       // global number of source points (all ranks)
+	double moments[32];   // reduced moment sums (16 point-to-point, 28 point-to-plane)
+	double err_sum;       // sum of squared residuals
+	float  R[9];          // this iteration's rotation (column-major) and translation
+	float  T[3];
+	double Rtot[9];       // accumulated transform
+	double ttot[3];
+	float  last_err;
+};
+
+struct K1Params {
+	const float* px; const float* py; const float* pz;   // SoA sources, padded to nb * block sources
+	const float* qtiles;                                  // [nt][3][K1_TT]
+	u64*         keys;                                    // per source: (distance bits << 32) | target index
+	int          n;                                       // valid sources
+	int          nt;                                      // target tiles
+	long long    units;                                   // nb * nt (source block x target tile work units)
+	float        thr0;                                    // initial threshold in the squared-distance domain
+	float        sentinel;
+	const int*   done;
+};
+
+struct ReduceParams {
+	const float* px; const float* py; const float* pz;
+	float*       ox; float* oy; float* oz;               // transform output (in place allowed)
+	const float4* q4;                                     // targets AoS padded to float4
+	const float4* nrm4;                                   // normals (point-to-plane)
+	u64*         keys;
+	int*         idx;
+	int          n;
+	double*      partials;                                // [grid][32]
+	IterState*   st;
+	float*       errors;                                  // [max_iter + 1]
+	int          fuse_tail;                               // single GPU: the last block also runs the solve / bookkeeping
+	int          metric;
+};
+
+// ---- error handling -----------------------------------------------------------------------------
+struct Ctx;
+int  fail_cuda(Ctx* c, cudaError_t e, const char* what, const char* file, int line);
+#define ICPB_CUDA(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::icpb::fail_cuda((c), e__, #call, __FILE__, __LINE__); } while (0)
+
+// ---- kernel launchers (defined next to their kernels) -------------------------------------------
+int  k1_max_block_sources();
+int  launch_match_brute(Ctx* c, int dist_mode, float sentinel);
+int  launch_key_reset(Ctx* c);
+int  launch_resolve(Ctx* c, float sentinel);
+int  launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel);
+int  launch_match_grid(Ctx* c, int dist_mode, float sentinel);
+int  launch_moments(Ctx* c, int metric);
+int  launch_solve(Ctx* c, int metric);
+int  launch_transform(Ctx* c);
+int  launch_finish(Ctx* c);
+int  launch_pack_source(Ctx* c, const float* d_xyz, int n);
+int  launch_unpack_source(Ctx* c, float* d_xyz);
+int  launch_pack_target(Ctx* c, const float* d_xyz, int m);
+int  launch_fp32_peak(Ctx* c, float* d_out, int iters, int blocks);
+
+// ---- NCCL (loaded lazily with dlopen; see dist.cpp) ------------------------------------------------
+struct Dist;
+int  dist_unique_id(void* id128);
+int  dist_init(Dist** out, int rank, int world, const void* id128, char* err, size_t errlen);
+int  dist_allreduce_f64(Dist* d, double* dev_buf, int count, cudaStream_t s, char* err, size_t errlen);
+void dist_destroy(Dist* d);
+
+// ---- the context ---------------------------------------------------------------------------------
+struct Ctx {
+	int device = 0, sm_count = 0, sm_clock_khz = 0;
+	char name[64] = {0};
+	cudaStream_t stream = nullptr;
+	char err[512] = {0};
+	long long launches = 0;
+
+	// distributed
+	int rank = 0, world = 1;
+	Dist* dist = nullptr;
+
+	// target
+	int m = 0, nt = 0;
+	float4* q4 = nullptr;        // [m] x,y,z,0
+	float*  qtiles = nullptr;    // [nt][3][K1_TT], padded with +inf
+	float4* nrm4 = nullptr;      // [m] normals
+	int*    nbr = nullptr;       // [m][k+1]
+	int     knn_k = 0;
+	bool    have_normals = false;
+
+	// exact uniform-grid index of the target (ICPB_NN_GRID)
+	bool    grid_ready = false;
+	int*    grid_cell_start = nullptr;
+	float4* grid_sorted4 = nullptr;
+	int     grid_dim[3] = {0, 0, 0};
+	float   grid_origin[3] = {0, 0, 0};
+	float   grid_cell = 0.f;
+
+	// source (this rank's shard)
+	int n = 0, n_cap = 0;        // n_cap: padded capacity
+	float *px = nullptr, *py = nullptr, *pz = nullptr;
+	u64*  keys = nullptr;
+	int*  idx = nullptr;
+	float* dmin = nullptr;       // winning distance per source (icpb_match / icpb_time_match)
+	float* stage_xyz = nullptr;  // device AoS staging for H2D/D2H
+	size_t stage_cap = 0;
+
+	// iteration state
+	IterState* st = nullptr;     // device
+	IterState* st_host = nullptr;// pinned
+	double* partials = nullptr;  // [reduce_grid][32]
+	int reduce_grid = 0;
+	float* errors = nullptr;     // device [err_cap]
+	int err_cap = 0;
+	float* errors_host = nullptr;// pinned
+	bool   step_state_ready = false;
+
+	// K1 configuration
+	int k1_cfg = 0;              // index into the instantiated (S, THREADS) table
+	int k1_grid_override = 0;
+	double pairs_acc = 0;
+
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t* ev_match = nullptr; int ev_match_cap = 0;
+};
+
+} // namespace icpb

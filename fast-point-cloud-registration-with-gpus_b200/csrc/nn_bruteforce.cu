@@ -1,0 +1,365 @@
+// nn_bruteforce.cu — K1: exact brute-force nearest-neighbour matching for sm_100a.
+//
+// Replaces `Matching<<<>>>` of the reference (src/ICP_point_to_point.cu:31-57; sqrt variant
+// src/ICP_point_to_plane.cu:163-181; double pow/sqrt variant src/ICP_standard.cu:21-39) with
+// bit-identical correspondences: idx[i] = argmin_j d(P_i, Q_j), lowest j on ties, nothing written
+// when no distance is below the sentinel.
+//
+// Design:
+//  * FP32-pipe bound by construction: the reference's distance is the rounded chain
+//        dx = xp-xq, dy = yp-yq, dz = zp-zq,  d = fma(dz,dz, fma(dx,dx, dy*dy))
+//    (6 FP32 operations per pair); it is evaluated with the packed sm_100 instructions
+//    FADD2 / FMUL2 / FFMA2 (two targets per instruction, source coordinate broadcast), which are
+//    IEEE-identical per element to the scalar ops but halve the issue slots, leaving room for the
+//    min on the ALU pipe.
+//  * The inner loop keeps ONLY a running minimum per source (one FMNMX3 per two pairs). Which
+//    target produced it is recovered later: after every sub-tile of K1_TRK targets the thread
+//    checks `m < thr` (strict, so an equal distance in a later sub-tile never replaces an earlier
+//    one — the reference's tie rule) and remembers the sub-tile; when a block of sources is done
+//    each thread re-scans its one remembered sub-tile with the same arithmetic to find the first
+//    index that attains the minimum.
+//  * sqrt mode never takes a square root in the inner loop: sqrt.rn is monotone, so the running
+//    compare `sqrt(d) < smin` is done in the squared domain against thr = the smallest float whose
+//    sqrt.rn equals smin (recomputed only when the minimum improves).
+//  * Targets stream through a 3-stage shared-memory ring filled by 1-D TMA bulk copies
+//    (cp.async.bulk + mbarrier); every lane reads the same float4 (broadcast LDS.128).
+//  * Work = (source block x target tile) units, flattened and split evenly over a persistent grid
+//    of (SMs x resident CTAs) blocks (stream-K style), so small clouds still fill 148 SMs; partial
+//    results of CTAs that share a source block are merged with one 64-bit atomicMin per source on
+//    (distance bits << 32 | index), which is exactly "smallest distance, then lowest index".
+#include "common.cuh"
+#include <cmath>
+
+namespace icpb {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 pack2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred P1;\n"
+		"LAB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+		"@P1 bra DONE;\n"
+		"bra LAB_WAIT;\n"
+		"DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// The reference's distance chain, scalar, with the contraction nvcc applies to
+// src/ICP_point_to_point.cu:48-50 spelled out (SASS: FADD, FADD, FMUL dy*dy, FFMA dx, FADD, FFMA dz).
+__device__ __forceinline__ float dist_chain(float xp, float yp, float zp, float xq, float yq, float zq)
+{
+	float dx = __fsub_rn(xp, xq), dy = __fsub_rn(yp, yq), dz = __fsub_rn(zp, zq);
+	return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Smallest float y with sqrt.rn(y) == sqrt.rn(m): comparing squared distances against it is the
+// same as comparing their correctly-rounded square roots with strict `<` against sqrt(m).
+__device__ __forceinline__ float sqrt_class_floor(float m)
+{
+	float s = __fsqrt_rn(m), y = m;
+	for (int k = 0; k < 8; k++) {
+		if (!(y > 0.0f)) break;
+		float yd = __uint_as_float(__float_as_uint(y) - 1u);
+		if (__fsqrt_rn(yd) != s) break;
+		y = yd;
+	}
+	return y;
+}
+template <int MODE> __device__ __forceinline__ float lower_threshold(float m)
+{
+	if (MODE == ICPB_DIST_SQRT) return sqrt_class_floor(m);
+	return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 main kernel
+// ------------------------------------------------------------------------------------------------
+template <int S, int THREADS, int MODE, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
+{
+	constexpr int SB   = S * THREADS;          // sources per block
+	constexpr int SUBS = K1_TT / K1_TRK;       // tracking sub-tiles per tile
+	if (p.done != nullptr && *p.done) return;
+
+	extern __shared__ __align__(128) unsigned char k1_smem[];
+	__shared__ __align__(8) uint64_t full_bar[K1_STAGES];
+	float* ring = reinterpret_cast<float*>(k1_smem);
+
+	const int tid = threadIdx.x;
+	const long long u0 = (p.units * (long long)blockIdx.x) / gridDim.x;
+	const long long u1 = (p.units * (long long)(blockIdx.x + 1)) / gridDim.x;
+	if (u0 >= u1) return;
+
+	if (tid == 0) {
+		for (int s = 0; s < K1_STAGES; s++) mbar_init(&full_bar[s], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+
+	long long next_load = u0;   // producer cursor (thread 0 only)
+	if (tid == 0) {
+		for (int k = 0; k < K1_STAGES - 1 && next_load < u1; k++, next_load++) {
+			const int t = (int)(next_load % p.nt);
+			mbar_expect_tx(&full_bar[k], K1_TILE_BYTES);
+			tma_load_1d(ring + (size_t)k * 3 * K1_TT, p.qtiles + (size_t)t * 3 * K1_TT, K1_TILE_BYTES, &full_bar[k]);
+		}
+	}
+
+	float sx[S], sy[S], sz[S], m[S], thr[S];
+	int best[S];
+	int cur_sb = -1;
+
+	auto flush = [&](int sb) {
+#pragma unroll
+		for (int s = 0; s < S; s++) {
+			const int i = sb * SB + s * THREADS + tid;
+			if (i < p.n && best[s] >= 0) {
+				const float* gx = p.qtiles + (size_t)(best[s] / SUBS) * 3 * K1_TT + (size_t)(best[s] % SUBS) * K1_TRK;
+				const float4* X4 = reinterpret_cast<const float4*>(gx);
+				const float4* Y4 = reinterpret_cast<const float4*>(gx + K1_TT);
+				const float4* Z4 = reinterpret_cast<const float4*>(gx + 2 * K1_TT);
+				const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(thr[s]) : thr[s];
+				int found = -1;
+				for (int j = 0; j < K1_TRK / 4 && found < 0; j++) {
+					const float4 X = __ldg(X4 + j), Y = __ldg(Y4 + j), Z = __ldg(Z4 + j);
+					float d0 = dist_chain(sx[s], sy[s], sz[s], X.x, Y.x, Z.x);
+					float d1 = dist_chain(sx[s], sy[s], sz[s], X.y, Y.y, Z.y);
+					float d2 = dist_chain(sx[s], sy[s], sz[s], X.z, Y.z, Z.z);
+					float d3 = dist_chain(sx[s], sy[s], sz[s], X.w, Y.w, Z.w);
+					if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+					if (d0 <= target) found = 4 * j;
+					else if (d1 <= target) found = 4 * j + 1;
+					else if (d2 <= target) found = 4 * j + 2;
+					else if (d3 <= target) found = 4 * j + 3;
+				}
+				if (found >= 0) {
+					const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(best[s] * K1_TRK + found);
+					atomicMin(p.keys + i, key);
+				}
+			}
+		}
+	};
+
+	for (long long u = u0; u < u1; u++) {
+		const int it    = (int)(u - u0);
+		const int stage = it % K1_STAGES;
+		const uint32_t parity = (uint32_t)((it / K1_STAGES) & 1);
+		const int sb = (int)(u / p.nt);
+		const int t  = (int)(u % p.nt);
+
+		if (sb != cur_sb) {
+			if (cur_sb >= 0) flush(cur_sb);
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				const int i = sb * SB + s * THREADS + tid;
+				sx[s] = p.px[i]; sy[s] = p.py[i]; sz[s] = p.pz[i];
+				m[s] = p.thr0; thr[s] = p.thr0; best[s] = -1;
+			}
+			cur_sb = sb;
+		}
+
+		__syncthreads();   // every thread has finished tile it-1: its ring slot may be refilled
+		if (tid == 0 && next_load < u1) {
+			const int ls = (it + K1_STAGES - 1) % K1_STAGES;
+			const int lt = (int)(next_load % p.nt);
+			mbar_expect_tx(&full_bar[ls], K1_TILE_BYTES);
+			tma_load_1d(ring + (size_t)ls * 3 * K1_TT, p.qtiles + (size_t)lt * 3 * K1_TT, K1_TILE_BYTES, &full_bar[ls]);
+			next_load++;
+		}
+		mbar_wait(&full_bar[stage], parity);
+
+		const float4* X4 = reinterpret_cast<const float4*>(ring + (size_t)stage * 3 * K1_TT);
+		const float4* Y4 = X4 + K1_TT / 4;
+		const float4* Z4 = Y4 + K1_TT / 4;
+
+#pragma unroll 1
+		for (int sub = 0; sub < SUBS; sub++) {
+#pragma unroll 2
+			for (int j = sub * (K1_TRK / 4); j < (sub + 1) * (K1_TRK / 4); j++) {
+				const float4 X = X4[j], Y = Y4[j], Z = Z4[j];
+				const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+				const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+				const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+#pragma unroll
+				for (int s = 0; s < S; s++) {
+					const u64 PX = pack2(sx[s], sx[s]), PY = pack2(sy[s], sy[s]), PZ = pack2(sz[s], sz[s]);
+					u64 dx = sub2(PX, x01), dy = sub2(PY, y01), dz = sub2(PZ, z01);
+					u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+					float a, b;
+					unpack2(d, a, b);
+					m[s] = min3(m[s], a, b);
+					dx = sub2(PX, x23); dy = sub2(PY, y23); dz = sub2(PZ, z23);
+					d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+					unpack2(d, a, b);
+					m[s] = min3(m[s], a, b);
+				}
+			}
+			const int gsub = t * SUBS + sub;
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				if (m[s] < thr[s]) {
+					best[s] = gsub;
+					thr[s]  = lower_threshold<MODE>(m[s]);
+					m[s]    = thr[s];
+				}
+			}
+		}
+	}
+	flush(cur_sb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ICP_standard's formula: float differences, squares/sum/sqrt in double, result cast to float
+// (src/ICP_standard.cu:31). FP64 throughout; only ever used at that program's 1024 points, so a plain
+// one-thread-per-source kernel with shared-memory target tiles is all it needs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k1_match_std(const K1Params p)
+{
+	if (p.done != nullptr && *p.done) return;
+	__shared__ float tx[256], ty[256], tz[256];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = i < p.n;
+	const float xp = valid ? p.px[i] : 0.f, yp = valid ? p.py[i] : 0.f, zp = valid ? p.pz[i] : 0.f;
+	float mn = p.sentinel;
+	int best = -1;
+	for (int t = 0; t < p.nt; t++) {
+		for (int c = 0; c < K1_TT; c += 256) {
+			__syncthreads();
+			for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+				const float* g = p.qtiles + (size_t)t * 3 * K1_TT + c + k;
+				tx[k] = g[0]; ty[k] = g[K1_TT]; tz[k] = g[2 * K1_TT];
+			}
+			__syncthreads();
+			for (int k = 0; k < 256; k++) {
+				const float dx = __fsub_rn(xp, tx[k]), dy = __fsub_rn(yp, ty[k]), dz = __fsub_rn(zp, tz[k]);
+				const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)),
+				                           __dmul_rn((double)dz, (double)dz));
+				const float d = (float)sqrt(s);
+				if (d < mn) { mn = d; best = t * K1_TT + c + k; }
+			}
+		}
+	}
+	if (valid && best >= 0) p.keys[i] = ((u64)__float_as_uint(mn) << 32) | (u64)(uint32_t)best;
+}
+
+__global__ void key_reset_kernel(u64* keys, int n, const int* done)
+{
+	if (done != nullptr && *done) return;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) keys[i] = KEY_UNMATCHED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+struct K1Config { int S, threads, minb; };
+static const K1Config k1_table[] = {
+	{ 8, 256, 2 }, { 8, 512, 1 }, { 4, 256, 3 }, { 4, 512, 1 }, { 16, 256, 1 }, { 8, 128, 4 },
+};
+constexpr int K1_NUM_CFG = (int)(sizeof(k1_table) / sizeof(k1_table[0]));
+
+int k1_max_block_sources()
+{
+	int mx = 0;
+	for (int k = 0; k < K1_NUM_CFG; k++) { int sbs = k1_table[k].S * k1_table[k].threads; if (sbs > mx) mx = sbs; }
+	return mx;
+}
+
+// Smallest float y whose correctly-rounded square root is >= sentinel: `sqrt(d) < sentinel` <=> `d < y`.
+static float sqrt_domain_threshold(float sentinel)
+{
+	if (!(sentinel > 0.0f)) return 0.0f;
+	float y = sentinel * sentinel;
+	if (std::isinf(y)) return y;
+	while (sqrtf(y) < sentinel) y = nextafterf(y, INFINITY);
+	while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
+	return y;
+}
+
+template <int S, int THREADS, int MINB>
+static int launch_cfg(Ctx* c, int mode, const K1Params& base)
+{
+	K1Params p = base;
+	constexpr int SB = S * THREADS;
+	const int nb = (c->n + SB - 1) / SB;
+	p.units = (long long)nb * p.nt;
+	const size_t smem = (size_t)K1_STAGES * K1_TILE_BYTES;
+	auto kern = (mode == ICPB_DIST_SQRT) ? k1_match<S, THREADS, ICPB_DIST_SQRT, MINB> : k1_match<S, THREADS, ICPB_DIST_SQ, MINB>;
+	ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+	if (per_sm < 1) per_sm = 1;
+	long long grid = (long long)c->sm_count * per_sm;
+	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
+	if (grid > p.units) grid = p.units;
+	if (grid < 1) return ICPB_OK;
+	kern<<<(unsigned)grid, THREADS, smem, c->stream>>>(p);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+
+int launch_key_reset(Ctx* c)
+{
+	if (c->n <= 0) return ICPB_OK;
+	key_reset_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->keys, c->n, nullptr);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+
+int launch_match_brute(Ctx* c, int dist_mode, float sentinel)
+{
+	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
+	K1Params p;
+	p.px = c->px; p.py = c->py; p.pz = c->pz;
+	p.qtiles = c->qtiles; p.keys = c->keys;
+	p.n = c->n; p.nt = c->nt; p.units = 0;
+	p.sentinel = sentinel;
+	p.thr0 = (dist_mode == ICPB_DIST_SQRT) ? sqrt_domain_threshold(sentinel) : sentinel;
+	p.done = &c->st->done;
+	c->pairs_acc += (double)c->n * (double)c->m;
+	if (dist_mode == ICPB_DIST_STD) {
+		k1_match_std<<<(c->n + 127) / 128, 128, 0, c->stream>>>(p);
+		c->launches++;
+		ICPB_CUDA(c, cudaGetLastError());
+		return ICPB_OK;
+	}
+	switch (c->k1_cfg) {
+	default:
+	case 0: return launch_cfg<8, 256, 2>(c, dist_mode, p);
+	case 1: return launch_cfg<8, 512, 1>(c, dist_mode, p);
+	case 2: return launch_cfg<4, 256, 3>(c, dist_mode, p);
+	case 3: return launch_cfg<4, 512, 1>(c, dist_mode, p);
+	case 4: return launch_cfg<16, 256, 1>(c, dist_mode, p);
+	case 5: return launch_cfg<8, 128, 4>(c, dist_mode, p);
+	}
+}
+
+} // namespace icpb

@@ -1,0 +1,18 @@
+// pending.cu — entry points whose kernels land later in round 1 (normals, grid NN, batched).
+#include "common.cuh"
+namespace icpb {
+int launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel)
+{
+	if (nn_method == ICPB_NN_GRID) return launch_match_grid(c, dist_mode, sentinel);
+	return launch_match_brute(c, dist_mode, sentinel);
+}
+int launch_match_grid(Ctx* c, int, float) { snprintf(c->err, sizeof c->err, "ICPB_NN_GRID: not built yet"); return ICPB_ERR_STATE; }
+}
+using namespace icpb;
+extern "C" {
+int icpb_estimate_normals(icpb_ctx* ctx, int, float*) { if (!ctx) return ICPB_ERR_BADARG; snprintf(reinterpret_cast<Ctx*>(ctx)->err, 512, "icpb_estimate_normals: not built yet"); return ICPB_ERR_STATE; }
+int icpb_get_neighbors(icpb_ctx* ctx, int*, int) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
+int icpb_get_normals(icpb_ctx* ctx, float*, int) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
+int icpb_set_normals(icpb_ctx* ctx, const float*, int) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
+int icpb_run_batched(icpb_ctx* ctx, const icpb_params*, int, const float*, int, const float*, int, float*, int*, double*, double*, float*) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
+}

@@ -1,0 +1,161 @@
+/* icp_b200.h — C ABI of the B200-native ICP registration engine (libicp_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of
+ * Carlos310197/Fast-Point-Cloud-Registration-with-GPUs. The reference has no library API: its
+ * hot path is the body of `while (iteration < MAX_ITER)` in three single-file programs. Each entry
+ * point below names the reference code it replaces (paths relative to the reference repository).
+ *
+ * Conventions kept from the reference
+ *   - clouds are AoS float xyzxyz... (a column-major 3xN matrix, ld = 3)  src/ICP_point_to_point.cu:142-152
+ *   - R is column-major, R[row + 3*col]                                    src/ICP_point_to_point.cu:85-87
+ *   - the error array has slot 0 = 0 and iteration k writes slot k+1       src/ICP_point_to_point.cu:416
+ *   - matching scans targets in ascending order and updates on strict `<`: the LOWEST index wins
+ *     ties; the running minimum starts at `sentinel` (100000) and a source whose every distance is
+ *     >= sentinel keeps its previous correspondence                        src/ICP_point_to_point.cu:36,51-55
+ *
+ * Plain C: pointers and sizes only. All functions return ICPB_OK (0) or a negative ICPB_ERR_*;
+ * they never print. One host thread drives one context; calls are synchronous at return.
+ * There is NO CPU fallback: every entry point needs a CUDA device of compute capability 10.0.
+ */
+#ifndef ICP_B200_H
+#define ICP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICPB_VERSION 100
+
+#define ICPB_OK            0
+#define ICPB_ERR_CUDA     -1   /* a CUDA runtime call or kernel failed (see icpb_last_error) */
+#define ICPB_ERR_BADARG   -2
+#define ICPB_ERR_NCCL     -3
+#define ICPB_ERR_STATE    -4   /* e.g. icpb_run before icpb_set_target, normals missing for point-to-plane */
+#define ICPB_ERR_NOMEM    -5
+#define ICPB_ERR_NUMERIC  -6   /* 6x6 system not positive definite (cusolver's devInfo > 0 in the reference) */
+#define ICPB_ERR_NODEVICE -7
+
+/* Distance formula of the matching step — one per reference executable (SURVEY.md §7 hard part 2). */
+#define ICPB_DIST_SQ    0   /* d = dx*dx + dy*dy + dz*dz, fused as nvcc fuses it     src/ICP_point_to_point.cu:48-50 */
+#define ICPB_DIST_SQRT  1   /* (float)sqrt of the same chain                         src/ICP_point_to_plane.cu:172-174 */
+#define ICPB_DIST_STD   2   /* (float)sqrt(pow(dx,2)+pow(dy,2)+pow(dz,2)) in double  src/ICP_standard.cu:31 */
+
+#define ICPB_POINT_TO_POINT 0   /* centroids, 3x3 cross-covariance, SVD, R = U*V^T   src/ICP_point_to_point.cu:313-398 */
+#define ICPB_POINT_TO_PLANE 1   /* 6x6 normal equations, Cholesky, Euler -> R        src/ICP_point_to_plane.cu:537-601 */
+
+#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method) */
+#define ICPB_NN_GRID  1         /* exact uniform-grid search, identical indices */
+
+typedef struct icpb_ctx icpb_ctx;
+
+typedef struct icpb_params {
+	int    metric;       /* ICPB_POINT_TO_POINT | ICPB_POINT_TO_PLANE */
+	int    dist_mode;    /* ICPB_DIST_* */
+	int    nn_method;    /* ICPB_NN_* */
+	int    max_iter;     /* MAX_ITER: 40 (src/ICP_point_to_point.cu:24), 50 (ICP_point_to_plane.cu:23) */
+	int    stop_early;   /* 1: break when e < tol or |e_k+1 - e_k| < tol (src/ICP_point_to_point.cu:420-421);
+	                        0: always run max_iter iterations (src/ICP_standard.cu:369) */
+	int    sync_every;   /* iterations enqueued between host reads of the device-side stop flag (>=1) */
+	float  sentinel;     /* 100000 (src/ICP_point_to_point.cu:36); 1e6 in the LiDAR programs */
+	double tol;          /* 0.000001 (GPU programs), 0.00001 (src/ICP_CPU.c:267) */
+} icpb_params;
+
+typedef struct icpb_result {
+	int    iterations;      /* the reference's `iteration` counter when its loop exits */
+	int    iterations_run;  /* loop bodies executed (= iterations + 1 after a break) */
+	double R[9];            /* accumulated rotation, column-major: R_tot <- R_k * R_tot */
+	double t[3];            /* accumulated translation:           t_tot <- R_k * t_tot + T_k */
+	float  last_R[9];       /* transform of the last iteration (d_temp_r / d_temp_T) */
+	float  last_T[3];
+	float  elapsed_ms;      /* cudaEvent time around the loop, as src/ICP_point_to_point.cu:294,424-426 */
+	float  match_ms;        /* part of elapsed_ms spent in the matching kernels */
+	double nn_pairs;        /* source x target pairs evaluated by brute-force matching (this rank) */
+} icpb_result;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         icpb_version(void);
+const char* icpb_status_string(int status);
+void        icpb_default_params(icpb_params* p);   /* the constants of src/ICP_point_to_point.cu */
+int         icpb_device_count(int* count);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Replaces the cudaMalloc / cublasCreate / cusolverDnCreate block of each main
+ * (src/ICP_point_to_point.cu:203-285). All device memory is owned by the context and allocated
+ * once per cloud size — nothing is allocated inside the loop (cf. src/ICP_point_to_plane.cu:577). */
+int  icpb_create(icpb_ctx** out, int device);
+/* Multi-GPU: one context per process/GPU. Source points are sharded (each rank passes its own
+ * shard to icpb_set_source), the target is replicated, and the per-iteration moment partials are
+ * combined with ncclAllReduce. `nccl_unique_id` is the 128-byte ncclUniqueId made by rank 0 with
+ * icpb_nccl_unique_id and handed to every rank by the caller (MPI, torch.distributed, a file...). */
+int  icpb_nccl_unique_id(void* id128);
+int  icpb_create_dist(icpb_ctx** out, int device, int rank, int world, const void* nccl_unique_id);
+int  icpb_destroy(icpb_ctx* ctx);
+const char* icpb_last_error(const icpb_ctx* ctx);
+int  icpb_device_info(const icpb_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name64);
+
+/* ---- clouds ------------------------------------------------------------------------------- */
+/* `xyz` is AoS float[3*count]; `on_device` != 0 means it already is a device pointer on the
+ * context's GPU. Replaces the cudaMemcpy H2D of src/ICP_point_to_point.cu:207-208. The target is
+ * re-tiled once here (it never moves during a registration). */
+int  icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device);
+int  icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device);
+int  icpb_get_source(icpb_ctx* ctx, float* xyz, int on_device);          /* current (transformed) source */
+int  icpb_get_correspondences(icpb_ctx* ctx, int* idx, int on_device);   /* d_idx */
+int  icpb_get_min_distances(icpb_ctx* ctx, float* d, int on_device);     /* the winning distance per source, in dist_mode units */
+
+/* ---- the steps of one iteration ------------------------------------------------------------ */
+/* Matching — `Matching<<<>>>` (src/ICP_point_to_point.cu:31-57,298; variants src/ICP_standard.cu:21-39,
+ * src/ICP_point_to_plane.cu:163-181). Exact; bit-identical indices. */
+int  icpb_match(icpb_ctx* ctx, int dist_mode, int nn_method, float sentinel);
+/* Minimisation — Q_index + cublasSgemv x2 + deviation + cublasSgemm + cusolverDnSgesvd + 2 cublasSgemm
+ * (src/ICP_point_to_point.cu:308-397) or Cxb + cublasSgemv x2 + Spotrf/Spotrs + Euler
+ * (src/ICP_point_to_plane.cu:532-601). Outputs this iteration's R (column-major) and T. */
+int  icpb_minimize(icpb_ctx* ctx, int metric, float R[9], float T[3]);
+/* Transformation + error — RyT + cublasScopy + Scopy/Saxpy/Snrm2 (src/ICP_point_to_point.cu:403-416).
+ * Applies the R,T of the last icpb_minimize; returns the RMS  ||P' - Q_idx|| / sqrt(N). */
+int  icpb_transform(icpb_ctx* ctx, float* rms);
+/* Moments of the last icpb_minimize (after the allreduce when distributed): 16 doubles for
+ * point-to-point {sum p (3), sum q (3), sum q p^T (9, column-major, rows = q), N},
+ * 28 for point-to-plane {upper triangle of C row by row (21), b (6), N}. */
+int  icpb_get_moments(icpb_ctx* ctx, double* mom, int count);
+
+/* ---- normals (point-to-plane) --------------------------------------------------------------- */
+/* knn<<<>>> + Normals<<<>>> + host LAPACKE_ssyev/cblas_isamin (src/ICP_point_to_plane.cu:378-447)
+ * on the target: exact k+1 nearest (self first, lowest index first on ties, over sqrt'ed float
+ * distances), PCA normal = eigenvector of the eigenvalue of smallest magnitude. No MxM matrix. */
+int  icpb_estimate_normals(icpb_ctx* ctx, int k, float* elapsed_ms);
+int  icpb_get_neighbors(icpb_ctx* ctx, int* nbr /* m*(k+1), row-major */, int on_device);
+int  icpb_get_normals(icpb_ctx* ctx, float* normals /* 3*m AoS */, int on_device);
+int  icpb_set_normals(icpb_ctx* ctx, const float* normals, int on_device);
+
+/* ---- whole loop ------------------------------------------------------------------------------ */
+/* The `while (iteration < MAX_ITER)` loop of src/ICP_point_to_point.cu:295-423,
+ * src/ICP_standard.cu:369-463 (stop_early = 0, dist_mode = STD) and src/ICP_point_to_plane.cu:517-631,
+ * entirely on the device; `errors` receives max_iter+1 floats (slot 0 = 0). */
+int  icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_result* result);
+/* One iteration from HOST buffers: uploads both clouds, matches, minimises, transforms, downloads
+ * the correspondences and the transform. The end-to-end entry point bench.py times. */
+int  icpb_iterate_host(icpb_ctx* ctx, const icpb_params* params, const float* source_xyz, int n,
+                       const float* target_xyz, int m, int* idx_out, float R[9], float T[3], float* rms);
+
+/* ---- batched registration (BASELINE.json config 5) ------------------------------------------- */
+/* `batch` independent registrations, one per thread-block cluster, whole loop in one kernel.
+ * sources: batch*n*3 floats, targets: batch*m*3 floats (host). errors: batch*(max_iter+1);
+ * iterations: batch; R: batch*9 (accumulated, column-major, double); t: batch*3. */
+int  icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int batch, const float* sources, int n,
+                      const float* targets, int m, float* errors, int* iterations, double* R, double* t,
+                      float* elapsed_ms);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+/* Register-resident FFMA loop on every SM: the measured FP32 roofline denominator (TFLOP/s). */
+int  icpb_measure_fp32_peak(icpb_ctx* ctx, double* tflops);
+/* Times `reps` launches of the matching step alone with CUDA events on the context's stream
+ * (the protocol of src/CUDA/Matching_opt.cu:213-226); returns the mean and the minimum in ms. */
+int  icpb_time_match(icpb_ctx* ctx, int dist_mode, int nn_method, float sentinel, int reps, float* mean_ms, float* min_ms);
+/* Number of kernels this context has launched since creation. */
+long long icpb_launch_count(const icpb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICP_B200_H */

@@ -1,0 +1,573 @@
+/* =====================================================================================
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * CPU restatement ("oracle") of the reference ICP hot path of
+ * Carlos310197/Fast-Point-Cloud-Registration-with-GPUs. Plain C, no GPU, no third-party
+ * library. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this file; the product (libicp_b200.so) never does.
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * /root/reference/). Build with  -O2 -ffp-contract=off  (see oracle/Makefile): all fused
+ * multiply-adds are spelled fmaf()/fma() explicitly, in the order the reference's kernels
+ * execute them when compiled by nvcc 12.9 with its default -fmad=true (SASS inspected,
+ * see DESIGN.md "Arithmetic contract").
+ *
+ * Pinning status:
+ *   - orc_icp_cpu_f64 is pinned against the stdout of the UNMODIFIED reference
+ *     src/ICP_CPU.c built into oracle/_ref/icp_cpu (tests/golden/icp_cpu_stdout.txt).
+ *   - orc_match_f32 / orc_transform_f32 / orc_knn_f32 / orc_cxb are pinned against the
+ *     reference's own CUDA kernels compiled from /root/reference into
+ *     oracle/_ref/ref_kernels (fixtures in tests/golden/, produced on a B200).
+ *   - Library arithmetic the reference delegates to Intel MKL / cuBLAS / cuSOLVER
+ *     (gesvd, potrf/potrs, ssyev, gemm/gemv summation order) has no golden vector in the
+ *     reference: PARITY UNPINNED beyond the 1e-5 tolerance the north star states; the
+ *     restatement uses the mathematically intended operation in double precision.
+ * ===================================================================================== */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+enum { ORC_MODE_SQ = 0, ORC_MODE_SQRT = 1, ORC_MODE_STD = 2 };
+
+ORC_API int orc_num_threads(void)
+{
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic data
+ * ---------------------------------------------------------------------------------- */
+
+/* Naive column-major GEMM of src/my_lib.cpp:80-93 (SmatrixMul), float, left to right, no FMA. */
+static void orc_smatmul(const float* A, const float* B, float* C, int m, int n, int k)
+{
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < m; j++) {
+			float temp = 0.0f;
+			for (int q = 0; q < k; q++) temp += A[j + q * m] * B[q + i * k];
+			C[j + (size_t)i * m] = temp;
+		}
+}
+
+/* Source cloud of src/ICP_point_to_point.cu:103-152 (identical in ICP_point_to_plane.cu:258-307):
+ * all-float lin_space (:109), point index = k*W + j with x = lin[k] (slow), y = lin[j] (fast)
+ * (:118-130), z = (float)(pow((double)x,2) - pow((double)y,2)) (:136). `npts` <= width*width
+ * keeps the first npts points in generation order ("100k = first 100 000 points
+ * of the WIDTH=317 grid"). AoS xyzxyz... */
+ORC_API void orc_synth_source_f32(int width, int npts, float* D)
+{
+	float lenght = (float)(2.0 - (-2.0));
+	float* lin = (float*)malloc(sizeof(float) * (size_t)width);
+	for (int i = 0; i < width; i++) lin[i] = (float)-2.0 + ((float)i * (float)lenght) / ((float)width - 1.0f);
+	for (int i = 0; i < npts; i++) {
+		float x = lin[i / width], y = lin[i % width];
+		D[3 * (size_t)i + 0] = x;
+		D[3 * (size_t)i + 1] = y;
+		D[3 * (size_t)i + 2] = (float)(pow((double)x, 2) - pow((double)y, 2));
+	}
+	free(lin);
+}
+
+/* Rotation of src/ICP_point_to_point.cu:167-172 from Euler angles ri (column-major 3x3). */
+ORC_API void orc_euler_matrix_f32(const float ri[3], float h_r[9])
+{
+	float cx = (float)cos(ri[0]), cy = (float)cos(ri[1]), cz = (float)cos(ri[2]);
+	float sx = (float)sin(ri[0]), sy = (float)sin(ri[1]), sz = (float)sin(ri[2]);
+	h_r[0] = cy * cz; h_r[1] = (cz * sx * sy) + (cx * sz); h_r[2] = -(cx * cz * sy) + (sx * sz);
+	h_r[3] = -cy * sz; h_r[4] = (cx * cz) - (sx * sy * sz); h_r[5] = (cx * sy * sz) + (cz * sx);
+	h_r[6] = sy; h_r[7] = -cy * sx; h_r[8] = cx * cy;
+}
+
+/* Target cloud M = h_r * D + t of src/ICP_point_to_point.cu:176-190. */
+ORC_API void orc_rigid_move_f32(const float* D, int npts, const float h_r[9], const float ti[3], float* M)
+{
+	orc_smatmul(h_r, D, M, 3, npts, 3);
+	for (int i = 0; i < npts; i++)
+		for (int j = 0; j < 3; j++) M[j + 3 * (size_t)i] += ti[j];
+}
+
+/* The default pose of ICP_point_to_point.cu / ICP_point_to_plane.cu (:157-165 / :312-320). */
+ORC_API void orc_synth_p2p_f32(int width, int npts, float* D, float* M)
+{
+	float ti[3] = { 0.8f, -0.3f, 0.2f }, ri[3] = { 0.2f, -0.2f, 0.05f }, h_r[9];
+	orc_synth_source_f32(width, npts, D);
+	orc_euler_matrix_f32(ri, h_r);
+	orc_rigid_move_f32(D, npts, h_r, ti, M);
+}
+
+/* src/ICP_standard.cu:160-263: lin_space is a double expression rounded to float (:164),
+ * rotation is the hard-coded 9 floats of :247-249, t = (1,-0.3,0.2) (:211-213). */
+ORC_API void orc_synth_standard_f32(int width, float* D, float* M)
+{
+	float lenght = (float)(2.0 - (-2.0));
+	int n = width, npts = width * width;
+	float* lin = (float*)malloc(sizeof(float) * (size_t)width);
+	for (int i = 0; i < width; i++) lin[i] = (float)(-2.0 + (double)((float)i * lenght / ((float)n - 1.0f)));
+	for (int i = 0; i < npts; i++) {
+		float x = lin[i / width], y = lin[i % width];
+		D[3 * (size_t)i + 0] = x;
+		D[3 * (size_t)i + 1] = y;
+		D[3 * (size_t)i + 2] = (float)(pow((double)x, 2) - pow((double)y, 2));
+	}
+	free(lin);
+	float h_r[9] = { 0.876485812f, -0.37591464f, 0.300767018f,
+	                 -0.04386084f, 0.559789799f, 0.827473024f,
+	                 -0.47942553f, -0.73846026f, 0.474159881f };
+	float ti[3] = { 1.0f, -0.3f, 0.2f };
+	orc_rigid_move_f32(D, npts, h_r, ti, M);
+}
+
+/* src/ICP_CPU.c:51-149: double precision, SoA (x... y... z...), transposed-sign elementary
+ * rotations (:110-126), r = rx*ry*rz (:132-133, intended product), M = r*D + t (:141-149). */
+ORC_API void orc_synth_cpu_f64(int width, double* D, double* M)
+{
+	int n = width, npts = width * width;
+	double lenght = 2.0 - (-2.0);
+	double* lin = (double*)malloc(sizeof(double) * (size_t)width);
+	for (int i = 0; i < width; i++) lin[i] = -2.0 + (double)i * lenght / ((double)n - 1.0);
+	for (int i = 0; i < npts; i++) {
+		double x = lin[i / width], y = lin[i % width];
+		D[i] = x; D[npts + i] = y; D[2 * (size_t)npts + i] = pow(x, 2) - pow(y, 2);
+	}
+	free(lin);
+	double ti[3] = { 1.0, -0.3, 0.2 }, ri[3] = { 1, -0.5, 0.05 };
+	double rx[3][3] = { { 1, 0, 0 }, { 0, cos(ri[0]), sin(ri[0]) }, { 0, -sin(ri[0]), cos(ri[0]) } };
+	double ry[3][3] = { { cos(ri[1]), 0, -sin(ri[1]) }, { 0, 1, 0 }, { sin(ri[1]), 0, cos(ri[1]) } };
+	double rz[3][3] = { { cos(ri[2]), sin(ri[2]), 0 }, { -sin(ri[2]), cos(ri[2]), 0 }, { 0, 0, 1 } };
+	double t1[3][3], r[3][3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double a = 0; for (int q = 0; q < 3; q++) a += rx[i][q] * ry[q][j]; t1[i][j] = a; }
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double a = 0; for (int q = 0; q < 3; q++) a += t1[i][q] * rz[q][j]; r[i][j] = a; }
+	for (int i = 0; i < 3; i++)
+		for (int p = 0; p < npts; p++) {
+			double a = 0; for (int q = 0; q < 3; q++) a += r[i][q] * D[(size_t)q * npts + p];
+			M[(size_t)i * npts + p] = a + ti[i];
+		}
+}
+
+/* ------------------------------------------------------------------------------------
+ * Matching
+ * ---------------------------------------------------------------------------------- */
+
+/* One distance, exactly as each reference kernel evaluates it on the GPU:
+ *  SQ   src/ICP_point_to_point.cu:48-50   fma(dz,dz, fma(dx,dx, dy*dy))        (SASS: FADD x3, FMUL dy, FFMA dx, FFMA dz)
+ *  SQRT src/ICP_point_to_plane.cu:172-174 sqrt.rn.f32 of the same chain
+ *  STD  src/ICP_standard.cu:31            (float)sqrt(pow(dx,2)+pow(dy,2)+pow(dz,2)) in double, dx.. float differences
+ *       (pow(x,2.0) of a float-valued double is exact: 48 significand bits). */
+static inline float orc_dist(int mode, float xp, float yp, float zp, float xq, float yq, float zq)
+{
+	float dx = xp - xq, dy = yp - yq, dz = zp - zq;
+	if (mode == ORC_MODE_STD) {
+		double s = (double)dx * (double)dx + (double)dy * (double)dy + (double)dz * (double)dz;
+		return (float)sqrt(s);
+	}
+	float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+	return (mode == ORC_MODE_SQRT) ? sqrtf(d) : d;
+}
+
+/* Brute-force nearest neighbour: `Matching`, src/ICP_point_to_point.cu:31-57 (and the two
+ * variants above). j ascending, update on strict `<`, so the LOWEST index wins ties; running
+ * minimum starts at `sentinel` (100000, :36); idx[i] is left untouched when nothing beats it.
+ * P, Q are AoS xyz. */
+ORC_API void orc_match_f32(const float* P, int n, const float* Q, int m, int mode, float sentinel, int* idx)
+{
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; i++) {
+		float xp = P[3 * (size_t)i], yp = P[3 * (size_t)i + 1], zp = P[3 * (size_t)i + 2];
+		float min = sentinel; int best = -1;
+		for (int j = 0; j < m; j++) {
+			float d = orc_dist(mode, xp, yp, zp, Q[3 * (size_t)j], Q[3 * (size_t)j + 1], Q[3 * (size_t)j + 2]);
+			if (d < min) { min = d; best = j; }
+		}
+		if (best >= 0) idx[i] = best;
+	}
+}
+
+/* Same, restricted to sources [i0,i1): the bounded sample bench.py times. */
+ORC_API void orc_match_slice_f32(const float* P, int i0, int i1, const float* Q, int m, int mode, float sentinel, int* idx)
+{
+	orc_match_f32(P + 3 * (size_t)i0, i1 - i0, Q, m, mode, sentinel, idx + i0);
+}
+
+/* CPU twin, src/ICP_CPU.c:220-234: double, SoA; vdSub / vdSqr / vdAdd round separately
+ * (q - p, squares, (x2 + y2) + z2), cblas_idamin = first index of the minimum. */
+ORC_API void orc_match_cpu_f64(const double* pt, int n, const double* q, int m, int* idx)
+{
+#pragma omp parallel for schedule(static)
+	for (int j = 0; j < n; j++) {
+		double px = pt[j], py = pt[(size_t)n + j], pz = pt[2 * (size_t)n + j];
+		double best = INFINITY; int bi = 0;
+		for (int c = 0; c < m; c++) {
+			double dx = q[c] - px, dy = q[(size_t)m + c] - py, dz = q[2 * (size_t)m + c] - pz;
+			double d = (dx * dx + dy * dy) + dz * dz;
+			if (fabs(d) < best) { best = fabs(d); bi = c; }
+		}
+		idx[j] = bi;
+	}
+}
+
+/* ------------------------------------------------------------------------------------
+ * 3x3 SVD / polar factor, 6x6 Cholesky, symmetric 3x3 eigen (double, Jacobi)
+ * ---------------------------------------------------------------------------------- */
+
+/* One-sided Jacobi SVD of a column-major 3x3 W; returns R = U*V^T column-major — what
+ * cusolverDnSgesvd + cublasSgemm(U,VT) (src/ICP_point_to_point.cu:369-381) and
+ * LAPACKE_dgesvd + cblas_dgemm (src/ICP_CPU.c:240-246) compute. No reflection fix (:379-381). */
+ORC_API void orc_polar_rotation(const double W[9], double R[9])
+{
+	double a[3][3], v[3][3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { a[i][j] = W[i + 3 * j]; v[i][j] = (i == j); }
+	for (int sweep = 0; sweep < 60; sweep++) {
+		double off = 0.0;
+		for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+			double alpha = 0, beta = 0, gamma = 0;
+			for (int i = 0; i < 3; i++) { alpha += a[i][p] * a[i][p]; beta += a[i][q] * a[i][q]; gamma += a[i][p] * a[i][q]; }
+			if (gamma == 0.0) continue;
+			double lim = fabs(gamma) / sqrt(alpha * beta);
+			if (lim > off) off = lim;
+			if (lim < 1e-17) continue;
+			double zeta = (beta - alpha) / (2.0 * gamma);
+			double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+			double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+			for (int i = 0; i < 3; i++) {
+				double x = a[i][p], y = a[i][q]; a[i][p] = c * x - s * y; a[i][q] = s * x + c * y;
+				x = v[i][p]; y = v[i][q]; v[i][p] = c * x - s * y; v[i][q] = s * x + c * y;
+			}
+		}
+		if (off < 1e-16) break;
+	}
+	double u[3][3], sv[3];
+	for (int j = 0; j < 3; j++) {
+		sv[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
+		for (int i = 0; i < 3; i++) u[i][j] = (sv[j] > 0) ? a[i][j] / sv[j] : 0.0;
+	}
+	/* rank-2 input: complete the missing left vector (sign convention: right-handed with the
+	 * other two; the reference's libraries leave this case to their own convention) */
+	int small = 0; for (int j = 1; j < 3; j++) if (sv[j] < sv[small]) small = j;
+	double big = fmax(sv[0], fmax(sv[1], sv[2]));
+	if (sv[small] <= 1e-14 * big) {
+		int j1 = (small + 1) % 3, j2 = (small + 2) % 3;
+		u[0][small] = u[1][j1] * u[2][j2] - u[2][j1] * u[1][j2];
+		u[1][small] = u[2][j1] * u[0][j2] - u[0][j1] * u[2][j2];
+		u[2][small] = u[0][j1] * u[1][j2] - u[1][j1] * u[0][j2];
+	}
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		double acc = 0; for (int q = 0; q < 3; q++) acc += u[i][q] * v[j][q];
+		R[i + 3 * j] = acc;
+	}
+}
+
+/* Cyclic Jacobi for a symmetric 3x3 (row-major full), eigenvalues ascending, eigenvectors in
+ * columns of V (row-major) — the operation of LAPACKE_ssyev(ROW_MAJOR,'V','U',3)
+ * (src/ICP_point_to_plane.cu:435). */
+static void orc_eig3(const double A[9], double w[3], double V[9])
+{
+	double a[3][3], v[3][3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { a[i][j] = A[3 * i + j]; v[i][j] = (i == j); }
+	for (int sweep = 0; sweep < 60; sweep++) {
+		double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+		double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+		if (off <= 1e-18 * diag || off == 0.0) break;
+		for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+			if (a[p][q] == 0.0) continue;
+			double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+			double t = ((theta >= 0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(1.0 + theta * theta));
+			double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+			for (int k = 0; k < 3; k++) { double x = a[k][p], y = a[k][q]; a[k][p] = c * x - s * y; a[k][q] = s * x + c * y; }
+			for (int k = 0; k < 3; k++) { double x = a[p][k], y = a[q][k]; a[p][k] = c * x - s * y; a[q][k] = s * x + c * y; }
+			for (int k = 0; k < 3; k++) { double x = v[k][p], y = v[k][q]; v[k][p] = c * x - s * y; v[k][q] = s * x + c * y; }
+		}
+	}
+	int ord[3] = { 0, 1, 2 };
+	for (int i = 0; i < 2; i++) for (int j = i + 1; j < 3; j++) if (a[ord[j]][ord[j]] < a[ord[i]][ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+	for (int jj = 0; jj < 3; jj++) { w[jj] = a[ord[jj]][ord[jj]]; for (int i = 0; i < 3; i++) V[3 * i + jj] = v[i][ord[jj]]; }
+}
+
+/* Solve the SPD system C x = b (C column-major 6x6, only the UPPER triangle is read), the
+ * operation of cusolverDnSpotrf/Spotrs(UPPER, n=6) at src/ICP_point_to_plane.cu:576-581.
+ * Returns 0, or k>0 if the leading minor k is not positive (potrf's devInfo). */
+ORC_API int orc_solve6_spd(const double C[36], const double b[6], double x[6])
+{
+	double U[6][6]; memset(U, 0, sizeof U);
+	for (int j = 0; j < 6; j++) {
+		double s = C[j + 6 * j];
+		for (int k = 0; k < j; k++) s -= U[k][j] * U[k][j];
+		if (!(s > 0.0)) return j + 1;
+		U[j][j] = sqrt(s);
+		for (int i = j + 1; i < 6; i++) {
+			double t = C[j + 6 * i];
+			for (int k = 0; k < j; k++) t -= U[k][j] * U[k][i];
+			U[j][i] = t / U[j][j];
+		}
+	}
+	double y[6];
+	for (int i = 0; i < 6; i++) { double t = b[i]; for (int k = 0; k < i; k++) t -= U[k][i] * y[k]; y[i] = t / U[i][i]; }
+	for (int i = 5; i >= 0; i--) { double t = y[i]; for (int k = i + 1; k < 6; k++) t -= U[i][k] * x[k]; x[i] = t / U[i][i]; }
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Point-to-point minimisation, transform, error, GPU-path layout (AoS f32)
+ * ---------------------------------------------------------------------------------- */
+
+/* Raw moments over the correspondences, accumulated in double:
+ *   mom[0..2] = sum p, mom[3..5] = sum q_idx, mom[6..14] = sum q_idx p^T (column-major, rows = q,
+ *   cols = p: mom[6 + r + 3c] = sum q_r p_c), mom[15] = count.
+ * Restates Q_index + cublasSgemv x2 + deviation + cublasSgemm of src/ICP_point_to_point.cu:308-357
+ * up to the (unpinned) summation order of cuBLAS. */
+ORC_API void orc_moments(const float* P, const float* Q, const int* idx, int n, double mom[16])
+{
+	for (int k = 0; k < 16; k++) mom[k] = 0.0;
+	for (int i = 0; i < n; i++) {
+		const float* p = P + 3 * (size_t)i; const float* q = Q + 3 * (size_t)idx[i];
+		for (int c = 0; c < 3; c++) { mom[c] += p[c]; mom[3 + c] += q[c]; }
+		for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) mom[6 + r + 3 * c] += (double)q[r] * (double)p[c];
+	}
+	mom[15] = (double)n;
+}
+
+/* Centroids, W = sum (q-qbar)(p-pbar)^T = sum q p^T - N qbar pbar^T, R = U V^T, T = qbar - R pbar
+ * (src/ICP_point_to_point.cu:316-397; src/ICP_CPU.c:237-248). R column-major. */
+ORC_API void orc_rt_from_moments(const double mom[16], double R[9], double T[3])
+{
+	double N = mom[15], pb[3], qb[3], W[9];
+	for (int c = 0; c < 3; c++) { pb[c] = mom[c] / N; qb[c] = mom[3 + c] / N; }
+	for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) W[r + 3 * c] = mom[6 + r + 3 * c] - N * qb[r] * pb[c];
+	orc_polar_rotation(W, R);
+	for (int r = 0; r < 3; r++) T[r] = qb[r] - (R[r] * pb[0] + R[r + 3] * pb[1] + R[r + 6] * pb[2]);
+}
+
+/* `RyT`, src/ICP_point_to_point.cu:81-88, in the arithmetic nvcc gives it:
+ *   out_r = ( fma(R[r+6], z, fma(R[r], x, R[r+3]*y)) ) + T[r]        (SASS: FMUL, FFMA, FFMA, FADD)
+ * followed by the copy back into P (:407). In place. */
+ORC_API void orc_transform_f32(float* P, int n, const float R[9], const float T[3])
+{
+	for (int i = 0; i < n; i++) {
+		float x = P[3 * (size_t)i], y = P[3 * (size_t)i + 1], z = P[3 * (size_t)i + 2];
+		for (int r = 0; r < 3; r++) P[3 * (size_t)i + r] = fmaf(R[r + 6], z, fmaf(R[r], x, R[r + 3] * y)) + T[r];
+	}
+}
+
+/* RMS of src/ICP_point_to_point.cu:412-416: || P - Q_idx ||_2 / sqrt(N), differences in float
+ * (cublasSaxpy), norm accumulated in double here (cublasSnrm2's order is unpinned). */
+ORC_API double orc_rms(const float* P, const float* Q, const int* idx, int n)
+{
+	double acc = 0.0;
+	for (int i = 0; i < n; i++)
+		for (int c = 0; c < 3; c++) { float d = P[3 * (size_t)i + c] - Q[3 * (size_t)idx[i] + c]; acc += (double)d * (double)d; }
+	return sqrt(acc) / sqrt((double)n);
+}
+
+static void orc_compose(double Rt[9], double tt[3], const double R[9], const double T[3])
+{
+	/* R_tot <- R * R_tot ; t_tot <- R * t_tot + T   (SURVEY.md §8b "Conventions to preserve") */
+	double Rn[9], tn[3];
+	for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) { double a = 0; for (int q = 0; q < 3; q++) a += R[r + 3 * q] * Rt[q + 3 * c]; Rn[r + 3 * c] = a; }
+	for (int r = 0; r < 3; r++) tn[r] = R[r] * tt[0] + R[r + 3] * tt[1] + R[r + 6] * tt[2] + T[r];
+	memcpy(Rt, Rn, sizeof Rn); memcpy(tt, tn, sizeof tn);
+}
+
+/* Whole point-to-point loop, src/ICP_point_to_point.cu:295-423 (stop_early=1: break when
+ * e < tol or |e_k+1 - e_k| < tol, :420-421) and src/ICP_standard.cu:369-463 (stop_early=0, STD
+ * matching, 40 fixed iterations). P is transformed in place. errors has max_iter+1 slots:
+ * errors[0]=0, iteration k writes errors[k+1] (:416). Returns the reference's `iteration`
+ * counter at loop exit (number of completed iterations not counting the one that broke).
+ * idx must hold n ints (zero-initialised by the caller: see the sentinel note above). */
+ORC_API int orc_icp_p2p_f32(float* P, int n, const float* Q, int m, int mode, float sentinel, int max_iter, double tol, int stop_early,
+	float* errors, int* idx, double Rtot[9], double ttot[3], int* iters_run)
+{
+	for (int k = 0; k < 9; k++) Rtot[k] = (k % 4 == 0); for (int k = 0; k < 3; k++) ttot[k] = 0;
+	for (int k = 0; k <= max_iter; k++) errors[k] = 0.0f;
+	int iteration = 0, run = 0;
+	while (iteration < max_iter) {
+		double mom[16], R[9], T[3]; float Rf[9], Tf[3];
+		orc_match_f32(P, n, Q, m, mode, sentinel, idx);
+		orc_moments(P, Q, idx, n, mom);
+		orc_rt_from_moments(mom, R, T);
+		for (int k = 0; k < 9; k++) Rf[k] = (float)R[k]; for (int k = 0; k < 3; k++) Tf[k] = (float)T[k];
+		for (int k = 0; k < 9; k++) R[k] = Rf[k]; for (int k = 0; k < 3; k++) T[k] = Tf[k];
+		orc_compose(Rtot, ttot, R, T);
+		orc_transform_f32(P, n, Rf, Tf);
+		errors[iteration + 1] = (float)orc_rms(P, Q, idx, n);
+		run++;
+		if (stop_early && ((errors[iteration + 1] < tol) ||
+			((float)fabs((double)errors[iteration + 1] - (double)errors[iteration]) < tol))) break;
+		iteration++;
+	}
+	if (iters_run) *iters_run = run;
+	return iteration;
+}
+
+/* Whole loop of src/ICP_CPU.c:207-271 in double / SoA. E has max_iter+1 slots. Returns
+ * num_iterations (= i at exit, :274). pt (3n, SoA) is transformed in place. */
+ORC_API int orc_icp_cpu_f64(double* pt, int n, const double* q, int m, int max_iter, double tol, double* E, int* idx, double Rtot[9], double ttot[3])
+{
+	for (int k = 0; k < 9; k++) Rtot[k] = (k % 4 == 0); for (int k = 0; k < 3; k++) ttot[k] = 0;
+	for (int k = 0; k <= max_iter; k++) E[k] = 0.0;
+	double* qm = (double*)malloc(sizeof(double) * 3 * (size_t)n);
+	double* pm = (double*)malloc(sizeof(double) * 3 * (size_t)n);
+	int i = 0;
+	while (1) {
+		orc_match_cpu_f64(pt, n, q, m, idx);
+		/* centroid_deviation (:342-366) for q[idx] and pt */
+		double qb[3], pb[3];
+		for (int c = 0; c < 3; c++) {
+			double s = 0, s2 = 0;
+			for (int k = 0; k < n; k++) { s += q[(size_t)c * m + idx[k]]; s2 += pt[(size_t)c * n + k]; }
+			qb[c] = s * (1.0 / (double)n); pb[c] = s2 * (1.0 / (double)n);
+			for (int k = 0; k < n; k++) { qm[(size_t)c * n + k] = q[(size_t)c * m + idx[k]] - qb[c]; pm[(size_t)c * n + k] = pt[(size_t)c * n + k] - pb[c]; }
+		}
+		/* N = q_mark * p_mark^T (:239), row-major 3x3 -> column-major W[r+3c] */
+		double W[9], R[9], T[3];
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { double a = 0; for (int k = 0; k < n; k++) a += qm[(size_t)r * n + k] * pm[(size_t)c * n + k]; W[r + 3 * c] = a; }
+		orc_polar_rotation(W, R);                                              /* :240-246 */
+		for (int r = 0; r < 3; r++) T[r] = qb[r] - (R[r] * pb[0] + R[r + 3] * pb[1] + R[r + 6] * pb[2]); /* :247-248 */
+		orc_compose(Rtot, ttot, R, T);
+		for (int k = 0; k < n; k++) {                                           /* :251-253 */
+			double x = pt[k], y = pt[(size_t)n + k], z = pt[2 * (size_t)n + k];
+			for (int r = 0; r < 3; r++) pt[(size_t)r * n + k] = (R[r] * x + R[r + 3] * y + R[r + 6] * z) + T[r];
+		}
+		double acc = 0;                                                        /* :257-266 */
+		for (int c = 0; c < 3; c++) for (int k = 0; k < n; k++) { double d = q[(size_t)c * m + idx[k]] - pt[(size_t)c * n + k]; acc += d * d; }
+		E[i + 1] = sqrt(acc) / pow((double)n, 0.5);
+		if ((E[i + 1] < tol) || (fabs(E[i + 1] - E[i]) < tol)) break;          /* :267 */
+		i++;
+		if (i > max_iter - 1) break;                                          /* :269 */
+	}
+	free(qm); free(pm);
+	return i;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Point-to-plane: k-NN, PCA normals, normal equations, solve
+ * ---------------------------------------------------------------------------------- */
+
+/* `knn` + `minimum`, src/ICP_point_to_plane.cu:30-70, called with P = Q = target and k+1 = 5
+ * (:406): distances are sqrt.rn.f32 of the Matching chain; k1 successive argmin scans with strict
+ * `<` from 10000.0 (lowest index first on ties), each winner invalidated with 10000.0.
+ * nbr is m x k1 row-major (:62). No m x m matrix is materialised here. */
+ORC_API void orc_knn_f32(const float* Q, int m, int k1, int* nbr)
+{
+#pragma omp parallel
+	{
+		float* d = (float*)malloc(sizeof(float) * (size_t)m);
+#pragma omp for schedule(static)
+		for (int i = 0; i < m; i++) {
+			float xp = Q[3 * (size_t)i], yp = Q[3 * (size_t)i + 1], zp = Q[3 * (size_t)i + 2];
+			for (int j = 0; j < m; j++) d[j] = orc_dist(ORC_MODE_SQRT, xp, yp, zp, Q[3 * (size_t)j], Q[3 * (size_t)j + 1], Q[3 * (size_t)j + 2]);
+			for (int r = 0; r < k1; r++) {
+				float min = 10000.0f; int best = 0;
+				for (int j = 0; j < m; j++) if (d[j] < min) { min = d[j]; best = j; }
+				nbr[(size_t)i * k1 + r] = best;
+				d[best] = 10000.0f;
+			}
+		}
+		free(d);
+	}
+}
+
+/* `Normals` steps 1-2 (src/ICP_point_to_plane.cu:80-101) + host eigen-solve (:431-439):
+ * centroid bar = sum_{j=1..k} q_nbr/(float)k added term by term in float (:83-85, neighbour 0 = the
+ * point itself is skipped); A = sum (q-bar)(q-bar)^T NOT divided by k, upper triangle, each
+ * term fused (fmaf) as nvcc contracts `A += a*b`; normal = eigenvector of the eigenvalue of
+ * smallest |lambda| (cblas_isamin, :436). Sign of the normal is arbitrary (ssyev convention is
+ * unpinned) and irrelevant downstream (orc_cxb is even in n). */
+ORC_API void orc_normals_f32(const float* Q, int m, const int* nbr, int k, float* normals)
+{
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < m; i++) {
+		float bar[3] = { 0, 0, 0 }, A[6] = { 0, 0, 0, 0, 0, 0 };
+		for (int j = 1; j < k + 1; j++) {
+			const float* q = Q + 3 * (size_t)nbr[(size_t)i * (k + 1) + j];
+			for (int c = 0; c < 3; c++) bar[c] += q[c] / (float)k;
+		}
+		for (int j = 1; j < k + 1; j++) {
+			const float* q = Q + 3 * (size_t)nbr[(size_t)i * (k + 1) + j];
+			float dx = q[0] - bar[0], dy = q[1] - bar[1], dz = q[2] - bar[2];
+			A[0] = fmaf(dx, dx, A[0]); A[1] = fmaf(dx, dy, A[1]); A[2] = fmaf(dx, dz, A[2]);
+			A[3] = fmaf(dy, dy, A[3]); A[4] = fmaf(dy, dz, A[4]); A[5] = fmaf(dz, dz, A[5]);
+		}
+		double F[9] = { A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5] }, w[3], V[9];
+		orc_eig3(F, w, V);
+		float wf[3] = { (float)w[0], (float)w[1], (float)w[2] };
+		int im = 0; for (int c = 1; c < 3; c++) if (fabsf(wf[c]) < fabsf(wf[im])) im = c;
+		for (int c = 0; c < 3; c++) normals[3 * (size_t)i + c] = (float)V[3 * c + im];
+	}
+}
+
+/* `Cxb` + the two column sums (src/ICP_point_to_plane.cu:193-234, 546-556). Per point, in float
+ * with nvcc's contraction: c = p x n as fmaf(a,b,-(c*d)); the 21 upper-triangle products;
+ * aux = fmaf(d2,nz, fmaf(d0,nx, d1*ny)) with d = p - q_idx; b_i = -[c;n]*aux. Sums in double
+ * (cuBLAS order unpinned). C column-major 6x6, lower triangle left at 0 (:469,477). */
+ORC_API void orc_cxb(const float* P, const float* Q, const int* idx, const float* normals, int n, double C[36], double b[6])
+{
+	for (int k = 0; k < 36; k++) C[k] = 0.0; for (int k = 0; k < 6; k++) b[k] = 0.0;
+	for (int i = 0; i < n; i++) {
+		const float* p = P + 3 * (size_t)i; const float* q = Q + 3 * (size_t)idx[i]; const float* nn = normals + 3 * (size_t)idx[i];
+		float v[6];
+		v[0] = fmaf(p[1], nn[2], -(p[2] * nn[1]));
+		v[1] = fmaf(p[2], nn[0], -(p[0] * nn[2]));
+		v[2] = fmaf(nn[1], p[0], -(p[1] * nn[0]));
+		v[3] = nn[0]; v[4] = nn[1]; v[5] = nn[2];
+		for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) C[r + 6 * c] += (double)(v[r] * v[c]);
+		float d0 = p[0] - q[0], d1 = p[1] - q[1], d2 = p[2] - q[2];
+		float aux = fmaf(nn[2], d2, fmaf(nn[0], d0, nn[1] * d1));
+		for (int r = 0; r < 6; r++) b[r] += (double)(v[r] * -aux);
+	}
+}
+
+/* Solve + Euler -> R of src/ICP_point_to_plane.cu:576-601. x = (alpha,beta,gamma,tx,ty,tz);
+ * R column-major = Rz(gamma) Ry(beta) Rx(alpha) assembled from float cos/sin exactly as :585-589. */
+ORC_API int orc_plane_rt(const double C[36], const double b[6], float Rf[9], float Tf[3])
+{
+	double x[6];
+	/* the reference hands float C, b to cusolver: round first */
+	double Cf[36], bf[6];
+	for (int k = 0; k < 36; k++) Cf[k] = (double)(float)C[k]; for (int k = 0; k < 6; k++) bf[k] = (double)(float)b[k];
+	int info = orc_solve6_spd(Cf, bf, x);
+	if (info) return info;
+	float hb[6]; for (int k = 0; k < 6; k++) hb[k] = (float)x[k];
+	float cx = (float)cos(hb[0]), cy = (float)cos(hb[1]), cz = (float)cos(hb[2]);
+	float sx = (float)sin(hb[0]), sy = (float)sin(hb[1]), sz = (float)sin(hb[2]);
+	Rf[0] = cy * cz; Rf[3] = cz * sx * sy - cx * sz; Rf[6] = cx * cz * sy + sx * sz;
+	Rf[1] = cy * sz; Rf[4] = cx * cz + sx * sy * sz; Rf[7] = cx * sy * sz - cz * sx;
+	Rf[2] = -sy; Rf[5] = cy * sx; Rf[8] = cx * cy;
+	Tf[0] = hb[3]; Tf[1] = hb[4]; Tf[2] = hb[5];
+	return 0;
+}
+
+/* Whole point-to-plane loop, src/ICP_point_to_plane.cu:517-631 (normals computed before, :378-447).
+ * Same conventions as orc_icp_p2p_f32; matching in SQRT mode (:172-174); the reported error is the
+ * point-to-POINT RMS (:618-622). */
+ORC_API int orc_icp_p2plane_f32(float* P, int n, const float* Q, int m, const float* normals, float sentinel, int max_iter, double tol,
+	float* errors, int* idx, double Rtot[9], double ttot[3], int* iters_run)
+{
+	for (int k = 0; k < 9; k++) Rtot[k] = (k % 4 == 0); for (int k = 0; k < 3; k++) ttot[k] = 0;
+	for (int k = 0; k <= max_iter; k++) errors[k] = 0.0f;
+	int iteration = 0, run = 0;
+	while (iteration < max_iter) {
+		double C[36], b[6], R[9], T[3]; float Rf[9], Tf[3];
+		orc_match_f32(P, n, Q, m, ORC_MODE_SQRT, sentinel, idx);
+		orc_cxb(P, Q, idx, normals, n, C, b);
+		if (orc_plane_rt(C, b, Rf, Tf)) break;
+		for (int k = 0; k < 9; k++) R[k] = Rf[k]; for (int k = 0; k < 3; k++) T[k] = Tf[k];
+		orc_compose(Rtot, ttot, R, T);
+		orc_transform_f32(P, n, Rf, Tf);
+		errors[iteration + 1] = (float)orc_rms(P, Q, idx, n);
+		run++;
+		if ((errors[iteration + 1] < tol) ||
+			((float)fabs((double)errors[iteration + 1] - (double)errors[iteration]) < tol)) break;
+		iteration++;
+	}
+	if (iters_run) *iters_run = run;
+	return iteration;
+}

@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE — ctypes loader for oracle/liboracle.so (the CPU restatement in icp_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+REF_DIR = os.path.join(_HERE, "_ref")
+
+MODE_SQ, MODE_SQRT, MODE_STD = 0, 1, 2
+
+
+def build():
+    """Compile the restatement (and, where /root/reference exists, oracle/_ref)."""
+    subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+    return C.CDLL(LIB_PATH)
+
+
+_lib = _load()
+_f = C.POINTER(C.c_float)
+_d = C.POINTER(C.c_double)
+_i = C.POINTER(C.c_int)
+
+
+def _fp(a): return a.ctypes.data_as(_f)
+def _dp(a): return a.ctypes.data_as(_d)
+def _ip(a): return a.ctypes.data_as(_i)
+
+
+_lib.orc_num_threads.restype = C.c_int
+_lib.orc_icp_p2p_f32.restype = C.c_int
+_lib.orc_icp_p2plane_f32.restype = C.c_int
+_lib.orc_icp_cpu_f64.restype = C.c_int
+_lib.orc_rms.restype = C.c_double
+_lib.orc_plane_rt.restype = C.c_int
+_lib.orc_solve6_spd.restype = C.c_int
+
+
+def num_threads():
+    return _lib.orc_num_threads()
+
+
+def synth_p2p(width, npts=None):
+    npts = width * width if npts is None else npts
+    D = np.zeros((npts, 3), np.float32); M = np.zeros((npts, 3), np.float32)
+    _lib.orc_synth_p2p_f32(C.c_int(width), C.c_int(npts), _fp(D), _fp(M))
+    return D, M
+
+
+def synth_source(width, npts=None):
+    npts = width * width if npts is None else npts
+    D = np.zeros((npts, 3), np.float32)
+    _lib.orc_synth_source_f32(C.c_int(width), C.c_int(npts), _fp(D))
+    return D
+
+
+def euler_matrix(ri):
+    r = np.zeros(9, np.float32)
+    _lib.orc_euler_matrix_f32(_fp(np.asarray(ri, np.float32)), _fp(r))
+    return r
+
+
+def rigid_move(D, h_r, t):
+    D = np.ascontiguousarray(D, np.float32)
+    M = np.zeros_like(D)
+    _lib.orc_rigid_move_f32(_fp(D), C.c_int(D.shape[0]), _fp(np.asarray(h_r, np.float32)), _fp(np.asarray(t, np.float32)), _fp(M))
+    return M
+
+
+def synth_standard(width):
+    n = width * width
+    D = np.zeros((n, 3), np.float32); M = np.zeros((n, 3), np.float32)
+    _lib.orc_synth_standard_f32(C.c_int(width), _fp(D), _fp(M))
+    return D, M
+
+
+def synth_cpu_f64(width):
+    n = width * width
+    D = np.zeros(3 * n, np.float64); M = np.zeros(3 * n, np.float64)
+    _lib.orc_synth_cpu_f64(C.c_int(width), _dp(D), _dp(M))
+    return D, M
+
+
+def match(P, Q, mode=MODE_SQ, sentinel=100000.0, idx0=None):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    idx = np.zeros(P.shape[0], np.int32) if idx0 is None else np.ascontiguousarray(idx0, np.int32).copy()
+    _lib.orc_match_f32(_fp(P), C.c_int(P.shape[0]), _fp(Q), C.c_int(Q.shape[0]), C.c_int(mode), C.c_float(sentinel), _ip(idx))
+    return idx
+
+
+def moments(P, Q, idx):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32); idx = np.ascontiguousarray(idx, np.int32)
+    mom = np.zeros(16, np.float64)
+    _lib.orc_moments(_fp(P), _fp(Q), _ip(idx), C.c_int(P.shape[0]), _dp(mom))
+    return mom
+
+
+def rt_from_moments(mom):
+    R = np.zeros(9, np.float64); T = np.zeros(3, np.float64)
+    _lib.orc_rt_from_moments(_dp(np.ascontiguousarray(mom, np.float64)), _dp(R), _dp(T))
+    return R, T
+
+
+def polar_rotation(W):
+    R = np.zeros(9, np.float64)
+    _lib.orc_polar_rotation(_dp(np.ascontiguousarray(W, np.float64)), _dp(R))
+    return R
+
+
+def transform(P, R, T):
+    P = np.ascontiguousarray(P, np.float32).copy()
+    _lib.orc_transform_f32(_fp(P), C.c_int(P.shape[0]), _fp(np.asarray(R, np.float32)), _fp(np.asarray(T, np.float32)))
+    return P
+
+
+def rms(P, Q, idx):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32); idx = np.ascontiguousarray(idx, np.int32)
+    return float(_lib.orc_rms(_fp(P), _fp(Q), _ip(idx), C.c_int(P.shape[0])))
+
+
+def icp_p2p(P, Q, mode=MODE_SQ, sentinel=100000.0, max_iter=40, tol=1e-6, stop_early=True):
+    P = np.ascontiguousarray(P, np.float32).copy(); Q = np.ascontiguousarray(Q, np.float32)
+    n = P.shape[0]
+    errors = np.zeros(max_iter + 1, np.float32); idx = np.zeros(n, np.int32)
+    R = np.zeros(9); t = np.zeros(3); run = C.c_int()
+    it = _lib.orc_icp_p2p_f32(_fp(P), C.c_int(n), _fp(Q), C.c_int(Q.shape[0]), C.c_int(mode), C.c_float(sentinel), C.c_int(max_iter),
+                              C.c_double(tol), C.c_int(1 if stop_early else 0), _fp(errors), _ip(idx), _dp(R), _dp(t), C.byref(run))
+    return {"iterations": it, "iterations_run": run.value, "errors": errors, "idx": idx, "R": R, "t": t, "P": P}
+
+
+def icp_cpu_f64(width=100, max_iter=200, tol=1e-5):
+    D, M = synth_cpu_f64(width)
+    n = width * width
+    pt = D.copy(); E = np.zeros(max_iter + 1); idx = np.zeros(n, np.int32); R = np.zeros(9); t = np.zeros(3)
+    it = _lib.orc_icp_cpu_f64(_dp(pt), C.c_int(n), _dp(M), C.c_int(n), C.c_int(max_iter), C.c_double(tol), _dp(E), _ip(idx), _dp(R), _dp(t))
+    return {"iterations": it, "errors": E, "idx": idx, "R": R, "t": t, "D": D, "M": M, "pt": pt}
+
+
+def knn(Q, k1=5):
+    Q = np.ascontiguousarray(Q, np.float32)
+    nbr = np.zeros((Q.shape[0], k1), np.int32)
+    _lib.orc_knn_f32(_fp(Q), C.c_int(Q.shape[0]), C.c_int(k1), _ip(nbr))
+    return nbr
+
+
+def normals(Q, nbr, k=4):
+    Q = np.ascontiguousarray(Q, np.float32); nbr = np.ascontiguousarray(nbr, np.int32)
+    out = np.zeros((Q.shape[0], 3), np.float32)
+    _lib.orc_normals_f32(_fp(Q), C.c_int(Q.shape[0]), _ip(nbr), C.c_int(k), _fp(out))
+    return out
+
+
+def cxb(P, Q, idx, nrm):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    idx = np.ascontiguousarray(idx, np.int32); nrm = np.ascontiguousarray(nrm, np.float32)
+    Cm = np.zeros(36); b = np.zeros(6)
+    _lib.orc_cxb(_fp(P), _fp(Q), _ip(idx), _fp(nrm), C.c_int(P.shape[0]), _dp(Cm), _dp(b))
+    return Cm, b
+
+
+def plane_rt(Cm, b):
+    R = np.zeros(9, np.float32); T = np.zeros(3, np.float32)
+    info = _lib.orc_plane_rt(_dp(np.ascontiguousarray(Cm, np.float64)), _dp(np.ascontiguousarray(b, np.float64)), _fp(R), _fp(T))
+    return info, R, T
+
+
+def icp_p2plane(P, Q, nrm, sentinel=100000.0, max_iter=50, tol=1e-6):
+    P = np.ascontiguousarray(P, np.float32).copy(); Q = np.ascontiguousarray(Q, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
+    n = P.shape[0]
+    errors = np.zeros(max_iter + 1, np.float32); idx = np.zeros(n, np.int32)
+    R = np.zeros(9); t = np.zeros(3); run = C.c_int()
+    it = _lib.orc_icp_p2plane_f32(_fp(P), C.c_int(n), _fp(Q), C.c_int(Q.shape[0]), _fp(nrm), C.c_float(sentinel), C.c_int(max_iter),
+                                  C.c_double(tol), _fp(errors), _ip(idx), _dp(R), _dp(t), C.byref(run))
+    return {"iterations": it, "iterations_run": run.value, "errors": errors, "idx": idx, "R": R, "t": t, "P": P}
