@@ -1,0 +1,47 @@
+"""numpy restatement of the reference's synthetic clouds (src/ICP_point_to_point.cu:103-190): the
+saddle z = x^2 - y^2 on a WxW grid over [-2,2]^2 and its rigidly moved copy. Every operation is an
+element-wise float32 numpy op (one rounding each, no FMA), in the reference's order, so the clouds are
+bit-identical to what the reference host code builds (tests/test_synth.py checks this against the
+oracle's C generator). Used by bench.py; the C++ twin for the executables is apps/synth.h."""
+import numpy as np
+
+F = np.float32
+
+
+def source(width, npts=None):
+    npts = width * width if npts is None else npts
+    i = np.arange(width, dtype=np.float32)
+    lin = F(-2.0) + (i * F(4.0)) / (F(width) - F(1.0))
+    k = np.arange(npts)
+    x = lin[k // width]
+    y = lin[k % width]
+    z = (x.astype(np.float64) ** 2 - y.astype(np.float64) ** 2).astype(np.float32)
+    return np.ascontiguousarray(np.stack([x, y, z], axis=1))
+
+
+def euler_matrix(ri):
+    cx, cy, cz = (F(np.cos(np.float64(F(a)))) for a in ri)
+    sx, sy, sz = (F(np.sin(np.float64(F(a)))) for a in ri)
+    r = np.zeros(9, np.float32)
+    r[0] = cy * cz; r[1] = (cz * sx * sy) + (cx * sz); r[2] = -(cx * cz * sy) + (sx * sz)
+    r[3] = -cy * sz; r[4] = (cx * cz) - (sx * sy * sz); r[5] = (cx * sy * sz) + (cz * sx)
+    r[6] = sy; r[7] = -cy * sx; r[8] = cx * cy
+    return r
+
+
+def rigid_move(D, r, t):
+    x, y, z = D[:, 0], D[:, 1], D[:, 2]
+    cols = []
+    for j in range(3):
+        acc = r[j] * x            # temp = 0 + A[j,0]*B[0]
+        acc = acc + r[j + 3] * y
+        acc = acc + r[j + 6] * z
+        cols.append(acc + F(t[j]))
+    return np.ascontiguousarray(np.stack(cols, axis=1).astype(np.float32))
+
+
+def p2p_clouds(width, npts=None):
+    """Defaults of ICP_point_to_point.cu: t = (0.8,-0.3,0.2), r = (0.2,-0.2,0.05) rad."""
+    D = source(width, npts)
+    M = rigid_move(D, euler_matrix([0.2, -0.2, 0.05]), [0.8, -0.3, 0.2])
+    return D, M

@@ -1,0 +1,66 @@
+"""CPU suite: the C-ABI library loads and exports exactly what include/*.h declare; my_lib drop-in parity."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "fast-point-cloud-registration-with-gpus_b200")
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "icp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(icpb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(ib):
+    lib = ctypes.CDLL(os.path.join(PKG, "libicp_b200.so"))
+    names = _declared()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), "libicp_b200.so does not export %s" % n
+    assert sorted(ib.EXPORTS) == names, "python binding and header disagree"
+    assert lib.icpb_version() == 100
+
+
+def test_only_abi_symbols_are_exported():
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(PKG, "libicp_b200.so")], capture_output=True, text=True, check=True).stdout
+    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert syms and all(s.startswith("icpb_") for s in syms), syms
+
+
+def test_no_silent_cpu_fallback(ib):
+    """Without a GPU the product fails loudly (no CPU path exists)."""
+    n = ctypes.c_int(-1)
+    rc = ib.lib.icpb_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ib.IcpError):
+        ib.Context(0)
+    p = ib.default_params()
+    assert (p.metric, p.dist_mode, p.max_iter, p.stop_early) == (0, 0, 40, 1)
+    assert abs(p.sentinel - 100000.0) < 1e-3 and p.tol == 0.000001
+    assert ib.lib.icpb_status_string(-7).decode() == "no sm_100 CUDA device"
+
+
+def test_product_does_not_link_or_open_the_oracle():
+    out = subprocess.run(["ldd", os.path.join(PKG, "libicp_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    blob = open(os.path.join(PKG, "libicp_b200.so"), "rb").read()
+    assert b"liboracle" not in blob and b"icp_oracle" not in blob
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")) and "selftest" not in f:
+                src = open(os.path.join(root, f)).read()
+                assert "liboracle" not in src and "import oracle" not in src, f
+
+
+def test_my_lib_dropin_matches_reference_library(golden_dir):
+    """include/my_lib.h vs the reference's src/my_lib.h through the same driver (oracle/ref_my_lib.cpp):
+    bit patterns of the three GEMMs and the exact text of the six printers."""
+    exe = os.path.join(PKG, "apps", "selftest_my_lib")
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(golden_dir, "ref_my_lib_stdout.txt")).read()
