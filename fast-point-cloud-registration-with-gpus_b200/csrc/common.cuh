@@ -146,7 +146,7 @@ struct Ctx {
 	bool   step_state_ready = false;
 
 	// K1 configuration
-	int k1_cfg = 0;              // index into the instantiated (S, THREADS) table
+	int k1_cfg = 6;              // index into the K1 tuning table (nn_bruteforce.cu); 6 = best measured on B200
 	int k1_grid_override = 0;
 	double pairs_acc = 0;
 

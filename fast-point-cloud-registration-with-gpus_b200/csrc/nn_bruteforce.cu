@@ -35,6 +35,7 @@ namespace icpb {
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 bcast2v(float a) { u64 r; asm volatile("mov.b64 %0, {%1,%1};" : "=l"(r) : "f"(a)); return r; }
 __device__ __forceinline__ u64 pack2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -100,7 +101,12 @@ template <int MODE> __device__ __forceinline__ float lower_threshold(float m)
 // ------------------------------------------------------------------------------------------------
 // K1 main kernel
 // ------------------------------------------------------------------------------------------------
-template <int S, int THREADS, int MODE, int MINB>
+// VAR bits (tuning variants, selected at run time through the config table):
+//   1: re-materialise the broadcast source operand inside the loop (asm volatile), which makes ptxas use
+//      the scalar-broadcast operand form (R.F32) instead of keeping duplicated register pairs
+//   2: software-prefetch the next target quad from shared memory into registers
+//   4: keep thr[] / best[] in shared memory (touched once per sub-tile) instead of registers
+template <int S, int THREADS, int MODE, int MINB, int VAR>
 __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 {
 	constexpr int SB   = S * THREADS;          // sources per block
@@ -131,20 +137,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 		}
 	}
 
-	float sx[S], sy[S], sz[S], m[S], thr[S];
-	int best[S];
+	float sx[S], sy[S], sz[S], m[S];
+	float thr_r[(VAR & 4) ? 1 : S];
+	int   best_r[(VAR & 4) ? 1 : S];
+	// VAR&4: per-thread thr/best slots live behind the ring in dynamic shared memory, [s][tid] (conflict free)
+	float* thr_s  = reinterpret_cast<float*>(k1_smem + (size_t)K1_STAGES * K1_TILE_BYTES + 64) + tid;
+	int*   best_s = reinterpret_cast<int*>(thr_s - tid + S * THREADS) + tid;
+	auto get_thr  = [&](int s) -> float { if constexpr ((VAR & 4) != 0) return thr_s[s * THREADS]; else return thr_r[s]; };
+	auto get_best = [&](int s) -> int { if constexpr ((VAR & 4) != 0) return best_s[s * THREADS]; else return best_r[s]; };
+	auto set_thr  = [&](int s, float v) { if constexpr ((VAR & 4) != 0) thr_s[s * THREADS] = v; else thr_r[s] = v; };
+	auto set_best = [&](int s, int v) { if constexpr ((VAR & 4) != 0) best_s[s * THREADS] = v; else best_r[s] = v; };
 	int cur_sb = -1;
 
 	auto flush = [&](int sb) {
 #pragma unroll
 		for (int s = 0; s < S; s++) {
 			const int i = sb * SB + s * THREADS + tid;
-			if (i < p.n && best[s] >= 0) {
-				const float* gx = p.qtiles + (size_t)(best[s] / SUBS) * 3 * K1_TT + (size_t)(best[s] % SUBS) * K1_TRK;
+			const int bs = get_best(s);
+			if (i < p.n && bs >= 0) {
+				const float th = get_thr(s);
+				const float* gx = p.qtiles + (size_t)(bs / SUBS) * 3 * K1_TT + (size_t)(bs % SUBS) * K1_TRK;
 				const float4* X4 = reinterpret_cast<const float4*>(gx);
 				const float4* Y4 = reinterpret_cast<const float4*>(gx + K1_TT);
 				const float4* Z4 = reinterpret_cast<const float4*>(gx + 2 * K1_TT);
-				const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(thr[s]) : thr[s];
+				const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
 				int found = -1;
 				for (int j = 0; j < K1_TRK / 4 && found < 0; j++) {
 					const float4 X = __ldg(X4 + j), Y = __ldg(Y4 + j), Z = __ldg(Z4 + j);
@@ -159,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 					else if (d3 <= target) found = 4 * j + 3;
 				}
 				if (found >= 0) {
-					const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(best[s] * K1_TRK + found);
+					const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * K1_TRK + found);
 					atomicMin(p.keys + i, key);
 				}
 			}
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 			for (int s = 0; s < S; s++) {
 				const int i = sb * SB + s * THREADS + tid;
 				sx[s] = p.px[i]; sy[s] = p.py[i]; sz[s] = p.pz[i];
-				m[s] = p.thr0; thr[s] = p.thr0; best[s] = -1;
+				m[s] = p.thr0; set_thr(s, p.thr0); set_best(s, -1);
 			}
 			cur_sb = sb;
 		}
@@ -200,15 +216,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 
 #pragma unroll 1
 		for (int sub = 0; sub < SUBS; sub++) {
+			const int j0 = sub * (K1_TRK / 4), j1 = j0 + K1_TRK / 4;
+			float4 X = X4[j0], Y = Y4[j0], Z = Z4[j0];
 #pragma unroll 2
-			for (int j = sub * (K1_TRK / 4); j < (sub + 1) * (K1_TRK / 4); j++) {
-				const float4 X = X4[j], Y = Y4[j], Z = Z4[j];
+			for (int j = j0; j < j1; j++) {
+				float4 Xn, Yn, Zn;
+				if constexpr ((VAR & 2) != 0) { Xn = X4[j + 1]; Yn = Y4[j + 1]; Zn = Z4[j + 1]; }   // (reads 16 B past the sub-tile: still inside the ring + pad)
+				else if (j > j0) { X = X4[j]; Y = Y4[j]; Z = Z4[j]; }
 				const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
 				const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
 				const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
 #pragma unroll
 				for (int s = 0; s < S; s++) {
-					const u64 PX = pack2(sx[s], sx[s]), PY = pack2(sy[s], sy[s]), PZ = pack2(sz[s], sz[s]);
+					u64 PX, PY, PZ;
+					if constexpr ((VAR & 1) != 0) { PX = bcast2v(sx[s]); PY = bcast2v(sy[s]); PZ = bcast2v(sz[s]); }
+					else { PX = pack2(sx[s], sx[s]); PY = pack2(sy[s], sy[s]); PZ = pack2(sz[s], sz[s]); }
 					u64 dx = sub2(PX, x01), dy = sub2(PY, y01), dz = sub2(PZ, z01);
 					u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
 					float a, b;
@@ -219,14 +241,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 					unpack2(d, a, b);
 					m[s] = min3(m[s], a, b);
 				}
+				if constexpr ((VAR & 2) != 0) { X = Xn; Y = Yn; Z = Zn; }
 			}
 			const int gsub = t * SUBS + sub;
 #pragma unroll
 			for (int s = 0; s < S; s++) {
-				if (m[s] < thr[s]) {
-					best[s] = gsub;
-					thr[s]  = lower_threshold<MODE>(m[s]);
-					m[s]    = thr[s];
+				if (m[s] < get_thr(s)) {
+					const float nt_ = lower_threshold<MODE>(m[s]);
+					set_best(s, gsub);
+					set_thr(s, nt_);
+					m[s] = nt_;
 				}
 			}
 		}
@@ -278,9 +302,17 @@ __global__ void key_reset_kernel(u64* keys, int n, const int* done)
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-struct K1Config { int S, threads, minb; };
+struct K1Config { int S, threads, minb, var; };
+// index = ICPB_K1_CFG (tuning); entry 0 is the default chosen from measurements on B200 (profiles/)
+#define K1_CONFIGS(X) \
+	X(0, 8, 256, 2, 0) X(1, 8, 512, 1, 0) X(2, 4, 256, 3, 0) X(3, 4, 512, 1, 0) \
+	X(4, 8, 256, 2, 1) X(5, 8, 256, 2, 3) X(6, 8, 256, 2, 7) X(7, 8, 256, 3, 7) \
+	X(8, 4, 256, 4, 7) X(9, 4, 512, 2, 7) X(10, 8, 512, 1, 7) X(11, 4, 256, 3, 3) \
+	X(12, 8, 384, 1, 7) X(13, 6, 256, 3, 7) X(14, 4, 512, 1, 3) X(15, 8, 256, 2, 5)
 static const K1Config k1_table[] = {
-	{ 8, 256, 2 }, { 8, 512, 1 }, { 4, 256, 3 }, { 4, 512, 1 }, { 16, 256, 1 }, { 8, 128, 4 },
+#define X(i, s, t, b, v) { s, t, b, v },
+	K1_CONFIGS(X)
+#undef X
 };
 constexpr int K1_NUM_CFG = (int)(sizeof(k1_table) / sizeof(k1_table[0]));
 
@@ -302,15 +334,15 @@ static float sqrt_domain_threshold(float sentinel)
 	return y;
 }
 
-template <int S, int THREADS, int MINB>
+template <int S, int THREADS, int MINB, int VAR>
 static int launch_cfg(Ctx* c, int mode, const K1Params& base)
 {
 	K1Params p = base;
 	constexpr int SB = S * THREADS;
 	const int nb = (c->n + SB - 1) / SB;
 	p.units = (long long)nb * p.nt;
-	const size_t smem = (size_t)K1_STAGES * K1_TILE_BYTES;
-	auto kern = (mode == ICPB_DIST_SQRT) ? k1_match<S, THREADS, ICPB_DIST_SQRT, MINB> : k1_match<S, THREADS, ICPB_DIST_SQ, MINB>;
+	const size_t smem = (size_t)K1_STAGES * K1_TILE_BYTES + 64 + ((VAR & 4) ? (size_t)2 * S * THREADS * 4 : 0);
+	auto kern = (mode == ICPB_DIST_SQRT) ? k1_match<S, THREADS, ICPB_DIST_SQRT, MINB, VAR> : k1_match<S, THREADS, ICPB_DIST_SQ, MINB, VAR>;
 	ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -352,13 +384,10 @@ int launch_match_brute(Ctx* c, int dist_mode, float sentinel)
 		return ICPB_OK;
 	}
 	switch (c->k1_cfg) {
-	default:
-	case 0: return launch_cfg<8, 256, 2>(c, dist_mode, p);
-	case 1: return launch_cfg<8, 512, 1>(c, dist_mode, p);
-	case 2: return launch_cfg<4, 256, 3>(c, dist_mode, p);
-	case 3: return launch_cfg<4, 512, 1>(c, dist_mode, p);
-	case 4: return launch_cfg<16, 256, 1>(c, dist_mode, p);
-	case 5: return launch_cfg<8, 128, 4>(c, dist_mode, p);
+#define X(i, s, t, b, v) case i: return launch_cfg<s, t, b, v>(c, dist_mode, p);
+	K1_CONFIGS(X)
+#undef X
+	default: return launch_cfg<8, 256, 2, 0>(c, dist_mode, p);
 	}
 }
 
