@@ -260,7 +260,7 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 		if ((rc = dev_alloc(c, &c->nrm4, (size_t)0)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->nbr, (size_t)0)) != ICPB_OK) return rc;
 	}
-	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false;
+	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->step_state_ready = false;
 	const float* src = xyz;
 	if (!on_device) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)m)) != ICPB_OK) return rc;
@@ -290,7 +290,7 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 		if ((rc = dev_alloc(c, &c->dmin, (size_t)cap)) != ICPB_OK) return rc;
 		c->n_cap = cap;
 	}
-	c->n = n;
+	c->n = n; c->step_state_ready = false;   // the control block caches the global point count
 	const float* src = xyz;
 	if (!on_device && n > 0) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)n)) != ICPB_OK) return rc;

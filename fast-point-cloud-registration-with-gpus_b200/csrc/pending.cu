@@ -10,9 +10,5 @@ int launch_match_grid(Ctx* c, int, float) { snprintf(c->err, sizeof c->err, "ICP
 }
 using namespace icpb;
 extern "C" {
-int icpb_estimate_normals(icpb_ctx* ctx, int, float*) { if (!ctx) return ICPB_ERR_BADARG; snprintf(reinterpret_cast<Ctx*>(ctx)->err, 512, "icpb_estimate_normals: not built yet"); return ICPB_ERR_STATE; }
-int icpb_get_neighbors(icpb_ctx* ctx, int*, int) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
-int icpb_get_normals(icpb_ctx* ctx, float*, int) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
-int icpb_set_normals(icpb_ctx* ctx, const float*, int) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
 int icpb_run_batched(icpb_ctx* ctx, const icpb_params*, int, const float*, int, const float*, int, float*, int*, double*, double*, float*) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
 }
