@@ -1,0 +1,281 @@
+// batched.cu — K9: many small independent registrations, one per CTA, the whole ICP loop in ONE kernel.
+//
+// BASELINE.json config 5 (4096 pairs of 2048-point clouds). The reference has no batched mode; the
+// nearest relative is its shared-memory block reduction test (src/tests/centroid.cu:14-47). Each CTA
+// runs, for its registration, exactly the loop of src/ICP_point_to_point.cu:295-423:
+//   matching (K1's packed inner loop, target resident in shared memory, 8 sources per thread in registers,
+//   sub-tile tracking + re-scan for the index) -> FP64 block reduction of {sum p, sum q, sum q p^T} ->
+//   3x3 Jacobi SVD by one thread (solve_device.cuh) -> transform of the registers with RyT's arithmetic ->
+//   FP64 block reduction of the squared residual -> the reference's stop test,
+// with __syncthreads() as the only synchronisation: no kernel launches, no host round trips, no global
+// memory traffic inside the loop except the final results. Two CTAs (16 warps) share an SM.
+#include "common.cuh"
+#include "k1_device.cuh"
+#include "solve_device.cuh"
+
+namespace icpb {
+
+constexpr int K9_S = 8, K9_THREADS = 256;
+constexpr int K9_MAX_N = K9_S * K9_THREADS;     // 2048 sources per registration
+constexpr int K9_MAX_M = 4096;                  // targets per registration (48 KB of shared memory)
+constexpr int K9_TRK = 64;                      // tracking sub-tile (small clouds: keep the re-scan cheap)
+
+struct BatchParams {
+	const float* sources;   // [batch][n][3]
+	const float* targets;   // [batch][m][3]
+	int batch, n, m, max_iter, stop_early, mode;
+	float sentinel, thr0;
+	double tol;
+	float* errors;          // [batch][max_iter+1]
+	int* iterations;        // [batch]
+	int* iterations_run;    // [batch]
+	double* R;              // [batch][9]
+	double* t;              // [batch][3]
+	int* idx;               // [batch][n] or nullptr
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red /* [THREADS/32] */)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0.0;
+#pragma unroll
+	for (int w = 0; w < K9_THREADS / 32; w++) s += red[w];
+	return s;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchParams p)
+{
+	extern __shared__ __align__(16) unsigned char k9_smem[];
+	const int mpad = ((p.m + K9_TRK - 1) / K9_TRK) * K9_TRK;
+	float* tx = reinterpret_cast<float*>(k9_smem);      // [mpad + 4] each, padded with +inf
+	float* ty = tx + mpad + 4;
+	float* tz = ty + mpad + 4;
+	__shared__ double red[K9_THREADS / 32];
+	__shared__ double mom[16];
+	__shared__ IterState st;                            // reuse of the streaming path's control block + solver
+	__shared__ float err_prev;
+	const int tid = threadIdx.x;
+	const float inf = __int_as_float(0x7f800000);
+
+	for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+		__syncthreads();
+		const float* T = p.targets + (size_t)b * p.m * 3;
+		for (int j = tid; j < mpad + 4; j += K9_THREADS) {
+			const bool ok = j < p.m;
+			tx[j] = ok ? T[3 * (size_t)j] : inf; ty[j] = ok ? T[3 * (size_t)j + 1] : inf; tz[j] = ok ? T[3 * (size_t)j + 2] : inf;
+		}
+		float sx[K9_S], sy[K9_S], sz[K9_S];
+		int idx[K9_S];
+		const float* Sg = p.sources + (size_t)b * p.n * 3;
+#pragma unroll
+		for (int s = 0; s < K9_S; s++) {
+			const int i = s * K9_THREADS + tid;
+			const bool ok = i < p.n;
+			sx[s] = ok ? Sg[3 * (size_t)i] : 0.f; sy[s] = ok ? Sg[3 * (size_t)i + 1] : 0.f; sz[s] = ok ? Sg[3 * (size_t)i + 2] : 0.f;
+			idx[s] = 0;
+		}
+		if (tid == 0) {
+			st.done = 0; st.iteration = 0; st.iters_run = 0;
+			for (int k = 0; k < 9; k++) st.Rtot[k] = (k % 4 == 0) ? 1.0 : 0.0;
+			for (int k = 0; k < 3; k++) st.ttot[k] = 0.0;
+			err_prev = 0.f;
+			p.errors[(size_t)b * (p.max_iter + 1)] = 0.f;
+		}
+		__syncthreads();
+
+		while (true) {
+			// ---- matching: K1's inner loop over the shared-memory target ----
+			float m[K9_S], thr[K9_S];
+			int best[K9_S];
+#pragma unroll
+			for (int s = 0; s < K9_S; s++) { m[s] = p.thr0; thr[s] = p.thr0; best[s] = -1; }
+			const float4* X4 = reinterpret_cast<const float4*>(tx);
+			const float4* Y4 = reinterpret_cast<const float4*>(ty);
+			const float4* Z4 = reinterpret_cast<const float4*>(tz);
+			const int nsub = mpad / K9_TRK;
+#pragma unroll 1
+			for (int sub = 0; sub < nsub; sub++) {
+				const int j0 = sub * (K9_TRK / 4), j1 = j0 + K9_TRK / 4;
+				float4 X = X4[j0], Y = Y4[j0], Z = Z4[j0];
+#pragma unroll 2
+				for (int j = j0; j < j1; j++) {
+					const float4 Xn = X4[j + 1], Yn = Y4[j + 1], Zn = Z4[j + 1];   // +4 floats of padding make this safe
+					const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+					const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+					const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+#pragma unroll
+					for (int s = 0; s < K9_S; s++) {
+						const u64 PX = bcast2v(sx[s]), PY = bcast2v(sy[s]), PZ = bcast2v(sz[s]);
+						u64 dx = sub2(PX, x01), dy = sub2(PY, y01), dz = sub2(PZ, z01);
+						u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+						float a, c;
+						unpack2(d, a, c);
+						m[s] = min3(m[s], a, c);
+						dx = sub2(PX, x23); dy = sub2(PY, y23); dz = sub2(PZ, z23);
+						d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+						unpack2(d, a, c);
+						m[s] = min3(m[s], a, c);
+					}
+					X = Xn; Y = Yn; Z = Zn;
+				}
+#pragma unroll
+				for (int s = 0; s < K9_S; s++) {
+					if (m[s] < thr[s]) { best[s] = sub; thr[s] = lower_threshold<MODE>(m[s]); m[s] = thr[s]; }
+				}
+			}
+			// index recovery: first j of the remembered sub-tile that attains the minimum
+#pragma unroll
+			for (int s = 0; s < K9_S; s++) {
+				if (best[s] >= 0) {
+					const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(thr[s]) : thr[s];
+					const int base = best[s] * K9_TRK;
+					int found = -1;
+					for (int j = 0; j < K9_TRK && found < 0; j++) {
+						float d = dist_chain(sx[s], sy[s], sz[s], tx[base + j], ty[base + j], tz[base + j]);
+						if (MODE == ICPB_DIST_SQRT) d = __fsqrt_rn(d);
+						if (d <= target) found = j;
+					}
+					if (found >= 0) idx[s] = base + found;
+				}
+			}
+			// ---- moments (FP64), SVD by thread 0 ----
+			double acc[15];
+#pragma unroll
+			for (int k = 0; k < 15; k++) acc[k] = 0.0;
+#pragma unroll
+			for (int s = 0; s < K9_S; s++) {
+				if (s * K9_THREADS + tid < p.n) {
+					const double x = sx[s], y = sy[s], z = sz[s];
+					const double qx = tx[idx[s]], qy = ty[idx[s]], qz = tz[idx[s]];
+					acc[0] += x; acc[1] += y; acc[2] += z; acc[3] += qx; acc[4] += qy; acc[5] += qz;
+					acc[6] += qx * x; acc[7] += qy * x; acc[8] += qz * x;
+					acc[9] += qx * y; acc[10] += qy * y; acc[11] += qz * y;
+					acc[12] += qx * z; acc[13] += qy * z; acc[14] += qz * z;
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < 15; k++) { const double v = block_sum(acc[k], red); if (tid == 0) mom[k] = v; }
+			if (tid == 0) {
+				for (int k = 0; k < 15; k++) st.moments[k] = mom[k];
+				st.moments[15] = (double)p.n;
+				solve_p2p(&st);
+			}
+			__syncthreads();
+			// ---- transform (RyT arithmetic) + residual against the same correspondences ----
+			const float r0 = st.R[0], r1 = st.R[1], r2 = st.R[2], r3 = st.R[3], r4 = st.R[4], r5 = st.R[5], r6 = st.R[6], r7 = st.R[7], r8 = st.R[8];
+			const float t0 = st.T[0], t1 = st.T[1], t2 = st.T[2];
+			double e = 0.0;
+#pragma unroll
+			for (int s = 0; s < K9_S; s++) {
+				const float x = sx[s], y = sy[s], z = sz[s];
+				sx[s] = __fadd_rn(__fmaf_rn(r6, z, __fmaf_rn(r0, x, __fmul_rn(r3, y))), t0);
+				sy[s] = __fadd_rn(__fmaf_rn(r7, z, __fmaf_rn(r1, x, __fmul_rn(r4, y))), t1);
+				sz[s] = __fadd_rn(__fmaf_rn(r8, z, __fmaf_rn(r2, x, __fmul_rn(r5, y))), t2);
+				if (s * K9_THREADS + tid < p.n) {
+					const float ex = __fsub_rn(sx[s], tx[idx[s]]), ey = __fsub_rn(sy[s], ty[idx[s]]), ez = __fsub_rn(sz[s], tz[idx[s]]);
+					e += (double)ex * (double)ex + (double)ey * (double)ey + (double)ez * (double)ez;
+				}
+			}
+			const double esum = block_sum(e, red);
+			if (tid == 0) {
+				// finish_iteration of the streaming path (src/ICP_point_to_point.cu:415-422)
+				const float err = (float)(sqrt(esum) / sqrt((double)p.n));
+				const int it = st.iteration;
+				p.errors[(size_t)b * (p.max_iter + 1) + it + 1] = err;
+				st.iters_run += 1;
+				const bool stop = p.stop_early && (((double)err < p.tol) || ((double)(float)fabs((double)err - (double)err_prev) < p.tol));
+				err_prev = err;
+				if (stop) st.done = 1;
+				else { st.iteration = it + 1; if (it + 1 >= p.max_iter) st.done = 1; }
+			}
+			__syncthreads();
+			if (st.done) break;
+		}
+		if (tid == 0) {
+			p.iterations[b] = st.iteration;
+			p.iterations_run[b] = st.iters_run;
+			for (int k = 0; k < 9; k++) p.R[(size_t)b * 9 + k] = st.Rtot[k];
+			for (int k = 0; k < 3; k++) p.t[(size_t)b * 3 + k] = st.ttot[k];
+		}
+		if (p.idx) {
+#pragma unroll
+			for (int s = 0; s < K9_S; s++) { const int i = s * K9_THREADS + tid; if (i < p.n) p.idx[(size_t)b * p.n + i] = idx[s]; }
+		}
+	}
+}
+
+} // namespace icpb
+
+using namespace icpb;
+
+static float sqrt_threshold_host(float sentinel)
+{
+	if (!(sentinel > 0.0f)) return 0.0f;
+	float y = sentinel * sentinel;
+	if (std::isinf(y)) return y;
+	while (sqrtf(y) < sentinel) y = nextafterf(y, INFINITY);
+	while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
+	return y;
+}
+
+extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int batch, const float* sources, int n, const float* targets, int m,
+                                float* errors, int* iterations, double* R, double* t, float* elapsed_ms)
+{
+	if (!ctx) return ICPB_ERR_BADARG;
+	Ctx* c = reinterpret_cast<Ctx*>(ctx);
+	ICPB_CUDA(c, cudaSetDevice(c->device));
+	auto bad = [&](const char* msg) { snprintf(c->err, sizeof c->err, "icpb_run_batched: %s", msg); return ICPB_ERR_BADARG; };
+	if (!params || !sources || !targets || !errors || !iterations || !R || !t) return bad("NULL argument");
+	if (batch < 1 || n < 1 || m < 1) return bad("empty batch");
+	if (n > K9_MAX_N || m > K9_MAX_M) return bad("clouds larger than 2048 sources / 4096 targets: use icpb_run per pair");
+	if (params->metric != ICPB_POINT_TO_POINT) return bad("only point-to-point is batched");
+	if (params->dist_mode != ICPB_DIST_SQ && params->dist_mode != ICPB_DIST_SQRT) return bad("dist_mode must be SQ or SQRT");
+	if (params->max_iter < 1 || params->max_iter > 4096) return bad("max_iter out of range");
+
+	const size_t sb = sizeof(float) * 3 * (size_t)batch * n, tb = sizeof(float) * 3 * (size_t)batch * m;
+	const size_t eb = sizeof(float) * (size_t)batch * (params->max_iter + 1);
+	float *d_s = nullptr, *d_t = nullptr, *d_e = nullptr; int *d_it = nullptr, *d_run = nullptr; double *d_R = nullptr, *d_tt = nullptr;
+	auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_t); cudaFree(d_e); cudaFree(d_it); cudaFree(d_run); cudaFree(d_R); cudaFree(d_tt); };
+#define K9_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(c, e__, #call, __FILE__, __LINE__); } } while (0)
+	K9_TRY(cudaMalloc((void**)&d_s, sb)); K9_TRY(cudaMalloc((void**)&d_t, tb)); K9_TRY(cudaMalloc((void**)&d_e, eb));
+	K9_TRY(cudaMalloc((void**)&d_it, sizeof(int) * batch)); K9_TRY(cudaMalloc((void**)&d_run, sizeof(int) * batch));
+	K9_TRY(cudaMalloc((void**)&d_R, sizeof(double) * 9 * batch)); K9_TRY(cudaMalloc((void**)&d_tt, sizeof(double) * 3 * batch));
+	K9_TRY(cudaMemcpyAsync(d_s, sources, sb, cudaMemcpyHostToDevice, c->stream));
+	K9_TRY(cudaMemcpyAsync(d_t, targets, tb, cudaMemcpyHostToDevice, c->stream));
+	K9_TRY(cudaMemsetAsync(d_e, 0, eb, c->stream));
+
+	BatchParams p;
+	p.sources = d_s; p.targets = d_t; p.batch = batch; p.n = n; p.m = m;
+	p.max_iter = params->max_iter; p.stop_early = params->stop_early; p.mode = params->dist_mode;
+	p.sentinel = params->sentinel; p.tol = params->tol;
+	p.thr0 = (params->dist_mode == ICPB_DIST_SQRT) ? sqrt_threshold_host(params->sentinel) : params->sentinel;
+	p.errors = d_e; p.iterations = d_it; p.iterations_run = d_run; p.R = d_R; p.t = d_tt; p.idx = nullptr;
+	const int mpad = ((m + K9_TRK - 1) / K9_TRK) * K9_TRK;
+	const size_t smem = sizeof(float) * 3 * (size_t)(mpad + 4);
+	auto kern = (params->dist_mode == ICPB_DIST_SQRT) ? icp_batched_kernel<ICPB_DIST_SQRT> : icp_batched_kernel<ICPB_DIST_SQ>;
+	K9_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	K9_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K9_THREADS, smem));
+	if (per_sm < 1) per_sm = 1;
+	int grid = c->sm_count * per_sm;
+	if (grid > batch) grid = batch;
+	K9_TRY(cudaEventRecord(c->ev[2], c->stream));
+	kern<<<grid, K9_THREADS, smem, c->stream>>>(p);
+	c->launches++;
+	K9_TRY(cudaGetLastError());
+	K9_TRY(cudaEventRecord(c->ev[3], c->stream));
+	K9_TRY(cudaMemcpyAsync(errors, d_e, eb, cudaMemcpyDeviceToHost, c->stream));
+	K9_TRY(cudaMemcpyAsync(iterations, d_it, sizeof(int) * batch, cudaMemcpyDeviceToHost, c->stream));
+	K9_TRY(cudaMemcpyAsync(R, d_R, sizeof(double) * 9 * batch, cudaMemcpyDeviceToHost, c->stream));
+	K9_TRY(cudaMemcpyAsync(t, d_tt, sizeof(double) * 3 * batch, cudaMemcpyDeviceToHost, c->stream));
+	K9_TRY(cudaStreamSynchronize(c->stream));
+	if (elapsed_ms) K9_TRY(cudaEventElapsedTime(elapsed_ms, c->ev[2], c->ev[3]));
+#undef K9_TRY
+	cleanup();
+	return ICPB_OK;
+}

@@ -10,5 +10,4 @@ int launch_match_grid(Ctx* c, int, float) { snprintf(c->err, sizeof c->err, "ICP
 }
 using namespace icpb;
 extern "C" {
-int icpb_run_batched(icpb_ctx* ctx, const icpb_params*, int, const float*, int, const float*, int, float*, int*, double*, double*, float*) { return ctx ? ICPB_ERR_STATE : ICPB_ERR_BADARG; }
 }

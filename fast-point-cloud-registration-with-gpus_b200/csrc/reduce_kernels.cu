@@ -15,6 +15,7 @@
 // atomics). Moments are raw sums (sum p, sum q, sum q p^T, N) in FP64 so that shards of several GPUs
 // can be combined with one ncclAllReduce; centring is done afterwards: W = sum q p^T - N qbar pbar^T.
 #include "common.cuh"
+#include "solve_device.cuh"
 
 namespace icpb {
 
@@ -66,131 +67,6 @@ template <int NV> __device__ __forceinline__ bool last_block_sum(double* partial
 	if (threadIdx.x == 0) *ticket = 0;
 	__syncthreads();
 	return true;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: R = U V^T from W by one-sided Jacobi in FP64 registers, T = qbar - R pbar.
-// ------------------------------------------------------------------------------------------------
-__device__ void polar_rotation(const double W[9] /*col-major*/, double R[9])
-{
-	double a[3][3], v[3][3];
-#pragma unroll
-	for (int i = 0; i < 3; i++)
-#pragma unroll
-		for (int j = 0; j < 3; j++) { a[i][j] = W[i + 3 * j]; v[i][j] = (i == j) ? 1.0 : 0.0; }
-	for (int sweep = 0; sweep < 60; sweep++) {
-		double off = 0.0;
-#pragma unroll
-		for (int pq = 0; pq < 3; pq++) {
-			const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
-			double alpha = 0, beta = 0, gamma = 0;
-#pragma unroll
-			for (int i = 0; i < 3; i++) { alpha += a[i][p] * a[i][p]; beta += a[i][q] * a[i][q]; gamma += a[i][p] * a[i][q]; }
-			if (gamma == 0.0) continue;
-			const double lim = fabs(gamma) / sqrt(alpha * beta);
-			if (lim > off) off = lim;
-			if (lim < 1e-17) continue;
-			const double zeta = (beta - alpha) / (2.0 * gamma);
-			const double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-			const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-#pragma unroll
-			for (int i = 0; i < 3; i++) {
-				double x = a[i][p], y = a[i][q]; a[i][p] = c * x - s * y; a[i][q] = s * x + c * y;
-				x = v[i][p]; y = v[i][q]; v[i][p] = c * x - s * y; v[i][q] = s * x + c * y;
-			}
-		}
-		if (off < 1e-16) break;
-	}
-	double u[3][3], sv[3];
-#pragma unroll
-	for (int j = 0; j < 3; j++) {
-		sv[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
-#pragma unroll
-		for (int i = 0; i < 3; i++) u[i][j] = (sv[j] > 0) ? a[i][j] / sv[j] : 0.0;
-	}
-	int small = 0;
-	if (sv[1] < sv[small]) small = 1;
-	if (sv[2] < sv[small]) small = 2;
-	const double big = fmax(sv[0], fmax(sv[1], sv[2]));
-	if (sv[small] <= 1e-14 * big) {   // rank-deficient W: complete the basis (never on the reference's inputs)
-		const int j1 = (small + 1) % 3, j2 = (small + 2) % 3;
-		u[0][small] = u[1][j1] * u[2][j2] - u[2][j1] * u[1][j2];
-		u[1][small] = u[2][j1] * u[0][j2] - u[0][j1] * u[2][j2];
-		u[2][small] = u[0][j1] * u[1][j2] - u[1][j1] * u[0][j2];
-	}
-#pragma unroll
-	for (int i = 0; i < 3; i++)
-#pragma unroll
-		for (int j = 0; j < 3; j++) R[i + 3 * j] = u[i][0] * v[j][0] + u[i][1] * v[j][1] + u[i][2] * v[j][2];
-}
-
-__device__ void compose_total(IterState* st)
-{
-	double Rn[9], tn[3];
-	for (int c = 0; c < 3; c++)
-		for (int r = 0; r < 3; r++)
-			Rn[r + 3 * c] = (double)st->R[r] * st->Rtot[3 * c] + (double)st->R[r + 3] * st->Rtot[1 + 3 * c] + (double)st->R[r + 6] * st->Rtot[2 + 3 * c];
-	for (int r = 0; r < 3; r++)
-		tn[r] = (double)st->R[r] * st->ttot[0] + (double)st->R[r + 3] * st->ttot[1] + (double)st->R[r + 6] * st->ttot[2] + (double)st->T[r];
-	for (int k = 0; k < 9; k++) st->Rtot[k] = Rn[k];
-	for (int k = 0; k < 3; k++) st->ttot[k] = tn[k];
-}
-
-// point-to-point: moments[0..15] -> R, T                                   (one thread)
-__device__ void solve_p2p(IterState* st)
-{
-	const double* mom = st->moments;
-	const double N = mom[15];
-	double pb[3], qb[3], W[9], R[9];
-	for (int c = 0; c < 3; c++) { pb[c] = mom[c] / N; qb[c] = mom[3 + c] / N; }
-	for (int c = 0; c < 3; c++)
-		for (int r = 0; r < 3; r++) W[r + 3 * c] = mom[6 + r + 3 * c] - N * qb[r] * pb[c];
-	polar_rotation(W, R);
-	for (int k = 0; k < 9; k++) st->R[k] = (float)R[k];
-	for (int r = 0; r < 3; r++) st->T[r] = (float)(qb[r] - (R[r] * pb[0] + R[r + 3] * pb[1] + R[r + 6] * pb[2]));
-	compose_total(st);
-}
-
-// point-to-plane: moments[0..20] = upper triangle of C (row by row), [21..26] = b, [27] = N.
-// Cholesky C = U^T U in FP64 on the float-rounded sums, two triangular solves, then the reference's
-// host code: float cos/sin of the solution, R = Rz(g) Ry(b) Rx(a) in float (src/ICP_point_to_plane.cu:585-593).
-__device__ void solve_p2plane(IterState* st)
-{
-	double C[6][6], U[6][6], b[6], y[6], x[6];
-	int k = 0;
-	for (int r = 0; r < 6; r++)
-		for (int c = r; c < 6; c++) C[r][c] = (double)(float)st->moments[k++];
-	for (int r = 0; r < 6; r++) b[r] = (double)(float)st->moments[21 + r];
-	for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) U[r][c] = 0.0;
-	for (int j = 0; j < 6; j++) {
-		double s = C[j][j];
-		for (int q = 0; q < j; q++) s -= U[q][j] * U[q][j];
-		if (!(s > 0.0)) { st->numeric_error = j + 1; st->done = 1; return; }
-		U[j][j] = sqrt(s);
-		for (int i = j + 1; i < 6; i++) {
-			double t = C[j][i];
-			for (int q = 0; q < j; q++) t -= U[q][j] * U[q][i];
-			U[j][i] = t / U[j][j];
-		}
-	}
-	for (int i = 0; i < 6; i++) { double t = b[i]; for (int q = 0; q < i; q++) t -= U[q][i] * y[q]; y[i] = t / U[i][i]; }
-	for (int i = 5; i >= 0; i--) { double t = y[i]; for (int q = i + 1; q < 6; q++) t -= U[i][q] * x[q]; x[i] = t / U[i][i]; }
-	float hb[6];
-	for (int i = 0; i < 6; i++) hb[i] = (float)x[i];
-	const float cx = (float)cos((double)hb[0]), cy = (float)cos((double)hb[1]), cz = (float)cos((double)hb[2]);
-	const float sx = (float)sin((double)hb[0]), sy = (float)sin((double)hb[1]), sz = (float)sin((double)hb[2]);
-	float* R = st->R;
-	R[0] = __fmul_rn(cy, cz);
-	R[3] = __fsub_rn(__fmul_rn(__fmul_rn(cz, sx), sy), __fmul_rn(cx, sz));
-	R[6] = __fadd_rn(__fmul_rn(__fmul_rn(cx, cz), sy), __fmul_rn(sx, sz));
-	R[1] = __fmul_rn(cy, sz);
-	R[4] = __fadd_rn(__fmul_rn(cx, cz), __fmul_rn(__fmul_rn(sx, sy), sz));
-	R[7] = __fsub_rn(__fmul_rn(__fmul_rn(cx, sy), sz), __fmul_rn(cz, sx));
-	R[2] = -sy;
-	R[5] = __fmul_rn(cy, sx);
-	R[8] = __fmul_rn(cx, cy);
-	st->T[0] = hb[3]; st->T[1] = hb[4]; st->T[2] = hb[5];
-	compose_total(st);
 }
 
 __global__ void solve_kernel(IterState* st, int metric)

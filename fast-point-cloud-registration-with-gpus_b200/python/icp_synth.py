@@ -45,3 +45,45 @@ def p2p_clouds(width, npts=None):
     D = source(width, npts)
     M = rigid_move(D, euler_matrix([0.2, -0.2, 0.05]), [0.8, -0.3, 0.2])
     return D, M
+
+
+# ---- BASELINE.json config 5: batched independent pairs ---------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(state):
+    """One step of splitmix64 on an array of uint64 states -> (new_state, output)."""
+    with np.errstate(over="ignore"):
+        state = state + np.uint64(0x9E3779B97F4A7C15)
+        z = state.copy()
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return state, z
+
+
+def batched_poses(batch, seed=20240):
+    """Pose of pair b from the counter-based generator: stream b of splitmix64(seed): r = 0.2*u, u in U(-1,1)^3;
+    t = (0.8,-0.3,0.2) * (0.5 + 0.5 v), v in U(0,1)^3."""
+    state = (np.uint64(seed) << np.uint64(32)) | np.arange(batch, dtype=np.uint64)
+    draws = []
+    for _ in range(6):
+        state, z = _splitmix64(state)
+        draws.append((z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0))
+    u = np.stack(draws[:3], axis=1) * 2.0 - 1.0
+    v = np.stack(draws[3:], axis=1)
+    r = (0.2 * u).astype(np.float32)
+    t = (np.array([0.8, -0.3, 0.2]) * (0.5 + 0.5 * v)).astype(np.float32)
+    return r, t
+
+
+def batched_pairs(batch, n=2048, width=46, seed=20240):
+    """sources [batch,n,3] (first n points of the width x width saddle, identical for every pair) and
+    targets [batch,n,3] (each moved by its own pose)."""
+    D = source(width, n)
+    r, t = batched_poses(batch, seed)
+    S = np.ascontiguousarray(np.broadcast_to(D, (batch, n, 3)))
+    T = np.empty((batch, n, 3), np.float32)
+    for b in range(batch):
+        T[b] = rigid_move(D, euler_matrix(r[b]), t[b])
+    return S, T, r, t
