@@ -52,6 +52,8 @@ struct K1Params {
 	float        thr0;                                    // initial threshold in the squared-distance domain
 	float        sentinel;
 	const int*   done;
+	const int*   remap;                                   // optional: process sources remap[0..*count_dev) only (grid fallback)
+	const int*   count_dev;
 };
 
 struct ReduceParams {
@@ -125,6 +127,9 @@ struct Ctx {
 	int     grid_dim[3] = {0, 0, 0};
 	float   grid_origin[3] = {0, 0, 0};
 	float   grid_cell = 0.f;
+	int*    grid_open_list = nullptr;   // sources the grid search left open (finished by brute force)
+	int     grid_open_cap = 0;
+	unsigned long long* grid_counters = nullptr;   // [0] open sources of the last pass, [1] candidates visited
 
 	// source (this rank's shard)
 	int n = 0, n_cap = 0;        // n_cap: padded capacity

@@ -222,7 +222,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4);
+	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters);
 	if (c->st_host) cudaFreeHost(c->st_host);
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	for (int k = 0; k < 4; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);

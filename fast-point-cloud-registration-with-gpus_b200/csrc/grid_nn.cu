@@ -1,0 +1,292 @@
+// grid_nn.cu — K1g: exact nearest neighbour through a uniform grid over the (static) target cloud.
+//
+// Same contract as K1 (`Matching`, src/ICP_point_to_point.cu:31-57): idx[i] = argmin_j d(P_i,Q_j) with the
+// reference's distance chain, the LOWEST index on ties, nothing for a source with no target below the
+// sentinel — so the indices are identical to the brute-force kernel's, bit for bit.
+//
+//  build (once per target):  bounding box -> cell size h (<= ~4 cells per point, <= 16M cells) ->
+//      counting sort of the targets by cell (histogram, exclusive scan, scatter); sorted points are stored
+//      as float4 {x, y, z, original index}.
+//  query (one thread per source): visit the cells of Chebyshev ring r = 0,1,2 around the source's cell,
+//      whole x-rows at a time (a row is one contiguous range of the sorted array). Candidates are compared
+//      as 64-bit keys (distance bits << 32 | index), i.e. by (distance, index) — independent of the visiting
+//      order. After ring r every unvisited target is at least r*h away, so the search stops once
+//      best < (r*h)^2 * 0.998 (the margin covers float rounding of the chain and of the cell assignment).
+//  fallback: sources still open after ring GRID_RMAX (far from the cloud, e.g. the first ICP iterations)
+//      are appended to a compact list and finished by the brute-force K1 kernel through its `remap`
+//      path (device-side count, no host round trip). Both paths are exact, so their union is.
+#include "common.cuh"
+#include "k1_device.cuh"
+#include <cmath>
+
+namespace icpb {
+
+constexpr int GRID_RMAX = 2;
+
+__device__ __forceinline__ unsigned f2ord(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void grid_bbox_kernel(const float4* __restrict__ q4, int m, unsigned* mm /* [6] min xyz, max xyz (ordered ints) */)
+{
+	float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+		const float4 q = q4[j];
+		lo[0] = fminf(lo[0], q.x); lo[1] = fminf(lo[1], q.y); lo[2] = fminf(lo[2], q.z);
+		hi[0] = fmaxf(hi[0], q.x); hi[1] = fmaxf(hi[1], q.y); hi[2] = fmaxf(hi[2], q.z);
+	}
+	for (int k = 0; k < 3; k++) {
+		for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+		if ((threadIdx.x & 31) == 0) { atomicMin(mm + k, f2ord(lo[k])); atomicMax(mm + 3 + k, f2ord(hi[k])); }
+	}
+}
+
+struct GridGeom { float ox, oy, oz, inv_h, h; int nx, ny, nz; };
+
+__device__ __forceinline__ int cell_coord(float v, float o, float inv_h) { return (int)floorf((v - o) * inv_h); }
+
+__global__ void grid_count_kernel(const float4* __restrict__ q4, int m, GridGeom g, int* __restrict__ counts, int* __restrict__ cell_of)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	const float4 q = q4[j];
+	int cx = min(max(cell_coord(q.x, g.ox, g.inv_h), 0), g.nx - 1);
+	int cy = min(max(cell_coord(q.y, g.oy, g.inv_h), 0), g.ny - 1);
+	int cz = min(max(cell_coord(q.z, g.oz, g.inv_h), 0), g.nz - 1);
+	const int c = cx + g.nx * (cy + g.ny * cz);
+	cell_of[j] = c;
+	atomicAdd(counts + c, 1);
+}
+
+// exclusive scan of `n` ints in three passes (1024 elements per block)
+__global__ void scan_block_kernel(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ block_sums, int n)
+{
+	__shared__ int sh[1024];
+	const int i = blockIdx.x * 1024 + threadIdx.x;
+	const int v = (i < n) ? in[i] : 0;
+	sh[threadIdx.x] = v;
+	__syncthreads();
+	for (int o = 1; o < 1024; o <<= 1) {
+		const int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+		__syncthreads();
+		sh[threadIdx.x] += t;
+		__syncthreads();
+	}
+	if (i < n) out[i] = sh[threadIdx.x] - v;
+	if (threadIdx.x == 1023) block_sums[blockIdx.x] = sh[1023];
+}
+__global__ void scan_sums_kernel(int* block_sums, int nb)
+{
+	// single block: sequential chunks of 1024 with a running carry
+	__shared__ int sh[1024];
+	__shared__ int carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < nb; base += 1024) {
+		const int i = base + threadIdx.x;
+		const int v = (i < nb) ? block_sums[i] : 0;
+		sh[threadIdx.x] = v;
+		__syncthreads();
+		for (int o = 1; o < 1024; o <<= 1) {
+			const int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+			__syncthreads();
+			sh[threadIdx.x] += t;
+			__syncthreads();
+		}
+		if (i < nb) block_sums[i] = carry + sh[threadIdx.x] - v;
+		__syncthreads();
+		if (threadIdx.x == 0) carry += sh[1023];
+		__syncthreads();
+	}
+}
+__global__ void scan_add_kernel(int* out, const int* __restrict__ block_sums, int n, int total_slot)
+{
+	const int i = blockIdx.x * 1024 + threadIdx.x;
+	if (i < n) out[i] += block_sums[blockIdx.x];
+	(void)total_slot;
+}
+__global__ void grid_scatter_kernel(const float4* __restrict__ q4, int m, const int* __restrict__ cell_of, const int* __restrict__ cell_start,
+                                    int* __restrict__ fill, float4* __restrict__ sorted4)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	const int c = cell_of[j];
+	const int pos = cell_start[c] + atomicAdd(fill + c, 1);
+	float4 q = q4[j];
+	q.w = __int_as_float(j);
+	sorted4[pos] = q;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) grid_query_kernel(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz, int n,
+                                                         const float4* __restrict__ sorted4, const int* __restrict__ cell_start, GridGeom g, float thr0,
+                                                         u64* __restrict__ keys, int* __restrict__ open_list, int* __restrict__ open_count,
+                                                         unsigned long long* __restrict__ visited, const int* done)
+{
+	if (done != nullptr && *done) return;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long seen = 0;
+	if (i < n) {
+		const float x = px[i], y = py[i], z = pz[i];
+		const int cx = cell_coord(x, g.ox, g.inv_h), cy = cell_coord(y, g.oy, g.inv_h), cz = cell_coord(z, g.oz, g.inv_h);
+		u64 best = KEY_UNMATCHED;
+		bool resolved = false;
+		const int rcover = max(max(max(cx, g.nx - 1 - cx), max(cy, g.ny - 1 - cy)), max(cz, g.nz - 1 - cz));   // ring that covers the whole grid
+		for (int r = 0; r <= GRID_RMAX && !resolved; r++) {
+			for (int dz = -r; dz <= r; dz++) {
+				const int zc = cz + dz;
+				if (zc < 0 || zc >= g.nz) continue;
+				for (int dy = -r; dy <= r; dy++) {
+					const int yc = cy + dy;
+					if (yc < 0 || yc >= g.ny) continue;
+					const bool shell = (abs(dz) == r) || (abs(dy) == r);
+					// shell rows: every x in [cx-r, cx+r]; interior rows: only the two end cells
+					for (int part = 0; part < (shell ? 1 : 2); part++) {
+						int x0 = shell ? cx - r : (part == 0 ? cx - r : cx + r);
+						int x1 = shell ? cx + r : x0;
+						if (!shell && r == 0) continue;
+						x0 = max(x0, 0); x1 = min(x1, g.nx - 1);
+						if (x0 > x1) continue;
+						const int row = g.nx * (yc + g.ny * zc);
+						const int k0 = cell_start[row + x0], k1 = cell_start[row + x1 + 1];
+						for (int k = k0; k < k1; k++) {
+							const float4 q = __ldg(sorted4 + k);
+							float d = dist_chain(x, y, z, q.x, q.y, q.z);
+							if (d < thr0) {
+								if (MODE == ICPB_DIST_SQRT) d = __fsqrt_rn(d);
+								const u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(uint32_t)__float_as_int(q.w);
+								if (key < best) best = key;
+							}
+						}
+						seen += (unsigned long long)(k1 - k0);
+					}
+				}
+			}
+			if (best != KEY_UNMATCHED) {
+				float bd = __uint_as_float((uint32_t)(best >> 32));
+				if (MODE == ICPB_DIST_SQRT) bd = bd * bd;
+				const float reach = (float)r * g.h;
+				if (bd < reach * reach * 0.998f) resolved = true;
+			}
+			if (r >= rcover) resolved = true;       // every cell of the grid has been visited
+		}
+		if (resolved) { if (best != KEY_UNMATCHED) keys[i] = best; }
+		else open_list[atomicAdd(open_count, 1)] = i;
+	}
+	for (int o = 16; o > 0; o >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, o);
+	if ((threadIdx.x & 31) == 0 && seen) atomicAdd(visited, seen);
+}
+
+int launch_match_brute_remap(Ctx* c, int dist_mode, float sentinel, const int* remap, const int* count_dev);
+
+static int build_grid(Ctx* c)
+{
+	const int m = c->m;
+	unsigned* mm = nullptr;
+	ICPB_CUDA(c, cudaMalloc((void**)&mm, 6 * sizeof(unsigned)));
+	unsigned init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+	ICPB_CUDA(c, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+	grid_bbox_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->q4, m, mm);
+	c->launches++;
+	unsigned h_mm[6];
+	ICPB_CUDA(c, cudaMemcpyAsync(h_mm, mm, sizeof h_mm, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(mm);
+	auto dec = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
+	float lo[3], hi[3], ext[3];
+	for (int k = 0; k < 3; k++) { lo[k] = dec(h_mm[k]); hi[k] = dec(h_mm[3 + k]); ext[k] = fmaxf(hi[k] - lo[k], 1e-6f); }
+	double cells_max = fmin(fmax(4.0 * m, 4096.0), 16.0 * 1024 * 1024);
+	double h = cbrt((double)ext[0] * ext[1] * ext[2] / cells_max);
+	// flat clouds: never let one axis explode the cell count
+	for (int it = 0; it < 8; it++) {
+		double cells = (floor(ext[0] / h) + 1) * (floor(ext[1] / h) + 1) * (floor(ext[2] / h) + 1);
+		if (cells <= cells_max) break;
+		h *= 1.26;
+	}
+	GridGeom g;
+	g.h = (float)h; g.inv_h = (float)(1.0 / h);
+	g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+	g.nx = (int)floor(ext[0] / h) + 1; g.ny = (int)floor(ext[1] / h) + 1; g.nz = (int)floor(ext[2] / h) + 1;
+	const size_t ncell = (size_t)g.nx * g.ny * g.nz;
+	c->grid_dim[0] = g.nx; c->grid_dim[1] = g.ny; c->grid_dim[2] = g.nz;
+	c->grid_origin[0] = g.ox; c->grid_origin[1] = g.oy; c->grid_origin[2] = g.oz; c->grid_cell = g.h;
+
+	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); c->grid_cell_start = nullptr; c->grid_sorted4 = nullptr;
+	int *counts = nullptr, *cell_of = nullptr, *sums = nullptr;
+	const int nb = (int)((ncell + 1 + 1023) / 1024);
+	ICPB_CUDA(c, cudaMalloc((void**)&c->grid_cell_start, sizeof(int) * (ncell + 1)));
+	ICPB_CUDA(c, cudaMalloc((void**)&c->grid_sorted4, sizeof(float4) * (size_t)m));
+	ICPB_CUDA(c, cudaMalloc((void**)&counts, sizeof(int) * (ncell + 1)));
+	ICPB_CUDA(c, cudaMalloc((void**)&cell_of, sizeof(int) * (size_t)m));
+	ICPB_CUDA(c, cudaMalloc((void**)&sums, sizeof(int) * (size_t)nb));
+	ICPB_CUDA(c, cudaMemsetAsync(counts, 0, sizeof(int) * (ncell + 1), c->stream));
+	grid_count_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->q4, m, g, counts, cell_of);
+	scan_block_kernel<<<nb, 1024, 0, c->stream>>>(counts, c->grid_cell_start, sums, (int)(ncell + 1));
+	scan_sums_kernel<<<1, 1024, 0, c->stream>>>(sums, nb);
+	scan_add_kernel<<<nb, 1024, 0, c->stream>>>(c->grid_cell_start, sums, (int)(ncell + 1), 0);
+	ICPB_CUDA(c, cudaMemsetAsync(counts, 0, sizeof(int) * (ncell + 1), c->stream));
+	grid_scatter_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->q4, m, cell_of, c->grid_cell_start, counts, c->grid_sorted4);
+	c->launches += 5;
+	ICPB_CUDA(c, cudaGetLastError());
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(counts); cudaFree(cell_of); cudaFree(sums);
+	if (!c->grid_open_list || c->grid_open_cap < c->n_cap) {
+		cudaFree(c->grid_open_list); c->grid_open_list = nullptr;
+		ICPB_CUDA(c, cudaMalloc((void**)&c->grid_open_list, sizeof(int) * (size_t)(c->n_cap > 0 ? c->n_cap : 1)));
+		c->grid_open_cap = c->n_cap;
+	}
+	if (!c->grid_counters) ICPB_CUDA(c, cudaMalloc((void**)&c->grid_counters, 4 * sizeof(unsigned long long)));
+	ICPB_CUDA(c, cudaMemsetAsync(c->grid_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+	c->grid_ready = true;
+	return ICPB_OK;
+}
+
+int launch_match_grid(Ctx* c, int dist_mode, float sentinel)
+{
+	if (dist_mode == ICPB_DIST_STD) { snprintf(c->err, sizeof c->err, "ICPB_NN_GRID supports ICPB_DIST_SQ and ICPB_DIST_SQRT"); return ICPB_ERR_BADARG; }
+	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
+	int rc;
+	if (!c->grid_ready || c->grid_open_cap < c->n_cap) { if ((rc = build_grid(c)) != ICPB_OK) return rc; }
+	GridGeom g;
+	g.h = c->grid_cell; g.inv_h = (float)(1.0 / (double)c->grid_cell);
+	g.ox = c->grid_origin[0]; g.oy = c->grid_origin[1]; g.oz = c->grid_origin[2];
+	g.nx = c->grid_dim[0]; g.ny = c->grid_dim[1]; g.nz = c->grid_dim[2];
+	float thr0 = sentinel;
+	if (dist_mode == ICPB_DIST_SQRT) {
+		float y = sentinel * sentinel;
+		if (!std::isinf(y)) {
+			while (sqrtf(y) < sentinel) y = nextafterf(y, INFINITY);
+			while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
+		}
+		thr0 = y;
+	}
+	int* open_count = reinterpret_cast<int*>(c->grid_counters);                    // [0] low word: open sources of this pass
+	unsigned long long* visited = c->grid_counters + 1;                           // [1] candidates visited (cumulative)
+	ICPB_CUDA(c, cudaMemsetAsync(open_count, 0, sizeof(unsigned long long), c->stream));
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? grid_query_kernel<ICPB_DIST_SQRT> : grid_query_kernel<ICPB_DIST_SQ>;
+	kern<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->px, c->py, c->pz, c->n, c->grid_sorted4, c->grid_cell_start, g, thr0, c->keys,
+	                                                 c->grid_open_list, open_count, visited, &c->st->done);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	c->pairs_acc += (double)c->n * (double)c->m;
+	// sources the grid could not close within GRID_RMAX rings: exact brute force over that compact list
+	return launch_match_brute_remap(c, dist_mode, sentinel, c->grid_open_list, open_count);
+}
+
+} // namespace icpb
+
+extern "C" int icpb_get_grid_stats(icpb_ctx* ctx, double* candidates_visited, int* last_open_sources, int dims[3], float* cell)
+{
+	using namespace icpb;
+	if (!ctx) return ICPB_ERR_BADARG;
+	Ctx* c = reinterpret_cast<Ctx*>(ctx);
+	ICPB_CUDA(c, cudaSetDevice(c->device));
+	if (!c->grid_ready) { snprintf(c->err, sizeof c->err, "no grid: run a matching step with ICPB_NN_GRID first"); return ICPB_ERR_STATE; }
+	unsigned long long h[2];
+	ICPB_CUDA(c, cudaMemcpyAsync(h, c->grid_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (candidates_visited) *candidates_visited = (double)h[1];
+	if (last_open_sources) *last_open_sources = (int)(h[0] & 0xffffffffull);
+	if (dims) { dims[0] = c->grid_dim[0]; dims[1] = c->grid_dim[1]; dims[2] = c->grid_dim[2]; }
+	if (cell) *cell = c->grid_cell;
+	return ICPB_OK;
+}

@@ -53,8 +53,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 	float* ring = reinterpret_cast<float*>(k1_smem);
 
 	const int tid = threadIdx.x;
-	const long long u0 = (p.units * (long long)blockIdx.x) / gridDim.x;
-	const long long u1 = (p.units * (long long)(blockIdx.x + 1)) / gridDim.x;
+	int n_eff = p.n;
+	long long units = p.units;
+	if (p.count_dev != nullptr) {            // compact source list whose length is only known on the device
+		n_eff = *p.count_dev;
+		units = (long long)((n_eff + SB - 1) / SB) * p.nt;
+	}
+	const long long u0 = (units * (long long)blockIdx.x) / gridDim.x;
+	const long long u1 = (units * (long long)(blockIdx.x + 1)) / gridDim.x;
 	if (u0 >= u1) return;
 
 	if (tid == 0) {
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 		for (int s = 0; s < S; s++) {
 			const int i = sb * SB + s * THREADS + tid;
 			const int bs = get_best(s);
-			if (i < p.n && bs >= 0) {
+			if (i < n_eff && bs >= 0) {
 				const float th = get_thr(s);
 				const float* gx = p.qtiles + (size_t)(bs / SUBS) * 3 * K1_TT + (size_t)(bs % SUBS) * K1_TRK;
 				const float4* X4 = reinterpret_cast<const float4*>(gx);
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 				}
 				if (found >= 0) {
 					const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * K1_TRK + found);
-					atomicMin(p.keys + i, key);
+					atomicMin(p.keys + (p.remap != nullptr ? p.remap[i] : i), key);
 				}
 			}
 		}
@@ -129,7 +135,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_match(const K1Params p)
 #pragma unroll
 			for (int s = 0; s < S; s++) {
 				const int i = sb * SB + s * THREADS + tid;
-				sx[s] = p.px[i]; sy[s] = p.py[i]; sz[s] = p.pz[i];
+				int gi = i;                                   // identity: the arrays are padded to a block multiple
+				if (p.remap != nullptr) gi = (i < n_eff) ? p.remap[i] : 0;
+				sx[s] = p.px[gi]; sy[s] = p.py[gi]; sz[s] = p.pz[gi];
 				m[s] = p.thr0; set_thr(s, p.thr0); set_best(s, -1);
 			}
 			cur_sb = sb;
@@ -301,17 +309,18 @@ int launch_key_reset(Ctx* c)
 	return ICPB_OK;
 }
 
-int launch_match_brute(Ctx* c, int dist_mode, float sentinel)
+static int launch_match_brute_impl(Ctx* c, int dist_mode, float sentinel, const int* remap, const int* count_dev)
 {
 	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
 	K1Params p;
+	p.remap = remap; p.count_dev = count_dev;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
 	p.qtiles = c->qtiles; p.keys = c->keys;
 	p.n = c->n; p.nt = c->nt; p.units = 0;
 	p.sentinel = sentinel;
 	p.thr0 = (dist_mode == ICPB_DIST_SQRT) ? sqrt_domain_threshold(sentinel) : sentinel;
 	p.done = &c->st->done;
-	c->pairs_acc += (double)c->n * (double)c->m;
+	if (remap == nullptr) c->pairs_acc += (double)c->n * (double)c->m;
 	if (dist_mode == ICPB_DIST_STD) {
 		k1_match_std<<<(c->n + 127) / 128, 128, 0, c->stream>>>(p);
 		c->launches++;
@@ -324,6 +333,12 @@ int launch_match_brute(Ctx* c, int dist_mode, float sentinel)
 #undef X
 	default: return launch_cfg<8, 256, 2, 0>(c, dist_mode, p);
 	}
+}
+
+int launch_match_brute(Ctx* c, int dist_mode, float sentinel) { return launch_match_brute_impl(c, dist_mode, sentinel, nullptr, nullptr); }
+int launch_match_brute_remap(Ctx* c, int dist_mode, float sentinel, const int* remap, const int* count_dev)
+{
+	return launch_match_brute_impl(c, dist_mode, sentinel, remap, count_dev);
 }
 
 } // namespace icpb

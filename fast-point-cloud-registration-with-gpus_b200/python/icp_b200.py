@@ -62,6 +62,7 @@ def _load():
         "icpb_run_batched": (C.c_int, [vp, C.POINTER(Params), C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, fp]),
         "icpb_measure_fp32_peak": (C.c_int, [vp, dp]),
         "icpb_time_match": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, C.c_int, fp, fp]),
+        "icpb_get_grid_stats": (C.c_int, [vp, dp, ip, ip, fp]),
         "icpb_launch_count": (C.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -230,6 +231,11 @@ class Context:
         mean, mn = C.c_float(), C.c_float()
         self._ck(lib.icpb_time_match(self.h, dist_mode, nn_method, sentinel, reps, C.byref(mean), C.byref(mn)), "time_match")
         return mean.value, mn.value
+
+    def grid_stats(self):
+        cand, opened, dims, cell = C.c_double(), C.c_int(), (C.c_int * 3)(), C.c_float()
+        self._ck(lib.icpb_get_grid_stats(self.h, C.byref(cand), C.byref(opened), dims, C.byref(cell)), "get_grid_stats")
+        return {"candidates_visited": cand.value, "last_open_sources": opened.value, "dims": list(dims), "cell": cell.value}
 
     def launch_count(self):
         return int(lib.icpb_launch_count(self.h))

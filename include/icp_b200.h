@@ -152,6 +152,9 @@ int  icpb_measure_fp32_peak(icpb_ctx* ctx, double* tflops);
 /* Times `reps` launches of the matching step alone with CUDA events on the context's stream
  * (the protocol of src/CUDA/Matching_opt.cu:213-226); returns the mean and the minimum in ms. */
 int  icpb_time_match(icpb_ctx* ctx, int dist_mode, int nn_method, float sentinel, int reps, float* mean_ms, float* min_ms);
+/* Uniform-grid matching statistics: candidates actually visited so far (vs the N*M a brute-force pass
+ * evaluates), sources the last pass had to hand to the brute-force kernel, grid dimensions and cell size. */
+int  icpb_get_grid_stats(icpb_ctx* ctx, double* candidates_visited, int* last_open_sources, int dims[3], float* cell);
 /* Number of kernels this context has launched since creation. */
 long long icpb_launch_count(const icpb_ctx* ctx);
 
