@@ -96,7 +96,7 @@ def cpu_match_rate(orc, D, M, seconds_target, mode=0):
     return sel.shape[0] * M.shape[0] / dt, sel.shape[0], dt
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, emit):
     """The reference's CPU implementation of the path, on the box's host cores (rank 0 only)."""
     if rank != 0:
         return
@@ -150,7 +150,7 @@ def run_reference_arm(args, rank):
                                             "iterations": its, "ms": ms, "nn_pairs_per_sec": (its + 1) * 1e8 / (ms * 1e-3), "wall_s": wall}
         except Exception as e:      # noqa: BLE001
             line["reference_binary"] = {"error": str(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -167,12 +167,21 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    # Libraries (NCCL's "NCCL version ..." banner, torchrun chatter) write to fd 1; the contract is ONE JSON line on
+    # stdout, so everything else is sent to stderr and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, emit)
         return
 
     import torch
@@ -297,7 +306,7 @@ def main():
             rate, S, dt = cpu_match_rate(orc, D, M, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                                     "sample": "%d of %d sources x all %d targets, %.1f s, oracle orc_match_f32 (OpenMP)" % (S, n_total, m, dt)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -83,6 +83,7 @@ int  launch_key_reset(Ctx* c);
 int  launch_resolve(Ctx* c, float sentinel);
 int  launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel);
 int  launch_match_grid(Ctx* c, int dist_mode, float sentinel);
+int  launch_match_filter(Ctx* c, int dist_mode, float sentinel);
 int  launch_moments(Ctx* c, int metric);
 int  launch_solve(Ctx* c, int metric);
 int  launch_transform(Ctx* c);
@@ -139,6 +140,16 @@ struct Ctx {
 	float* dmin = nullptr;       // winning distance per source (icpb_match / icpb_time_match)
 	float* stage_xyz = nullptr;  // device AoS staging for H2D/D2H
 	size_t stage_cap = 0;
+
+	// K1F: lower-bound filter data of the target (nn_filter.cu)
+	bool    kf_ready = false;
+	float*  kf_tiles7 = nullptr;        // [nt][X Y Z | Xc Yc Zc W][512]
+	float   kf_center[3] = {0, 0, 0};
+	float   kf_rq = 0.f;                // >= max |q - centre|
+	int     kf_nt = 0;
+	unsigned long long* kf_stats = nullptr;
+	bool    kf_use_seed = true;         // warm start from the previous correspondences
+	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)
 
 	// iteration state
 	IterState* st = nullptr;     // device

@@ -77,7 +77,7 @@ static int check_params(Ctx* c, const icpb_params* p)
 	if (p->max_iter < 1 || p->max_iter > (1 << 20)) return fail(c, ICPB_ERR_BADARG, "max_iter out of range");
 	if (p->metric != ICPB_POINT_TO_POINT && p->metric != ICPB_POINT_TO_PLANE) return fail(c, ICPB_ERR_BADARG, "unknown metric");
 	if (p->dist_mode < ICPB_DIST_SQ || p->dist_mode > ICPB_DIST_STD) return fail(c, ICPB_ERR_BADARG, "unknown dist_mode");
-	if (p->nn_method != ICPB_NN_BRUTE && p->nn_method != ICPB_NN_GRID) return fail(c, ICPB_ERR_BADARG, "unknown nn_method");
+	if (p->nn_method < ICPB_NN_BRUTE || p->nn_method > ICPB_NN_BRUTE_DIRECT) return fail(c, ICPB_ERR_BADARG, "unknown nn_method");
 	if (c->m <= 0) return fail(c, ICPB_ERR_STATE, "no target cloud: call icpb_set_target first");
 	if (c->n <= 0 && c->world == 1) return fail(c, ICPB_ERR_STATE, "no source cloud: call icpb_set_source first");
 	if (p->metric == ICPB_POINT_TO_PLANE && !c->have_normals) return fail(c, ICPB_ERR_STATE, "point-to-plane needs normals: call icpb_estimate_normals or icpb_set_normals");
@@ -140,6 +140,8 @@ static int create_common(Ctx** out, int device)
 	cudaMemset(c->st, 0, sizeof(IterState));
 	if (const char* e = getenv("ICPB_K1_CFG")) c->k1_cfg = atoi(e);
 	if (const char* e = getenv("ICPB_K1_GRID")) c->k1_grid_override = atoi(e);
+	if (const char* e = getenv("ICPB_K1_FILTER")) c->k1_use_filter = atoi(e) != 0;
+	if (const char* e = getenv("ICPB_K1_SEED")) c->kf_use_seed = atoi(e) != 0;
 	*out = c;
 	return ICPB_OK;
 }
@@ -222,7 +224,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters);
+	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_stats);
 	if (c->st_host) cudaFreeHost(c->st_host);
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	for (int k = 0; k < 4; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -260,7 +262,7 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 		if ((rc = dev_alloc(c, &c->nrm4, (size_t)0)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->nbr, (size_t)0)) != ICPB_OK) return rc;
 	}
-	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->step_state_ready = false;
+	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->step_state_ready = false;
 	const float* src = xyz;
 	if (!on_device) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)m)) != ICPB_OK) return rc;

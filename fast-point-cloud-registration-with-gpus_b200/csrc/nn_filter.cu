@@ -1,0 +1,400 @@
+// nn_filter.cu — K1F: exact brute-force matching with a rigorous lower-bound filter in front of the
+// reference's distance chain. Same contract and same bits as K1 (nn_bruteforce.cu): every (source, target)
+// pair is examined, idx[i] = argmin_j d_chain(P_i,Q_j) with the lowest j on ties.
+//
+// Why: the reference's chain costs 6 FP32-pipe operations per pair, which caps a direct evaluation at 66.7 %
+// of the FFMA peak. |p-q|^2 = |p|^2 + (|q|^2 - 2 p.q) needs only 3 FMAs per pair for the bracket
+//     e~_j = fma(ax, qx_j, fma(ay, qy_j, fma(az, qz_j, w_j))),   a = -2 (p - c),  q_j <- q_j - c,  w_j = |q_j - c|^2
+// (c = centre of the target's bounding box, removed to keep magnitudes — and hence rounding — small).
+// e~ is NOT the reference's arithmetic, so it is only used to PROVE that a sub-tile of 128 targets cannot
+// contain the answer:
+//     d_chain_j >= (|pc|^2 + e~_j - eps)(1 - 5u)      u = 2^-24, eps = u (8 Rq^2 + 10 Rp Rq + 2 Rp^2) (1.05)
+//   (Rq = max |q_j - c|, Rp = |p - c|; derivation in DESIGN.md §K1F), hence
+//     min_j e~_j  >  tau := thr (1 + 8u) - |pc|^2_lo + eps   ==>   every d_chain_j in the sub-tile > thr,
+// where thr is the running exact threshold of K1 (best exact distance so far, in the squared domain; the
+// factor 1+8u also covers the floats that sqrt.rn merges with thr in sqrt mode). Sub-tiles that fail the
+// test — the few that can hold the nearest neighbour — are evaluated by the whole warp with the exact
+// packed chain of K1 and update thr / the remembered sub-tile exactly as K1 does (strict `<` in ascending
+// sub-tile order => lowest index). thr starts from the exact distance to the previous iteration's
+// correspondence (ICP warm start; any index is a valid upper bound, so this only affects speed).
+// Everything the answer depends on is computed by the exact chain; the filter only decides what to skip.
+#include "common.cuh"
+#include "k1_device.cuh"
+#include <cmath>
+
+namespace icpb {
+
+constexpr int KF_TT     = 512;                 // targets per shared-memory tile (7 float arrays: X Y Z | Xc Yc Zc W)
+constexpr int KF_TRK    = 128;                 // filter / tracking sub-tile
+constexpr int KF_STAGES = 3;
+constexpr int KF_TILE_FLOATS = 7 * KF_TT;
+constexpr int KF_TILE_BYTES  = KF_TILE_FLOATS * 4;
+constexpr float KF_U = 5.9604644775390625e-08f;            // 2^-24
+
+struct KFParams {
+	const float* px; const float* py; const float* pz;
+	const float* tiles7;      // [nt][7][KF_TT]
+	const float4* q4;         // for the warm-start gather
+	const int*   seed_idx;    // previous correspondences (may hold anything in [0, m))
+	u64*         keys;
+	int          n, m, nt;
+	long long    units;
+	float        thr0;
+	float        cx, cy, cz;  // centre removed from both clouds for the filter quantities
+	float        rq;          // upper bound of max_j |q_j - c|
+	const int*   done;
+	unsigned long long* stats;   // [0] sub-tile x warp x source filter tests, [1] of which evaluated exactly
+};
+
+__global__ void kf_bbox_kernel(const float4* __restrict__ q4, int m, unsigned* mm)
+{
+	float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+		const float4 q = q4[j];
+		lo[0] = fminf(lo[0], q.x); lo[1] = fminf(lo[1], q.y); lo[2] = fminf(lo[2], q.z);
+		hi[0] = fmaxf(hi[0], q.x); hi[1] = fmaxf(hi[1], q.y); hi[2] = fmaxf(hi[2], q.z);
+	}
+	for (int k = 0; k < 3; k++) {
+		for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+		if ((threadIdx.x & 31) == 0) {
+			unsigned a = __float_as_uint(lo[k]); a = (a & 0x80000000u) ? ~a : (a | 0x80000000u);
+			unsigned b = __float_as_uint(hi[k]); b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+			atomicMin(mm + k, a); atomicMax(mm + 3 + k, b);
+		}
+	}
+}
+
+// tiles7 + the radius bound (max of the float chain value of |q-c|^2, as ordered uint)
+__global__ void kf_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, float cx, float cy, float cz, float* __restrict__ tiles7, unsigned* __restrict__ r2max)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m_pad) return;
+	float x = __int_as_float(0x7f800000), y = x, z = x, xc = 1e18f, yc = 1e18f, zc = 1e18f, w = 3e36f;
+	if (j < m) {
+		const float4 q = q4[j];
+		x = q.x; y = q.y; z = q.z;
+		xc = __fsub_rn(x, cx); yc = __fsub_rn(y, cy); zc = __fsub_rn(z, cz);
+		w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
+		atomicMax(r2max, __float_as_uint(w));        // w >= 0: uint order = float order
+	}
+	float* t = tiles7 + (size_t)(j / KF_TT) * KF_TILE_FLOATS + (j % KF_TT);
+	t[0] = x; t[KF_TT] = y; t[2 * KF_TT] = z; t[3 * KF_TT] = xc; t[4 * KF_TT] = yc; t[5 * KF_TT] = zc; t[6 * KF_TT] = w;
+}
+
+template <int S, int THREADS, int MODE, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
+{
+	constexpr int SB   = S * THREADS;
+	constexpr int SUBS = KF_TT / KF_TRK;
+	if (p.done != nullptr && *p.done) return;
+
+	extern __shared__ __align__(128) unsigned char kf_smem[];
+	__shared__ __align__(8) uint64_t full_bar[KF_STAGES];
+	float* ring = reinterpret_cast<float*>(kf_smem);
+	const int tid = threadIdx.x;
+	// per-thread slots behind the ring, [s][tid]: exact threshold, remembered sub-tile, original source coordinates
+	float* thr_s  = reinterpret_cast<float*>(kf_smem + (size_t)KF_STAGES * KF_TILE_BYTES + 64) + tid;
+	int*   best_s = reinterpret_cast<int*>(thr_s - tid + S * THREADS) + tid;
+	float* ox_s   = thr_s + 2 * S * THREADS;
+	float* oy_s   = thr_s + 3 * S * THREADS;
+	float* oz_s   = thr_s + 4 * S * THREADS;
+
+	const long long u0 = (p.units * (long long)blockIdx.x) / gridDim.x;
+	const long long u1 = (p.units * (long long)(blockIdx.x + 1)) / gridDim.x;
+	if (u0 >= u1) return;
+
+	if (tid == 0) {
+		for (int s = 0; s < KF_STAGES; s++) mbar_init(&full_bar[s], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	long long next_load = u0;
+	if (tid == 0) {
+		for (int k = 0; k < KF_STAGES - 1 && next_load < u1; k++, next_load++) {
+			const int t = (int)(next_load % p.nt);
+			mbar_expect_tx(&full_bar[k], KF_TILE_BYTES);
+			tma_load_1d(ring + (size_t)k * KF_TILE_FLOATS, p.tiles7 + (size_t)t * KF_TILE_FLOATS, KF_TILE_BYTES, &full_bar[k]);
+		}
+	}
+
+	float ax[S], ay[S], az[S], tau[S], kk[S];
+	int cur_sb = -1;
+	unsigned long long n_tests = 0, n_exact = 0;
+	const float inf = __int_as_float(0x7f800000);
+	const float one8u = 1.0f + 8.0f * KF_U;
+
+	auto flush = [&](int sb) {
+#pragma unroll
+		for (int s = 0; s < S; s++) {
+			const int i = sb * SB + s * THREADS + tid;
+			const int bs = best_s[s * THREADS];
+			if (i < p.n && bs >= 0) {
+				const float th = thr_s[s * THREADS];
+				const float sx = ox_s[s * THREADS], sy = oy_s[s * THREADS], sz = oz_s[s * THREADS];
+				const float* gx = p.tiles7 + (size_t)(bs / SUBS) * KF_TILE_FLOATS + (size_t)(bs % SUBS) * KF_TRK;
+				const float4* X4 = reinterpret_cast<const float4*>(gx);
+				const float4* Y4 = reinterpret_cast<const float4*>(gx + KF_TT);
+				const float4* Z4 = reinterpret_cast<const float4*>(gx + 2 * KF_TT);
+				const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
+				int found = -1;
+				for (int j = 0; j < KF_TRK / 4 && found < 0; j++) {
+					const float4 X = __ldg(X4 + j), Y = __ldg(Y4 + j), Z = __ldg(Z4 + j);
+					float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
+					float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
+					float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
+					float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
+					if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+					if (d0 <= target) found = 4 * j;
+					else if (d1 <= target) found = 4 * j + 1;
+					else if (d2 <= target) found = 4 * j + 2;
+					else if (d3 <= target) found = 4 * j + 3;
+				}
+				if (found >= 0) {
+					const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * KF_TRK + found);
+					atomicMin(p.keys + i, key);
+				}
+			}
+		}
+	};
+
+	for (long long u = u0; u < u1; u++) {
+		const int it    = (int)(u - u0);
+		const int stage = it % KF_STAGES;
+		const uint32_t parity = (uint32_t)((it / KF_STAGES) & 1);
+		const int sb = (int)(u / p.nt);
+		const int t  = (int)(u % p.nt);
+
+		if (sb != cur_sb) {
+			if (cur_sb >= 0) flush(cur_sb);
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				const int i = sb * SB + s * THREADS + tid;
+				const float x = p.px[i], y = p.py[i], z = p.pz[i];
+				ox_s[s * THREADS] = x; oy_s[s * THREADS] = y; oz_s[s * THREADS] = z;
+				const float pcx = __fsub_rn(x, p.cx), pcy = __fsub_rn(y, p.cy), pcz = __fsub_rn(z, p.cz);
+				ax[s] = -2.0f * pcx; ay[s] = -2.0f * pcy; az[s] = -2.0f * pcz;
+				const float p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
+				const float p2lo = __fmul_rd(p2, 1.0f - 8.0f * KF_U);
+				const float rp = __fmul_ru(__fsqrt_ru(p2), 1.0f + 8.0f * KF_U);
+				// eps = 1.05 u (8 Rq^2 + 10 Rp Rq + 2 Rp^2), every operation rounded up
+				float e = __fmul_ru(8.0f * p.rq, p.rq);
+				e = __fmaf_ru(10.0f * rp, p.rq, e);
+				e = __fmaf_ru(2.0f * rp, rp, e);
+				e = __fmul_ru(e, 1.05f * KF_U);
+				kk[s] = __fsub_ru(e, p2lo);
+				// warm start: exact distance to the previous correspondence is an upper bound of the minimum
+				float th = p.thr0;
+				if (p.seed_idx != nullptr && i < p.n) {
+					const int j0 = p.seed_idx[i];
+					if (j0 >= 0 && j0 < p.m) {
+						const float4 q = __ldg(p.q4 + j0);
+						const float us = dist_chain(x, y, z, q.x, q.y, q.z);
+						// strictly above the seed value so that the seed itself (or an equal, lower-indexed target) is
+						// found by the exact pass; in sqrt mode also above every float sharing its square root
+						const float up = (MODE == ICPB_DIST_SQRT) ? __fmul_ru(us, one8u) : us;
+						const float nx = __uint_as_float(__float_as_uint(up) + 1u);
+						if (us == us && nx < th) th = nx;
+					}
+				}
+				thr_s[s * THREADS] = th; best_s[s * THREADS] = -1;
+				tau[s] = __fadd_ru(__fmul_ru(th, one8u), kk[s]);
+			}
+			cur_sb = sb;
+		}
+
+		__syncthreads();
+		if (tid == 0 && next_load < u1) {
+			const int ls = (it + KF_STAGES - 1) % KF_STAGES;
+			const int lt = (int)(next_load % p.nt);
+			mbar_expect_tx(&full_bar[ls], KF_TILE_BYTES);
+			tma_load_1d(ring + (size_t)ls * KF_TILE_FLOATS, p.tiles7 + (size_t)lt * KF_TILE_FLOATS, KF_TILE_BYTES, &full_bar[ls]);
+			next_load++;
+		}
+		mbar_wait(&full_bar[stage], parity);
+
+		const float* tile = ring + (size_t)stage * KF_TILE_FLOATS;
+		const float4* X4  = reinterpret_cast<const float4*>(tile);
+		const float4* Y4  = X4 + KF_TT / 4;
+		const float4* Z4  = Y4 + KF_TT / 4;
+		const float4* XC4 = Z4 + KF_TT / 4;
+		const float4* YC4 = XC4 + KF_TT / 4;
+		const float4* ZC4 = YC4 + KF_TT / 4;
+		const float4* W4  = ZC4 + KF_TT / 4;
+
+#pragma unroll 1
+		for (int sub = 0; sub < SUBS; sub++) {
+			const int j0 = sub * (KF_TRK / 4), j1 = j0 + KF_TRK / 4;
+			float em[S];
+#pragma unroll
+			for (int s = 0; s < S; s++) em[s] = inf;
+			float4 X = XC4[j0], Y = YC4[j0], Z = ZC4[j0], W = W4[j0];
+#pragma unroll 2
+			for (int j = j0; j < j1; j++) {
+				const float4 Xn = XC4[j + 1], Yn = YC4[j + 1], Zn = ZC4[j + 1], Wn = W4[j + 1];   // stays inside the ring (+ pad)
+				const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+				const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+				const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+				const u64 w01 = pack2(W.x, W.y), w23 = pack2(W.z, W.w);
+#pragma unroll
+				for (int s = 0; s < S; s++) {
+					const u64 AX = bcast2v(ax[s]), AY = bcast2v(ay[s]), AZ = bcast2v(az[s]);
+					u64 e = fma2(AX, x01, fma2(AY, y01, fma2(AZ, z01, w01)));
+					float a, b;
+					unpack2(e, a, b);
+					em[s] = min3(em[s], a, b);
+					e = fma2(AX, x23, fma2(AY, y23, fma2(AZ, z23, w23)));
+					unpack2(e, a, b);
+					em[s] = min3(em[s], a, b);
+				}
+				X = Xn; Y = Yn; Z = Zn; W = Wn;
+			}
+			// which (warp, source) pairs cannot rule this sub-tile out?
+			unsigned need = 0;
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				const unsigned bal = __ballot_sync(0xffffffffu, em[s] <= tau[s]);
+				if (bal) need |= (1u << s);
+			}
+			n_tests += S;
+			if (need) {
+				const int gsub = t * SUBS + sub;
+#pragma unroll
+				for (int s = 0; s < S; s++) {
+					if (need & (1u << s)) {          // warp-uniform
+						n_exact += 1;
+						const float sx = ox_s[s * THREADS], sy = oy_s[s * THREADS], sz = oz_s[s * THREADS];
+						const float th = thr_s[s * THREADS];
+						const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
+						float mm = th;
+#pragma unroll 4
+						for (int j = j0; j < j1; j++) {
+							const float4 Xo = X4[j], Yo = Y4[j], Zo = Z4[j];
+							u64 dx = sub2(PX, pack2(Xo.x, Xo.y)), dy = sub2(PY, pack2(Yo.x, Yo.y)), dz = sub2(PZ, pack2(Zo.x, Zo.y));
+							u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+							float a, b;
+							unpack2(d, a, b);
+							mm = min3(mm, a, b);
+							dx = sub2(PX, pack2(Xo.z, Xo.w)); dy = sub2(PY, pack2(Yo.z, Yo.w)); dz = sub2(PZ, pack2(Zo.z, Zo.w));
+							d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+							unpack2(d, a, b);
+							mm = min3(mm, a, b);
+						}
+						if (mm < th) {
+							const float nt_ = lower_threshold<MODE>(mm);
+							thr_s[s * THREADS] = nt_; best_s[s * THREADS] = gsub;
+							tau[s] = __fadd_ru(__fmul_ru(nt_, one8u), kk[s]);
+						}
+					}
+				}
+			}
+		}
+	}
+	flush(cur_sb);
+	if (p.stats != nullptr) {
+		for (int o = 16; o > 0; o >>= 1) { n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o); n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o); }
+		if ((tid & 31) == 0) { atomicAdd(p.stats, n_tests / 32); atomicAdd(p.stats + 1, n_exact / 32); }
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static int build_filter_data(Ctx* c)
+{
+	const int m = c->m;
+	const int nt = (m + KF_TT - 1) / KF_TT;
+	unsigned* scratch = nullptr;
+	ICPB_CUDA(c, cudaMalloc((void**)&scratch, 8 * sizeof(unsigned)));
+	unsigned init[8] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u };
+	ICPB_CUDA(c, cudaMemcpyAsync(scratch, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+	kf_bbox_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->q4, m, scratch);
+	c->launches++;
+	unsigned h[8];
+	ICPB_CUDA(c, cudaMemcpyAsync(h, scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	auto dec = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
+	for (int k = 0; k < 3; k++) {
+		const float lo = dec(h[k]), hi = dec(h[3 + k]);
+		float ctr = 0.5f * lo + 0.5f * hi;
+		if (!std::isfinite(ctr)) ctr = 0.0f;       // non-finite coordinates: any centre is valid, only the bound's tightness changes
+		c->kf_center[k] = ctr;
+	}
+	cudaFree(c->kf_tiles7); c->kf_tiles7 = nullptr;
+	ICPB_CUDA(c, cudaMalloc((void**)&c->kf_tiles7, sizeof(float) * (size_t)nt * KF_TILE_FLOATS));
+	kf_pack_kernel<<<(nt * KF_TT + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * KF_TT, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_tiles7, scratch + 6);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	ICPB_CUDA(c, cudaMemcpyAsync(h, scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(scratch);
+	float r2; memcpy(&r2, &h[6], 4);
+	// Rq >= max |q - c|: the float chain value is within (1 +- 3u) of the real one
+	c->kf_rq = nextafterf(sqrtf(r2) * (1.0f + 8.0f * KF_U), INFINITY);
+	c->kf_nt = nt;
+	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 2 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 2 * sizeof(unsigned long long), c->stream)); }
+	c->kf_ready = true;
+	return ICPB_OK;
+}
+
+static float sqrt_domain_threshold_f(float sentinel)
+{
+	if (!(sentinel > 0.0f)) return 0.0f;
+	float y = sentinel * sentinel;
+	if (std::isinf(y)) return y;
+	while (sqrtf(y) < sentinel) y = nextafterf(y, INFINITY);
+	while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
+	return y;
+}
+
+int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
+{
+	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
+	int rc;
+	if (!c->kf_ready) { if ((rc = build_filter_data(c)) != ICPB_OK) return rc; }
+	// the bound needs finite magnitudes; anything else goes through the direct kernel
+	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f) return launch_match_brute(c, dist_mode, sentinel);
+	constexpr int S = 8, THREADS = 256, MINB = 2;
+	constexpr int SB = S * THREADS;
+	KFParams p;
+	p.px = c->px; p.py = c->py; p.pz = c->pz;
+	p.tiles7 = c->kf_tiles7; p.q4 = c->q4; p.seed_idx = c->kf_use_seed ? c->idx : nullptr; p.keys = c->keys;
+	p.n = c->n; p.m = c->m; p.nt = c->kf_nt;
+	const int nb = (c->n + SB - 1) / SB;
+	p.units = (long long)nb * p.nt;
+	p.thr0 = (dist_mode == ICPB_DIST_SQRT) ? sqrt_domain_threshold_f(sentinel) : sentinel;
+	p.cx = c->kf_center[0]; p.cy = c->kf_center[1]; p.cz = c->kf_center[2]; p.rq = c->kf_rq;
+	p.done = &c->st->done;
+	p.stats = c->kf_stats;
+	c->pairs_acc += (double)c->n * (double)c->m;
+	const size_t smem = (size_t)KF_STAGES * KF_TILE_BYTES + 64 + (size_t)5 * S * THREADS * 4;
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB>;
+	ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+	if (per_sm < 1) per_sm = 1;
+	long long grid = (long long)c->sm_count * per_sm;
+	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
+	if (grid > p.units) grid = p.units;
+	kern<<<(unsigned)grid, THREADS, smem, c->stream>>>(p);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+
+} // namespace icpb
+
+extern "C" int icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile_exact)
+{
+	using namespace icpb;
+	if (!ctx) return ICPB_ERR_BADARG;
+	Ctx* c = reinterpret_cast<Ctx*>(ctx);
+	ICPB_CUDA(c, cudaSetDevice(c->device));
+	unsigned long long h[2] = { 0, 0 };
+	if (c->kf_stats) {
+		ICPB_CUDA(c, cudaMemcpyAsync(h, c->kf_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	if (subtile_tests) *subtile_tests = (double)h[0];
+	if (subtile_exact) *subtile_exact = (double)h[1];
+	return ICPB_OK;
+}

@@ -13,7 +13,7 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "libicp_b200.so"))
 
 DIST_SQ, DIST_SQRT, DIST_STD = 0, 1, 2
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
-NN_BRUTE, NN_GRID = 0, 1
+NN_BRUTE, NN_GRID, NN_BRUTE_DIRECT = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -63,6 +63,7 @@ def _load():
         "icpb_measure_fp32_peak": (C.c_int, [vp, dp]),
         "icpb_time_match": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, C.c_int, fp, fp]),
         "icpb_get_grid_stats": (C.c_int, [vp, dp, ip, ip, fp]),
+        "icpb_get_filter_stats": (C.c_int, [vp, dp, dp]),
         "icpb_launch_count": (C.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -236,6 +237,11 @@ class Context:
         cand, opened, dims, cell = C.c_double(), C.c_int(), (C.c_int * 3)(), C.c_float()
         self._ck(lib.icpb_get_grid_stats(self.h, C.byref(cand), C.byref(opened), dims, C.byref(cell)), "get_grid_stats")
         return {"candidates_visited": cand.value, "last_open_sources": opened.value, "dims": list(dims), "cell": cell.value}
+
+    def filter_stats(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(lib.icpb_get_filter_stats(self.h, C.byref(a), C.byref(b)), "get_filter_stats")
+        return {"subtile_tests": a.value, "subtile_exact": b.value}
 
     def launch_count(self):
         return int(lib.icpb_launch_count(self.h))

@@ -43,8 +43,11 @@ extern "C" {
 #define ICPB_POINT_TO_POINT 0   /* centroids, 3x3 cross-covariance, SVD, R = U*V^T   src/ICP_point_to_point.cu:313-398 */
 #define ICPB_POINT_TO_PLANE 1   /* 6x6 normal equations, Cholesky, Euler -> R        src/ICP_point_to_plane.cu:537-601 */
 
-#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method) */
+#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method): a 3-FMA lower bound is
+                                   evaluated for every pair and the reference's chain wherever the bound cannot exclude
+                                   the pair's 128-target sub-tile; identical indices */
 #define ICPB_NN_GRID  1         /* exact uniform-grid search, identical indices */
+#define ICPB_NN_BRUTE_DIRECT 2  /* exact brute force, the reference's chain evaluated for every pair (no pruning) */
 
 typedef struct icpb_ctx icpb_ctx;
 
@@ -155,6 +158,9 @@ int  icpb_time_match(icpb_ctx* ctx, int dist_mode, int nn_method, float sentinel
 /* Uniform-grid matching statistics: candidates actually visited so far (vs the N*M a brute-force pass
  * evaluates), sources the last pass had to hand to the brute-force kernel, grid dimensions and cell size. */
 int  icpb_get_grid_stats(icpb_ctx* ctx, double* candidates_visited, int* last_open_sources, int dims[3], float* cell);
+/* ICPB_NN_BRUTE statistics since the target was set: (warp x source x 128-target sub-tile) bound tests, and
+ * how many of them had to be evaluated with the exact chain. */
+int  icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile_exact);
 /* Number of kernels this context has launched since creation. */
 long long icpb_launch_count(const icpb_ctx* ctx);
 
