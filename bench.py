@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1000, help="grid width W (W*W points per cloud); 1000 = BASELINE config 4")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-ref-binary", action="store_true")
@@ -227,6 +227,8 @@ def main():
     fp32_peak = ctx.fp32_peak_tflops()
     ctx.set_target(M)
     ctx.set_source(shard)
+    # the direct kernel (reference chain on every pair, no pruning) for comparison, outside the timed region
+    _, direct_ms = ctx.time_match(ib.DIST_SQ, ib.NN_BRUTE_DIRECT, reps=2)
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
@@ -278,6 +280,12 @@ def main():
     achieved = 8.0 * pairs_rank / (sum(match_ms) * 1e-3) * 1e-12
     achieved = allmax(-achieved) * -1.0 if world > 1 else achieved      # the slowest rank's figure
 
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+        traffic = tj.get("k1_filter", {}).get(str(args.width))
+    except Exception:      # noqa: BLE001
+        pass
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -297,8 +305,14 @@ def main():
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
-                         "kernel": "k1_match (brute-force NN)", "flop_per_pair": 8, "traffic": None,
-                         "note": "compute-bound: 6 FP32-pipe ops carry the 8 algorithmic FLOP, ceiling 66.7% of FFMA peak for the direct form"},
+                         "kernel": "k1_filter (brute-force NN: 3-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)",
+                         "flop_per_pair": 8, "traffic": traffic,
+                         "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "note": "compute-bound (FP32 pipe / register-file bandwidth); algorithmic 8 FLOP per pair as SURVEY.md 8(d) defines; "
+                                 "the direct form needs 6 FP32 ops per pair (ceiling 66.7% of FFMA peak), the filter 3"},
+            "roofline_direct_kernel": {"kernel": "k1_match (reference chain on every pair)", "ms_per_launch": direct_ms,
+                                       "achieved": 8.0 * float(hi - lo) * m / (direct_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                                       "frac": 8.0 * float(hi - lo) * m / (direct_ms * 1e-3) * 1e-12 / fp32_peak},
         }
         if world == 1 and not args.skip_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

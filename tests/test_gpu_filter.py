@@ -1,0 +1,97 @@
+"""GPU suite (-m gpu): the lower-bound-filter matching kernel (ICPB_NN_BRUTE) against the direct kernel
+(ICPB_NN_BRUTE_DIRECT) and the oracle. The filter only decides which 128-target sub-tiles may be skipped; the
+indices and winning distances must be identical bit for bit, whatever the warm start."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, ib, orc, P, Q, modes=(0, 1), sentinel=100000.0, oracle=True):
+    ctx.set_target(Q); ctx.set_source(P)
+    for mode in modes:
+        for rep in range(2):                      # second pass is warm-started from the first pass's indices
+            a = ctx.match(mode, ib.NN_BRUTE, sentinel); da = ctx.min_distances()
+            b = ctx.match(mode, ib.NN_BRUTE_DIRECT, sentinel); db = ctx.min_distances()
+            assert np.array_equal(a, b), (mode, rep)
+            assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), (mode, rep)
+        if oracle:
+            assert np.array_equal(a, orc.match(P, Q, mode, sentinel))
+
+
+def test_filter_equals_direct_on_registration_stages(ctx, ib, orc):
+    D, M = orc.synth_p2p(100)
+    for iters in (0, 1, 4, 9, 20):
+        P = D if iters == 0 else orc.icp_p2p(D, M, max_iter=iters, stop_early=False)["P"]
+        _check(ctx, ib, orc, P, M)
+    st = ctx.filter_stats()
+    assert st["subtile_tests"] > 0 and 0 < st["subtile_exact"] < st["subtile_tests"]
+
+
+def test_filter_with_adversarial_warm_start(ctx, ib, orc):
+    """The seed index may be anything: best possible, worst possible, stale from another cloud."""
+    rng = np.random.default_rng(0)
+    Q = rng.normal(size=(5000, 3)).astype(np.float32)
+    P = rng.normal(size=(3000, 3)).astype(np.float32)
+    ctx.set_target(Q); ctx.set_source(P)
+    ref = orc.match(P, Q, 0)
+    assert np.array_equal(ctx.match(0, ib.NN_BRUTE), ref)          # seeds = 0 everywhere
+    assert np.array_equal(ctx.match(0, ib.NN_BRUTE), ref)          # seeds = exact answer
+    P2 = (P[::-1] * 1.7).astype(np.float32)                        # same buffers, now stale seeds
+    ctx.set_target(Q); ctx.set_source(P2)
+    assert np.array_equal(ctx.match(1, ib.NN_BRUTE), orc.match(P2, Q, 1))
+
+
+def test_filter_ties_lattice_and_duplicates(ctx, ib, orc):
+    rng = np.random.default_rng(21)
+    Q = (rng.integers(-8, 9, size=(9000, 3)) * 0.25).astype(np.float32)
+    Q[7000:7500] = Q[200:700]
+    P = (rng.integers(-16, 17, size=(4100, 3)) * 0.125).astype(np.float32)
+    _check(ctx, ib, orc, P, Q)
+
+
+def test_filter_far_offsets_and_scales(ctx, ib, orc):
+    """Clouds far from the origin (centering matters), tiny and huge scales, a source far outside the target."""
+    rng = np.random.default_rng(8)
+    base_q = rng.normal(size=(3000, 3)).astype(np.float32)
+    base_p = rng.normal(size=(1500, 3)).astype(np.float32)
+    for shift, scale in ((1000.0, 1.0), (0.0, 1e-4), (-5e4, 30.0), (3.0, 1e5)):
+        Q = (base_q * np.float32(scale) + np.float32(shift)).astype(np.float32)
+        P = (base_p * np.float32(scale) + np.float32(shift)).astype(np.float32)
+        P[:10] += np.float32(50 * scale)
+        _check(ctx, ib, orc, P, Q, sentinel=3e38)
+
+
+def test_filter_sentinel_and_unmatched(ctx, ib, orc):
+    rng = np.random.default_rng(4)
+    Q = rng.normal(size=(2000, 3)).astype(np.float32)
+    P = (rng.normal(size=(700, 3)) * 3).astype(np.float32)
+    for s in (0.02, 0.5, 4.0):
+        _check(ctx, ib, orc, P, Q, sentinel=s, oracle=False)
+        ctx.set_target(Q); ctx.set_source(P)
+        a = ctx.match(0, ib.NN_BRUTE, s)
+        assert np.array_equal(a, orc.match(P, Q, 0, s, idx0=np.zeros(700, np.int32)))
+
+
+def test_filter_non_finite_inputs_fall_back_consistently(ctx, ib, orc):
+    rng = np.random.default_rng(6)
+    Q = rng.normal(size=(1500, 3)).astype(np.float32)
+    P = rng.normal(size=(600, 3)).astype(np.float32)
+    P[5] = np.nan; P[17, 1] = np.inf
+    _check(ctx, ib, orc, P, Q)                      # NaN/inf sources: never matched, by either kernel or the reference
+    Q2 = Q.copy(); Q2[3] = np.inf; Q2[40, 2] = np.nan
+    _check(ctx, ib, orc, P, Q2)                     # non-finite targets: the filter steps aside (direct kernel)
+    Q3 = (Q * np.float32(1e17)).astype(np.float32)
+    _check(ctx, ib, orc, (P * np.float32(1e17)).astype(np.float32), Q3, sentinel=3e38, oracle=False)
+
+
+def test_full_run_filter_is_bitwise_the_direct_run(ctx, ib, orc):
+    D, M = orc.synth_p2p(317, 100000)
+    ctx.set_target(M)
+    out = []
+    for nn in (ib.NN_BRUTE, ib.NN_BRUTE_DIRECT):
+        ctx.set_source(D)
+        e, r = ctx.run(ib.default_params(max_iter=64, nn_method=nn))
+        out.append((e.copy(), r.iterations, list(r.R), list(r.t), ctx.correspondences(), r.match_ms))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1:4] == out[1][1:4]
+    assert np.array_equal(out[0][4], out[1][4])

@@ -1,0 +1,87 @@
+// Microbenchmark: the 3-FFMA2 lower-bound filter loop in isolation, several operand forms.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
+__device__ __forceinline__ u64 bcast2v(float a) { u64 r; asm volatile("mov.b64 %0, {%1,%1};" : "=l"(r) : "f"(a)); return r; }
+__device__ __forceinline__ u64 pack2(float a, float b){ u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float&a, float&b){ asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c){ u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float min3(float a, float b, float c){ float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+// FORM 0: scalar-broadcast a (R.F32), targets packed by pairs.   FORM 1: a kept as duplicated register pairs.
+// FORM 2: "transposed": TWO SOURCES packed per register pair, target coordinate broadcast (R.F32) -> min per source is a plain FMNMX on each half
+template<int S, int FORM, int TT> __global__ void __launch_bounds__(256,2) filt(const float4* __restrict__ tiles, int ntiles, const float* __restrict__ src, float* out)
+{
+  extern __shared__ float4 sm[];
+  float ax[S],ay[S],az[S],m[S];
+  #pragma unroll
+  for(int s=0;s<S;s++){ int i=(blockIdx.x*S+s)*256+threadIdx.x; ax[s]=src[3*i]; ay[s]=src[3*i+1]; az[s]=src[3*i+2]; m[s]=1e30f; }
+  for (int t=0;t<ntiles;t++){
+    __syncthreads();
+    for (int i=threadIdx.x;i<TT;i+=256) sm[i]=tiles[(size_t)t*TT+i];
+    __syncthreads();
+    constexpr int NQ=TT/4;
+    if (FORM==2) {
+      // smem holds per target x,y,z,w as 4 SoA float arrays; each step takes 2 targets (scalars), sources packed in pairs
+      const float* X=(const float*)sm; const float* Y=X+TT; const float* Z=Y+TT; const float* W=Z+TT;
+      #pragma unroll 4
+      for (int j=0;j<TT;j+=2){
+        float2 xx=*(const float2*)(X+j), yy=*(const float2*)(Y+j), zz=*(const float2*)(Z+j), ww=*(const float2*)(W+j);
+        #pragma unroll
+        for(int s=0;s<S;s+=2){
+          u64 AX=pack2(ax[s],ax[s+1]),AY=pack2(ay[s],ay[s+1]),AZ=pack2(az[s],az[s+1]);
+          u64 e=fma2(AX,bcast2v(xx.x),fma2(AY,bcast2v(yy.x),fma2(AZ,bcast2v(zz.x),bcast2v(ww.x))));
+          u64 f=fma2(AX,bcast2v(xx.y),fma2(AY,bcast2v(yy.y),fma2(AZ,bcast2v(zz.y),bcast2v(ww.y))));
+          float a,b,c,d; unpack2(e,a,b); unpack2(f,c,d);
+          m[s]=min3(m[s],a,c); m[s+1]=min3(m[s+1],b,d);
+        }
+      }
+    } else {
+      #pragma unroll 2
+      for (int j=0;j<NQ;j++){
+        float4 X=sm[j],Y=sm[NQ+j],Z=sm[2*NQ+j],W=sm[3*NQ+j];
+        u64 x01=pack2(X.x,X.y),x23=pack2(X.z,X.w),y01=pack2(Y.x,Y.y),y23=pack2(Y.z,Y.w),z01=pack2(Z.x,Z.y),z23=pack2(Z.z,Z.w),w01=pack2(W.x,W.y),w23=pack2(W.z,W.w);
+        #pragma unroll
+        for(int s=0;s<S;s++){
+          u64 AX,AY,AZ;
+          if (FORM==0){ AX=bcast2v(ax[s]);AY=bcast2v(ay[s]);AZ=bcast2v(az[s]); } else { AX=pack2(ax[s],ax[s]);AY=pack2(ay[s],ay[s]);AZ=pack2(az[s],az[s]); }
+          u64 e=fma2(AX,x01,fma2(AY,y01,fma2(AZ,z01,w01)));
+          float a,b; unpack2(e,a,b); m[s]=min3(m[s],a,b);
+          e=fma2(AX,x23,fma2(AY,y23,fma2(AZ,z23,w23)));
+          unpack2(e,a,b); m[s]=min3(m[s],a,b);
+        }
+      }
+    }
+  }
+  #pragma unroll
+  for(int s=0;s<S;s++) out[(blockIdx.x*S+s)*256+threadIdx.x]=m[s];
+}
+template<int S,int FORM,int TT> void run(const float4* tiles,int M,const float* src,float* out,int N,const char* name){
+  int blocks=N/(256*S); size_t smem=TT*16;
+  CK(cudaFuncSetAttribute(filt<S,FORM,TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)smem));
+  cudaEvent_t a,b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float best=1e30f;
+  for(int r=0;r<6;r++){ cudaEventRecord(a); filt<S,FORM,TT><<<blocks,256,smem>>>(tiles,M/TT,src,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); float ms; cudaEventElapsedTime(&ms,a,b); if(r>0&&ms<best)best=ms; }
+  double pps=(double)N*M/(best*1e-3);
+  printf("%-34s S=%2d TT=%4d: %7.3f ms  %.3e pairs/s  (%.2f cycles per source x 4 targets per SMSP @1.965GHz)\n",name,S,TT,best,pps,128.0/(pps/(148*4*1.965e9)));
+}
+int main(){
+  int N=148*2*2048*2, M=32768;
+  std::vector<float> hs(3*(size_t)N), ht(4*(size_t)M);
+  for(size_t i=0;i<hs.size();i++) hs[i]=(float)((i*2654435761u>>8)&0xffff)/16384.f-2.f;
+  for(size_t i=0;i<ht.size();i++) ht[i]=(float)((i*2246822519u>>8)&0xffff)/16384.f-2.f;
+  float *src,*out; float4* tiles;
+  CK(cudaMalloc(&src,hs.size()*4)); CK(cudaMalloc(&out,(size_t)N*4)); CK(cudaMalloc(&tiles,ht.size()*4));
+  CK(cudaMemcpy(src,hs.data(),hs.size()*4,cudaMemcpyHostToDevice)); CK(cudaMemcpy(tiles,ht.data(),ht.size()*4,cudaMemcpyHostToDevice));
+  run<8,0,1024>(tiles,M,src,out,N,"bcast-scalar a, packed targets");
+  run<8,1,1024>(tiles,M,src,out,N,"pair a, packed targets");
+  run<4,0,1024>(tiles,M,src,out,N,"bcast-scalar a, packed targets");
+  run<4,1,1024>(tiles,M,src,out,N,"pair a, packed targets");
+  run<8,2,1024>(tiles,M,src,out,N,"packed sources, bcast target");
+  run<4,2,1024>(tiles,M,src,out,N,"packed sources, bcast target");
+  run<16,2,1024>(tiles,M,src,out,N,"packed sources, bcast target");
+  run<16,0,1024>(tiles,M,src,out,N,"bcast-scalar a, packed targets");
+  return 0;
+}
