@@ -1,4 +1,4 @@
-// pending.cu — nearest-neighbour method dispatch.
+// nn_dispatch.cu — nearest-neighbour method dispatch.
 #include "common.cuh"
 namespace icpb {
 int launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel)

@@ -351,8 +351,10 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
 	int rc;
 	if (!c->kf_ready) { if ((rc = build_filter_data(c)) != ICPB_OK) return rc; }
-	// the bound needs finite magnitudes; anything else goes through the direct kernel
-	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f) return launch_match_brute(c, dist_mode, sentinel);
+	// The bound's error analysis is relative (u = 2^-24 per operation): it needs finite magnitudes whose squares stay
+	// in the normal range. Anything else (non-finite coordinates, clouds of radius > 1e15 or < 1e-15) goes through
+	// the direct kernel.
+	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f || c->kf_rq < 1e-15f) return launch_match_brute(c, dist_mode, sentinel);
 	constexpr int S = 8, THREADS = 256, MINB = 2;
 	constexpr int SB = S * THREADS;
 	KFParams p;

@@ -62,6 +62,13 @@ def test_filter_far_offsets_and_scales(ctx, ib, orc):
         _check(ctx, ib, orc, P, Q, sentinel=3e38)
 
 
+def test_filter_denormal_squares_use_the_direct_kernel(ctx, ib, orc):
+    rng = np.random.default_rng(9)
+    Q = (rng.normal(size=(1200, 3)) * 1e-21).astype(np.float32)
+    P = (rng.normal(size=(500, 3)) * 1e-21).astype(np.float32)
+    _check(ctx, ib, orc, P, Q)
+
+
 def test_filter_sentinel_and_unmatched(ctx, ib, orc):
     rng = np.random.default_rng(4)
     Q = rng.normal(size=(2000, 3)).astype(np.float32)
