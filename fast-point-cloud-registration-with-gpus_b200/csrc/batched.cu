@@ -23,7 +23,7 @@ constexpr int K9_TRK = 64;                      // tracking sub-tile (small clou
 struct BatchParams {
 	const float* sources;   // [batch][n][3]
 	const float* targets;   // [batch][m][3]
-	int batch, n, m, max_iter, stop_early, mode;
+	int batch, n, m, max_iter, stop_early, mode, flags;
 	float sentinel, thr0;
 	double tol;
 	float* errors;          // [batch][max_iter+1]
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchP
 			idx[s] = 0;
 		}
 		if (tid == 0) {
-			st.done = 0; st.iteration = 0; st.iters_run = 0;
+			st.done = 0; st.iteration = 0; st.iters_run = 0; st.flags = p.flags;
 			for (int k = 0; k < 9; k++) st.Rtot[k] = (k % 4 == 0) ? 1.0 : 0.0;
 			for (int k = 0; k < 3; k++) st.ttot[k] = 0.0;
 			err_prev = 0.f;
@@ -251,7 +251,7 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 
 	BatchParams p;
 	p.sources = d_s; p.targets = d_t; p.batch = batch; p.n = n; p.m = m;
-	p.max_iter = params->max_iter; p.stop_early = params->stop_early; p.mode = params->dist_mode;
+	p.max_iter = params->max_iter; p.stop_early = params->stop_early; p.mode = params->dist_mode; p.flags = params->flags;
 	p.sentinel = params->sentinel; p.tol = params->tol;
 	p.thr0 = (params->dist_mode == ICPB_DIST_SQRT) ? sqrt_threshold_host(params->sentinel) : params->sentinel;
 	p.errors = d_e; p.iterations = d_it; p.iterations_run = d_run; p.R = d_R; p.t = d_tt; p.idx = nullptr;

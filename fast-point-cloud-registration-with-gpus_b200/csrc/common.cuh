@@ -31,6 +31,8 @@ struct IterState {
 	int    ticket_b;
 	int    max_iter;
 	int    stop_early;
+	int    flags;         // ICPB_FLAG_*
+	int    pad0;
 	double tol;
 	double n_total;       // global number of source points (all ranks)
 	double moments[32];   // reduced moment sums (16 point-to-point, 28 point-to-plane)

@@ -56,7 +56,7 @@ static int reset_state(Ctx* c, const icpb_params* p)
 {
 	IterState* h = c->st_host;
 	memset(h, 0, sizeof *h);
-	h->max_iter = p->max_iter; h->stop_early = p->stop_early; h->tol = p->tol;
+	h->max_iter = p->max_iter; h->stop_early = p->stop_early; h->tol = p->tol; h->flags = p->flags;
 	h->n_total = (double)c->n;
 	for (int k = 0; k < 9; k++) h->Rtot[k] = (k % 4 == 0) ? 1.0 : 0.0;
 	for (int k = 0; k < 9; k++) h->R[k] = (k % 4 == 0) ? 1.0f : 0.0f;
@@ -176,7 +176,7 @@ void icpb_default_params(icpb_params* p)
 {
 	if (!p) return;
 	p->metric = ICPB_POINT_TO_POINT; p->dist_mode = ICPB_DIST_SQ; p->nn_method = ICPB_NN_BRUTE;
-	p->max_iter = 40; p->stop_early = 1; p->sync_every = 1; p->sentinel = 100000.0f; p->tol = 0.000001;
+	p->max_iter = 40; p->stop_early = 1; p->sync_every = 1; p->sentinel = 100000.0f; p->tol = 0.000001; p->flags = 0;
 }
 
 int icpb_device_count(int* count)

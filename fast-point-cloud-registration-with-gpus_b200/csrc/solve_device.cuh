@@ -8,7 +8,7 @@ namespace icpb {
 // ------------------------------------------------------------------------------------------------
 // K3: R = U V^T from W by one-sided Jacobi in FP64 registers, T = qbar - R pbar.
 // ------------------------------------------------------------------------------------------------
-__device__ inline void polar_rotation(const double W[9] /*col-major*/, double R[9])
+__device__ inline void polar_rotation(const double W[9] /*col-major*/, double R[9], bool fix_reflection = false)
 {
 	double a[3][3], v[3][3];
 #pragma unroll
@@ -59,6 +59,15 @@ __device__ inline void polar_rotation(const double W[9] /*col-major*/, double R[
 	for (int i = 0; i < 3; i++)
 #pragma unroll
 		for (int j = 0; j < 3; j++) R[i + 3 * j] = u[i][0] * v[j][0] + u[i][1] * v[j][1] + u[i][2] * v[j][2];
+	if (fix_reflection) {
+		const double det = R[0] * (R[4] * R[8] - R[7] * R[5]) - R[3] * (R[1] * R[8] - R[7] * R[2]) + R[6] * (R[1] * R[5] - R[4] * R[2]);
+		if (det < 0.0) {      // Kabsch: flip the pair (u_k, v_k) of the smallest singular value: R -= 2 u_k v_k^T
+#pragma unroll
+			for (int i = 0; i < 3; i++)
+#pragma unroll
+				for (int j = 0; j < 3; j++) R[i + 3 * j] -= 2.0 * u[i][small] * v[j][small];
+		}
+	}
 }
 
 __device__ inline void compose_total(IterState* st)
@@ -82,7 +91,7 @@ __device__ inline void solve_p2p(IterState* st)
 	for (int c = 0; c < 3; c++) { pb[c] = mom[c] / N; qb[c] = mom[3 + c] / N; }
 	for (int c = 0; c < 3; c++)
 		for (int r = 0; r < 3; r++) W[r + 3 * c] = mom[6 + r + 3 * c] - N * qb[r] * pb[c];
-	polar_rotation(W, R);
+	polar_rotation(W, R, (st->flags & ICPB_FLAG_FIX_REFLECTION) != 0);
 	for (int k = 0; k < 9; k++) st->R[k] = (float)R[k];
 	for (int r = 0; r < 3; r++) st->T[r] = (float)(qb[r] - (R[r] * pb[0] + R[r + 3] * pb[1] + R[r + 6] * pb[2]));
 	compose_total(st);

@@ -14,11 +14,12 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "libicp_b200.so"))
 DIST_SQ, DIST_SQRT, DIST_STD = 0, 1, 2
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
 NN_BRUTE, NN_GRID, NN_BRUTE_DIRECT = 0, 1, 2
+FLAG_FIX_REFLECTION = 1
 
 
 class Params(C.Structure):
     _fields_ = [("metric", C.c_int), ("dist_mode", C.c_int), ("nn_method", C.c_int), ("max_iter", C.c_int),
-                ("stop_early", C.c_int), ("sync_every", C.c_int), ("sentinel", C.c_float), ("tol", C.c_double)]
+                ("stop_early", C.c_int), ("sync_every", C.c_int), ("sentinel", C.c_float), ("tol", C.c_double), ("flags", C.c_int)]
 
 
 class Result(C.Structure):

@@ -49,6 +49,10 @@ extern "C" {
 #define ICPB_NN_GRID  1         /* exact uniform-grid search, identical indices */
 #define ICPB_NN_BRUTE_DIRECT 2  /* exact brute force, the reference's chain evaluated for every pair (no pruning) */
 
+/* Robustness options the reference lacks; all off by default so parity is untouched. */
+#define ICPB_FLAG_FIX_REFLECTION 1   /* if det(U*V^T) < 0 flip the singular vector of the smallest singular value (Kabsch);
+                                        the reference keeps the reflection (src/ICP_point_to_point.cu:379-381) */
+
 typedef struct icpb_ctx icpb_ctx;
 
 typedef struct icpb_params {
@@ -61,6 +65,7 @@ typedef struct icpb_params {
 	int    sync_every;   /* iterations enqueued between host reads of the device-side stop flag (>=1) */
 	float  sentinel;     /* 100000 (src/ICP_point_to_point.cu:36); 1e6 in the LiDAR programs */
 	double tol;          /* 0.000001 (GPU programs), 0.00001 (src/ICP_CPU.c:267) */
+	int    flags;        /* ICPB_FLAG_*; 0 = the reference's behaviour */
 } icpb_params;
 
 typedef struct icpb_result {

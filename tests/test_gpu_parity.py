@@ -289,3 +289,27 @@ def test_1m_single_match_sampled_vs_oracle(ctx, orc):
     diff = (D - M[idx]).astype(np.float32)
     chain = diff[:, 2] * diff[:, 2] + (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1])
     assert np.allclose(d, chain, rtol=2e-6, atol=1e-12)
+
+
+def test_reflection_fix_flag(ctx, ib, orc):
+    """SURVEY.md §8 f-4. Sources = small clusters strung along y (so that matching is the identity), targets =
+    the same clusters mirrored in x: the reference's R = U*V^T is a reflection (det = -1); with
+    ICPB_FLAG_FIX_REFLECTION the engine returns the best proper rotation (Kabsch), checked against numpy."""
+    rng = np.random.default_rng(12)
+    off = (rng.normal(size=(400, 3)) * [1e-3, 1e-3, 5e-4]).astype(np.float32)     # well inside the 0.05 spacing
+    line = (np.arange(400, dtype=np.float32) * np.float32(0.05))[:, None] * np.array([0, 1, 0], np.float32)
+    P = (off + line).astype(np.float32)
+    Q = (off * np.array([-1, 1, 1], np.float32) + line).astype(np.float32)
+    ctx.set_target(Q)
+    out = {}
+    for flags in (0, ib.FLAG_FIX_REFLECTION):
+        ctx.set_source(P)
+        err, res = ctx.run(ib.default_params(max_iter=1, stop_early=0, flags=flags))
+        assert np.array_equal(ctx.correspondences(), np.arange(400))
+        out[flags] = np.array(res.R[:]).reshape(3, 3).T
+    assert np.linalg.det(out[0]) < -0.99, "the reference keeps the reflection"
+    assert np.linalg.det(out[ib.FLAG_FIX_REFLECTION]) > 0.99
+    pc, qc = P.astype(np.float64) - P.astype(np.float64).mean(0), Q.astype(np.float64) - Q.astype(np.float64).mean(0)
+    U, S, Vt = np.linalg.svd(qc.T @ pc)
+    assert np.abs(out[0] - U @ Vt).max() < 1e-5
+    assert np.abs(out[ib.FLAG_FIX_REFLECTION] - U @ np.diag([1, 1, -1]) @ Vt).max() < 1e-5

@@ -23,7 +23,22 @@ template<int S, int FORM, int TT> __global__ void __launch_bounds__(256,2) filt(
     for (int i=threadIdx.x;i<TT;i+=256) sm[i]=tiles[(size_t)t*TT+i];
     __syncthreads();
     constexpr int NQ=TT/4;
-    if (FORM==2) {
+    if (FORM==3) {
+      // scalar FFMA: 12 FFMA + 2 FMNMX3 per source x 4 targets
+      constexpr int NQ2=TT/4;
+      #pragma unroll 2
+      for (int j=0;j<NQ2;j++){
+        float4 X=sm[j],Y=sm[NQ2+j],Z=sm[2*NQ2+j],W=sm[3*NQ2+j];
+        #pragma unroll
+        for(int s=0;s<S;s++){
+          float e0=fmaf(ax[s],X.x,fmaf(ay[s],Y.x,fmaf(az[s],Z.x,W.x)));
+          float e1=fmaf(ax[s],X.y,fmaf(ay[s],Y.y,fmaf(az[s],Z.y,W.y)));
+          float e2=fmaf(ax[s],X.z,fmaf(ay[s],Y.z,fmaf(az[s],Z.z,W.z)));
+          float e3=fmaf(ax[s],X.w,fmaf(ay[s],Y.w,fmaf(az[s],Z.w,W.w)));
+          m[s]=min3(m[s],e0,e1); m[s]=min3(m[s],e2,e3);
+        }
+      }
+    } else if (FORM==2) {
       // smem holds per target x,y,z,w as 4 SoA float arrays; each step takes 2 targets (scalars), sources packed in pairs
       const float* X=(const float*)sm; const float* Y=X+TT; const float* Z=Y+TT; const float* W=Z+TT;
       #pragma unroll 4
@@ -75,6 +90,9 @@ int main(){
   float *src,*out; float4* tiles;
   CK(cudaMalloc(&src,hs.size()*4)); CK(cudaMalloc(&out,(size_t)N*4)); CK(cudaMalloc(&tiles,ht.size()*4));
   CK(cudaMemcpy(src,hs.data(),hs.size()*4,cudaMemcpyHostToDevice)); CK(cudaMemcpy(tiles,ht.data(),ht.size()*4,cudaMemcpyHostToDevice));
+  run<8,3,1024>(tiles,M,src,out,N,"scalar FFMA");
+  run<4,3,1024>(tiles,M,src,out,N,"scalar FFMA");
+  run<16,3,1024>(tiles,M,src,out,N,"scalar FFMA");
   run<8,0,1024>(tiles,M,src,out,N,"bcast-scalar a, packed targets");
   run<8,1,1024>(tiles,M,src,out,N,"pair a, packed targets");
   run<4,0,1024>(tiles,M,src,out,N,"bcast-scalar a, packed targets");
