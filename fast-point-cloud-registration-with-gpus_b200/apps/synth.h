@@ -88,7 +88,7 @@ inline Clouds standard_clouds(int W)
 
 // ---- optional command line (the reference takes none; with no arguments behaviour is identical) ----
 struct Options {
-	int width = 0, n = 0, max_iter = 0, gpus = 1, grid_nn = 0, report = 0, sync_every = 1;
+	int width = 0, n = 0, max_iter = 0, gpus = 1, grid_nn = 0, report = 0, sync_every = 0;
 	double tol = -1;
 };
 inline bool parse(int argc, char** argv, Options& o)

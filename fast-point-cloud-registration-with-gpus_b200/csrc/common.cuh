@@ -151,6 +151,7 @@ struct Ctx {
 	int     kf_nt = 0;
 	unsigned long long* kf_stats = nullptr;
 	bool    kf_use_seed = true;         // warm start from the previous correspondences
+	double  kf_min_pairs = 1e9;         // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS)
 	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)
 
 	// iteration state
@@ -165,6 +166,7 @@ struct Ctx {
 
 	// K1 configuration
 	int k1_cfg = 6;              // index into the K1 tuning table (nn_bruteforce.cu); 6 = best measured on B200
+	bool k1_cfg_forced = false;  // ICPB_K1_CFG given: no size-based choice
 	int k1_grid_override = 0;
 	double pairs_acc = 0;
 

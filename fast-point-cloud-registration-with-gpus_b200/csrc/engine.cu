@@ -138,10 +138,11 @@ static int create_common(Ctx** out, int device)
 		return ICPB_ERR_NOMEM;
 	}
 	cudaMemset(c->st, 0, sizeof(IterState));
-	if (const char* e = getenv("ICPB_K1_CFG")) c->k1_cfg = atoi(e);
+	if (const char* e = getenv("ICPB_K1_CFG")) { c->k1_cfg = atoi(e); c->k1_cfg_forced = true; }
 	if (const char* e = getenv("ICPB_K1_GRID")) c->k1_grid_override = atoi(e);
 	if (const char* e = getenv("ICPB_K1_FILTER")) c->k1_use_filter = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_SEED")) c->kf_use_seed = atoi(e) != 0;
+	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	*out = c;
 	return ICPB_OK;
 }
@@ -176,7 +177,7 @@ void icpb_default_params(icpb_params* p)
 {
 	if (!p) return;
 	p->metric = ICPB_POINT_TO_POINT; p->dist_mode = ICPB_DIST_SQ; p->nn_method = ICPB_NN_BRUTE;
-	p->max_iter = 40; p->stop_early = 1; p->sync_every = 1; p->sentinel = 100000.0f; p->tol = 0.000001; p->flags = 0;
+	p->max_iter = 40; p->stop_early = 1; p->sync_every = 0; p->sentinel = 100000.0f; p->tol = 0.000001; p->flags = 0;
 }
 
 int icpb_device_count(int* count)
@@ -425,7 +426,9 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	int rc;
 	if ((rc = check_params(c, params)) != ICPB_OK) return rc;
 	icpb_params p = *params;
-	if (p.sync_every < 1) p.sync_every = 1;
+	// sync_every <= 0: adaptive — small clouds are launch-latency bound, so several iterations are enqueued per read
+	// of the device-side stop flag (kernels launched after the flag is raised return immediately: same results)
+	if (p.sync_every < 1) p.sync_every = ((double)c->n * (double)c->m < 4e9) ? 4 : 1;
 	c->step_state_ready = false;
 	if ((rc = reset_state(c, &p)) != ICPB_OK) return rc;
 	if ((rc = launch_key_reset(c)) != ICPB_OK) return rc;

@@ -286,10 +286,14 @@ static int launch_cfg(Ctx* c, int mode, const K1Params& base)
 	p.units = (long long)nb * p.nt;
 	const size_t smem = (size_t)K1_STAGES * K1_TILE_BYTES + 64 + ((VAR & 4) ? (size_t)2 * S * THREADS * 4 : 0);
 	auto kern = (mode == ICPB_DIST_SQRT) ? k1_match<S, THREADS, ICPB_DIST_SQRT, MINB, VAR> : k1_match<S, THREADS, ICPB_DIST_SQ, MINB, VAR>;
-	ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 0;
-	ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-	if (per_sm < 1) per_sm = 1;
+	// per (kernel, device) launch attributes are queried once: they sit on the host path of every iteration
+	static int cached_per_sm[2][64] = {};
+	int& per_sm = cached_per_sm[mode == ICPB_DIST_SQRT ? 1 : 0][c->device & 63];
+	if (per_sm == 0) {
+		ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+		if (per_sm < 1) per_sm = 1;
+	}
 	long long grid = (long long)c->sm_count * per_sm;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
 	if (grid > p.units) grid = p.units;
@@ -327,7 +331,11 @@ static int launch_match_brute_impl(Ctx* c, int dist_mode, float sentinel, const 
 		ICPB_CUDA(c, cudaGetLastError());
 		return ICPB_OK;
 	}
-	switch (c->k1_cfg) {
+	// small problems (< 1e9 pairs) are dominated by per-block prologue/epilogue: 4 sources per thread gives twice
+	// the blocks per source and a cheaper index re-scan (measured: tools/sweep_small.py); ICPB_K1_CFG overrides
+	int cfg = c->k1_cfg;
+	if (!c->k1_cfg_forced && (double)c->n * (double)c->m < 1e9) cfg = 8;
+	switch (cfg) {
 #define X(i, s, t, b, v) case i: return launch_cfg<s, t, b, v>(c, dist_mode, p);
 	K1_CONFIGS(X)
 #undef X

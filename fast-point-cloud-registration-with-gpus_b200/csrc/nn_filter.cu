@@ -370,10 +370,13 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	c->pairs_acc += (double)c->n * (double)c->m;
 	const size_t smem = (size_t)KF_STAGES * KF_TILE_BYTES + 64 + (size_t)5 * S * THREADS * 4;
 	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB>;
-	ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 0;
-	ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-	if (per_sm < 1) per_sm = 1;
+	static int cached_per_sm[2][64] = {};
+	int& per_sm = cached_per_sm[dist_mode == ICPB_DIST_SQRT ? 1 : 0][c->device & 63];
+	if (per_sm == 0) {
+		ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+		if (per_sm < 1) per_sm = 1;
+	}
 	long long grid = (long long)c->sm_count * per_sm;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
 	if (grid > p.units) grid = p.units;

@@ -62,7 +62,8 @@ typedef struct icpb_params {
 	int    max_iter;     /* MAX_ITER: 40 (src/ICP_point_to_point.cu:24), 50 (ICP_point_to_plane.cu:23) */
 	int    stop_early;   /* 1: break when e < tol or |e_k+1 - e_k| < tol (src/ICP_point_to_point.cu:420-421);
 	                        0: always run max_iter iterations (src/ICP_standard.cu:369) */
-	int    sync_every;   /* iterations enqueued between host reads of the device-side stop flag (>=1) */
+	int    sync_every;   /* iterations enqueued between host reads of the device-side stop flag; 0 = adaptive
+	                        (4 below 4e9 pairs per pass, else 1). Never changes results. */
 	float  sentinel;     /* 100000 (src/ICP_point_to_point.cu:36); 1e6 in the LiDAR programs */
 	double tol;          /* 0.000001 (GPU programs), 0.00001 (src/ICP_CPU.c:267) */
 	int    flags;        /* ICPB_FLAG_*; 0 = the reference's behaviour */

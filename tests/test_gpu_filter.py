@@ -7,11 +7,29 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _check(ctx, ib, orc, P, Q, modes=(0, 1), sentinel=100000.0, oracle=True):
+@pytest.fixture(scope="module")
+def ctx(ib):
+    """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
+    use the direct kernel, which would make most of these small cases vacuous)."""
+    import os
+    old = os.environ.get("ICPB_K1_FILTER_MIN_PAIRS")
+    os.environ["ICPB_K1_FILTER_MIN_PAIRS"] = "0"
+    c = ib.Context(0)
+    if old is None:
+        del os.environ["ICPB_K1_FILTER_MIN_PAIRS"]
+    else:
+        os.environ["ICPB_K1_FILTER_MIN_PAIRS"] = old
+    yield c
+    c.close()
+
+
+def _check(ctx, ib, orc, P, Q, modes=(0, 1), sentinel=100000.0, oracle=True, expect_filter=True):
     ctx.set_target(Q); ctx.set_source(P)
     for mode in modes:
         for rep in range(2):                      # second pass is warm-started from the first pass's indices
+            s0 = ctx.filter_stats()["subtile_tests"]
             a = ctx.match(mode, ib.NN_BRUTE, sentinel); da = ctx.min_distances()
+            assert (ctx.filter_stats()["subtile_tests"] > s0) == expect_filter, "which kernel ran is part of the test"
             b = ctx.match(mode, ib.NN_BRUTE_DIRECT, sentinel); db = ctx.min_distances()
             assert np.array_equal(a, b), (mode, rep)
             assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), (mode, rep)
@@ -66,7 +84,7 @@ def test_filter_denormal_squares_use_the_direct_kernel(ctx, ib, orc):
     rng = np.random.default_rng(9)
     Q = (rng.normal(size=(1200, 3)) * 1e-21).astype(np.float32)
     P = (rng.normal(size=(500, 3)) * 1e-21).astype(np.float32)
-    _check(ctx, ib, orc, P, Q)
+    _check(ctx, ib, orc, P, Q, expect_filter=False)
 
 
 def test_filter_sentinel_and_unmatched(ctx, ib, orc):
@@ -87,9 +105,9 @@ def test_filter_non_finite_inputs_fall_back_consistently(ctx, ib, orc):
     P[5] = np.nan; P[17, 1] = np.inf
     _check(ctx, ib, orc, P, Q)                      # NaN/inf sources: never matched, by either kernel or the reference
     Q2 = Q.copy(); Q2[3] = np.inf; Q2[40, 2] = np.nan
-    _check(ctx, ib, orc, P, Q2)                     # non-finite targets: the filter steps aside (direct kernel)
+    _check(ctx, ib, orc, P, Q2, expect_filter=False)  # non-finite targets: the filter steps aside (direct kernel)
     Q3 = (Q * np.float32(1e17)).astype(np.float32)
-    _check(ctx, ib, orc, (P * np.float32(1e17)).astype(np.float32), Q3, sentinel=3e38, oracle=False)
+    _check(ctx, ib, orc, (P * np.float32(1e17)).astype(np.float32), Q3, sentinel=3e38, oracle=False, expect_filter=False)
 
 
 def test_full_run_filter_is_bitwise_the_direct_run(ctx, ib, orc):
