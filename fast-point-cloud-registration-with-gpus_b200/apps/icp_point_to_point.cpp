@@ -36,6 +36,7 @@ int main(int argc, char** argv)
 	p.sync_every = opt.sync_every;
 	if (opt.tol >= 0) p.tol = opt.tol;
 	if (opt.grid_nn) p.nn_method = ICPB_NN_GRID;
+	if (opt.report) p.flags |= ICPB_FLAG_PROFILE;     // per-iteration matching times for the report
 	std::vector<float> err((size_t)max_iter + 1, 0.f);
 	icpb_result res;
 	rc = icpb_run(ctx, &p, err.data(), &res);

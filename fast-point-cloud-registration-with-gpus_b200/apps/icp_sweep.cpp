@@ -37,7 +37,7 @@ int main(int argc, char** argv)
 		const int W = phases_w > 0 ? phases_w : 128;
 		synth::Clouds c = synth::point_to_point_clouds(W, W * W);
 		if (icpb_set_target(ctx, c.M.data(), c.n, 0) != ICPB_OK || icpb_set_source(ctx, c.D.data(), c.n, 0) != ICPB_OK) return fail(ctx, "upload");
-		icpb_params p; icpb_default_params(&p); p.nn_method = nn;
+		icpb_params p; icpb_default_params(&p); p.nn_method = nn; p.flags |= ICPB_FLAG_PROFILE;
 		std::vector<float> err((size_t)p.max_iter + 1);
 		icpb_result res;
 		if (icpb_run(ctx, &p, err.data(), &res) != ICPB_OK) return fail(ctx, "icpb_run");

@@ -170,6 +170,15 @@ struct Ctx {
 	int k1_grid_override = 0;
 	double pairs_acc = 0;
 
+	// CUDA-graph replay of a batch of iterations (launch-bound small problems, engine.cu)
+	cudaGraphExec_t graph_exec = nullptr;
+	long long graph_gen = 0, graph_built_gen = -1;   // bumped whenever clouds / buffers change
+	int  graph_batch = 0, graph_launches = 0;
+	int  graph_key[4] = {-1, -1, -1, -1};             // metric, dist_mode, nn_method, flags
+	float graph_sentinel = 0.f;
+	bool graphs_enabled = false;                     // ICPB_GRAPHS=1 (or ICPB_FLAG_GRAPH) enables: capture + instantiate cost
+	                                                 // milliseconds, which only repeated registrations of one size amortise
+
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t* ev_match = nullptr; int ev_match_cap = 0;
 };

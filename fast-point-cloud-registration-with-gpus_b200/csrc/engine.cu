@@ -143,6 +143,7 @@ static int create_common(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_FILTER")) c->k1_use_filter = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_SEED")) c->kf_use_seed = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
+	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	*out = c;
 	return ICPB_OK;
 }
@@ -221,6 +222,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	Ctx* c = C(ctx);
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
 	dist_destroy(c->dist);
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->dmin);
@@ -263,7 +265,7 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 		if ((rc = dev_alloc(c, &c->nrm4, (size_t)0)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->nbr, (size_t)0)) != ICPB_OK) return rc;
 	}
-	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->step_state_ready = false;
+	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->step_state_ready = false; c->graph_gen++;
 	const float* src = xyz;
 	if (!on_device) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)m)) != ICPB_OK) return rc;
@@ -294,6 +296,7 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 		c->n_cap = cap;
 	}
 	c->n = n; c->step_state_ready = false;   // the control block caches the global point count
+	c->graph_gen++;
 	const float* src = xyz;
 	if (!on_device && n > 0) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)n)) != ICPB_OK) return rc;
@@ -444,16 +447,62 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 		}
 	}
 	c->pairs_acc = 0;
+	// Opt-in (ICPB_FLAG_GRAPH / ICPB_GRAPHS=1) for launch-latency-bound small problems: after a first plain iteration
+	// (which also builds lazily created data and caches launch attributes) the remaining ones are replayed from a CUDA
+	// graph holding `sync_every` iterations; the instantiated graph is reused by later runs on clouds of the same size.
+	// Iterations past the stop flag / MAX_ITER return immediately, so results are those of the plain loop.
+	// Measured on B200: capture + instantiate cost 2-90 ms, so a single 27-iteration registration of 16 384 points
+	// (3.3 ms) is slower with it; it is off by default.
+	const bool use_graph = (c->graphs_enabled || (p.flags & ICPB_FLAG_GRAPH)) && c->world == 1 && p.nn_method != ICPB_NN_GRID && !(p.flags & ICPB_FLAG_PROFILE) &&
+	                       (double)c->n * (double)c->m < 4e9 && p.max_iter > 1;
 	ICPB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
 	int enq = 0;
-	while (true) {
-		for (int b = 0; b < p.sync_every && enq < p.max_iter; b++, enq++) {
-			cudaEvent_t e0 = (2 * enq + 1 < c->ev_match_cap) ? c->ev_match[2 * enq] : nullptr;
-			cudaEvent_t e1 = e0 ? c->ev_match[2 * enq + 1] : nullptr;
-			if ((rc = enqueue_iteration(c, &p, e0, e1)) != ICPB_OK) return rc;
-		}
+	bool timed_iterations = true;
+	if (use_graph) {
+		timed_iterations = false;
+		if ((rc = enqueue_iteration(c, &p, nullptr, nullptr)) != ICPB_OK) return rc;
+		enq = 1;
 		if ((rc = read_state(c)) != ICPB_OK) return rc;
-		if (c->st_host->done || enq >= p.max_iter) break;
+		if (!c->st_host->done) {
+			const bool valid = c->graph_exec != nullptr && c->graph_built_gen == c->graph_gen && c->graph_batch == p.sync_every &&
+			                   c->graph_key[0] == p.metric && c->graph_key[1] == p.dist_mode && c->graph_key[2] == p.nn_method &&
+			                   c->graph_key[3] == p.flags && c->graph_sentinel == p.sentinel;
+			if (!valid) {
+				if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+				const long long l0 = c->launches;
+				cudaGraph_t g = nullptr;
+				ICPB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+				for (int b = 0; b < p.sync_every && rc == ICPB_OK; b++) rc = enqueue_iteration(c, &p, nullptr, nullptr);
+				cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+				if (rc != ICPB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+				if (ce != cudaSuccess) return fail_cuda(c, ce, "cudaStreamEndCapture", __FILE__, __LINE__);
+				ce = cudaGraphInstantiate(&c->graph_exec, g, 0);
+				cudaGraphDestroy(g);
+				if (ce != cudaSuccess) return fail_cuda(c, ce, "cudaGraphInstantiate", __FILE__, __LINE__);
+				c->graph_launches = (int)(c->launches - l0);
+				c->launches = l0;                      // captured, not launched
+				c->graph_built_gen = c->graph_gen; c->graph_batch = p.sync_every;
+				c->graph_key[0] = p.metric; c->graph_key[1] = p.dist_mode; c->graph_key[2] = p.nn_method; c->graph_key[3] = p.flags;
+				c->graph_sentinel = p.sentinel;
+			}
+			while (true) {
+				ICPB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+				c->launches += c->graph_launches;
+				enq += p.sync_every;
+				if ((rc = read_state(c)) != ICPB_OK) return rc;
+				if (c->st_host->done || enq >= p.max_iter) break;
+			}
+		}
+	} else {
+		while (true) {
+			for (int b = 0; b < p.sync_every && enq < p.max_iter; b++, enq++) {
+				cudaEvent_t e0 = (2 * enq + 1 < c->ev_match_cap) ? c->ev_match[2 * enq] : nullptr;
+				cudaEvent_t e1 = e0 ? c->ev_match[2 * enq + 1] : nullptr;
+				if ((rc = enqueue_iteration(c, &p, e0, e1)) != ICPB_OK) return rc;
+			}
+			if ((rc = read_state(c)) != ICPB_OK) return rc;
+			if (c->st_host->done || enq >= p.max_iter) break;
+		}
 	}
 	ICPB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
 	ICPB_CUDA(c, cudaMemcpyAsync(c->errors_host, c->errors, sizeof(float) * (size_t)(p.max_iter + 1), cudaMemcpyDeviceToHost, c->stream));
@@ -468,7 +517,7 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 		memcpy(result->last_R, h->R, sizeof h->R); memcpy(result->last_T, h->T, sizeof h->T);
 		cudaEventElapsedTime(&result->elapsed_ms, c->ev[0], c->ev[1]);
 		float mm = 0.f;
-		for (int k = 0; k < h->iters_run && 2 * k + 1 < c->ev_match_cap; k++) {
+		for (int k = 0; timed_iterations && k < h->iters_run && 2 * k + 1 < c->ev_match_cap; k++) {
 			float ms = 0.f;
 			if (cudaEventElapsedTime(&ms, c->ev_match[2 * k], c->ev_match[2 * k + 1]) == cudaSuccess) mm += ms;
 		}

@@ -14,7 +14,7 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "libicp_b200.so"))
 DIST_SQ, DIST_SQRT, DIST_STD = 0, 1, 2
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
 NN_BRUTE, NN_GRID, NN_BRUTE_DIRECT = 0, 1, 2
-FLAG_FIX_REFLECTION = 1
+FLAG_FIX_REFLECTION, FLAG_PROFILE, FLAG_GRAPH = 1, 2, 4
 
 
 class Params(C.Structure):

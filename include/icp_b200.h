@@ -53,6 +53,11 @@ extern "C" {
 #define ICPB_FLAG_FIX_REFLECTION 1   /* if det(U*V^T) < 0 flip the singular vector of the smallest singular value (Kabsch);
                                         the reference keeps the reflection (src/ICP_point_to_point.cu:379-381) */
 
+#define ICPB_FLAG_PROFILE 2          /* per-iteration matching times wanted: never replay the loop from a CUDA graph */
+#define ICPB_FLAG_GRAPH   4          /* replay batches of `sync_every` iterations from a CUDA graph (problems below 4e9 pairs
+                                        per pass, one GPU). Identical results; match_ms is then reported as 0. Pays off only
+                                        when many registrations of one size reuse the instantiated graph. */
+
 typedef struct icpb_ctx icpb_ctx;
 
 typedef struct icpb_params {
@@ -77,7 +82,8 @@ typedef struct icpb_result {
 	float  last_R[9];       /* transform of the last iteration (d_temp_r / d_temp_T) */
 	float  last_T[3];
 	float  elapsed_ms;      /* cudaEvent time around the loop, as src/ICP_point_to_point.cu:294,424-426 */
-	float  match_ms;        /* part of elapsed_ms spent in the matching kernels */
+	float  match_ms;        /* part of elapsed_ms spent in the matching kernels (0 when the loop was replayed from a
+	                           CUDA graph, see ICPB_FLAG_GRAPH) */
 	double nn_pairs;        /* source x target pairs evaluated by brute-force matching (this rank) */
 } icpb_result;
 

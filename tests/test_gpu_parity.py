@@ -313,3 +313,25 @@ def test_reflection_fix_flag(ctx, ib, orc):
     U, S, Vt = np.linalg.svd(qc.T @ pc)
     assert np.abs(out[0] - U @ Vt).max() < 1e-5
     assert np.abs(out[ib.FLAG_FIX_REFLECTION] - U @ np.diag([1, 1, -1]) @ Vt).max() < 1e-5
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_graph_replay_equals_plain_loop(ctx, ib, orc, metric):
+    """ICPB_FLAG_GRAPH replays batches of iterations from a CUDA graph; the default is the plain loop.
+    Same errors, iteration counts and transform, bit for bit; repeated runs reuse the instantiated graph."""
+    D, M = orc.synth_p2p(128)
+    ctx.set_target(M)
+    mode = ib.DIST_SQRT if metric else ib.DIST_SQ
+    if metric:
+        ctx.estimate_normals(4)
+    out = []
+    G = ib.FLAG_GRAPH
+    for flags, sync in ((G, 0), (G, 0), (0, 0), (G, 3), (G | ib.FLAG_PROFILE, 1)):
+        ctx.set_source(D)
+        l0 = ctx.launch_count()
+        e, r = ctx.run(ib.default_params(metric=metric, dist_mode=mode, max_iter=50, flags=flags, sync_every=sync))
+        out.append((e.copy(), r.iterations, r.iterations_run, list(r.R), list(r.t), r.match_ms, ctx.launch_count() - l0))
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and o[1:5] == out[0][1:5]
+    assert out[0][5] == 0.0 and out[2][5] > 0.0, "match_ms is only measured in the plain loop"
+    assert out[0][2] == (5 if metric else 27)
