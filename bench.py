@@ -264,16 +264,21 @@ def main():
     hM = torch.from_numpy(M).pin_memory()
     hD_np, hM_np = hD.numpy(), hM.numpy()
     p = ib.default_params()
-    ctx.iterate_host(p, hD_np, hM_np)            # warm
+    # a genuine host-driven loop: every step uploads the CURRENT source and the target from pinned host memory, runs one
+    # iteration, and downloads the correspondences, the transform and the transformed source (which feeds the next step)
+    cur = hD_np
+    idx, R, T, rms = ctx.iterate_host(p, cur, hM_np)            # warm
+    cur = ctx.get_source()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        idx, R, T, rms = ctx.iterate_host(p, hD_np, hM_np)
+        idx, R, T, rms = ctx.iterate_host(p, cur, hM_np)
+        cur = ctx.get_source()
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
     e2e_value = float(n_total) * m * args.e2e_steps / e2e_s
     h2d = allsum(float(shard.nbytes + M.nbytes))
-    d2h = allsum(float(idx.nbytes + R.nbytes + T.nbytes + 4))
+    d2h = allsum(float(idx.nbytes + R.nbytes + T.nbytes + 4 + cur.nbytes))
 
     # per-GPU roofline of the dominant kernel (brute-force matching)
     pairs_rank = float(hi - lo) * m * args.steps
@@ -299,7 +304,7 @@ def main():
             "match_ms_per_step": match_total_ms / args.steps,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": "icpb_iterate_host (pinned host clouds -> idx, R, T, rms)", "steps": args.e2e_steps},
+                    "call": "icpb_iterate_host (pinned host clouds -> idx, R, T, rms) + icpb_get_source; host-driven loop, each step uploads the previous step's transformed source", "steps": args.e2e_steps},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,

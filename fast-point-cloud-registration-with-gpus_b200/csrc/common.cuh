@@ -65,6 +65,7 @@ struct ReduceParams {
 	const float4* nrm4;                                   // normals (point-to-plane)
 	u64*         keys;
 	int*         idx;
+	int*         seed;
 	int          n;
 	double*      partials;                                // [grid][32]
 	IterState*   st;
@@ -90,7 +91,7 @@ int  launch_moments(Ctx* c, int metric);
 int  launch_solve(Ctx* c, int metric);
 int  launch_transform(Ctx* c);
 int  launch_finish(Ctx* c);
-int  launch_pack_source(Ctx* c, const float* d_xyz, int n);
+int  launch_pack_source(Ctx* c, const float* d_xyz, int n, bool reset_seed);
 int  launch_unpack_source(Ctx* c, float* d_xyz);
 int  launch_pack_target(Ctx* c, const float* d_xyz, int m);
 int  launch_fp32_peak(Ctx* c, float* d_out, int iters, int blocks);
@@ -139,6 +140,8 @@ struct Ctx {
 	float *px = nullptr, *py = nullptr, *pz = nullptr;
 	u64*  keys = nullptr;
 	int*  idx = nullptr;
+	int*  seed = nullptr;        // last resolved correspondences: warm start of K1F; survives set_source of the same size
+	int   seed_n = -1;
 	float* dmin = nullptr;       // winning distance per source (icpb_match / icpb_time_match)
 	float* stage_xyz = nullptr;  // device AoS staging for H2D/D2H
 	size_t stage_cap = 0;

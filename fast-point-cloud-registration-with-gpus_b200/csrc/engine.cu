@@ -225,7 +225,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
 	dist_destroy(c->dist);
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
-	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->dmin);
+	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_stats);
 	if (c->st_host) cudaFreeHost(c->st_host);
@@ -265,6 +265,7 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 		if ((rc = dev_alloc(c, &c->nrm4, (size_t)0)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->nbr, (size_t)0)) != ICPB_OK) return rc;
 	}
+	if (m != c->m) c->seed_n = -1;      // seeds are indices into the target: only a different size invalidates them
 	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->step_state_ready = false; c->graph_gen++;
 	const float* src = xyz;
 	if (!on_device) {
@@ -292,6 +293,8 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 		if ((rc = dev_alloc(c, &c->pz, (size_t)cap)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->keys, (size_t)cap)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->idx, (size_t)cap)) != ICPB_OK) return rc;
+		if ((rc = dev_alloc(c, &c->seed, (size_t)cap)) != ICPB_OK) return rc;
+		c->seed_n = -1;
 		if ((rc = dev_alloc(c, &c->dmin, (size_t)cap)) != ICPB_OK) return rc;
 		c->n_cap = cap;
 	}
@@ -303,7 +306,11 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 		ICPB_CUDA(c, cudaMemcpyAsync(c->stage_xyz, xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
 		src = c->stage_xyz;
 	}
-	if ((rc = launch_pack_source(c, src, n)) != ICPB_OK) return rc;
+	// the warm-start seeds (last resolved correspondences) survive a new source of the same size against the same
+	// target: that is what a host-driven ICP loop uploads; any value in [0, m) is a valid seed, so this affects speed only
+	const bool reset_seed = (c->seed_n != n);
+	c->seed_n = n;
+	if ((rc = launch_pack_source(c, src, n, reset_seed)) != ICPB_OK) return rc;
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return ICPB_OK;
 }

@@ -359,7 +359,7 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	constexpr int SB = S * THREADS;
 	KFParams p;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
-	p.tiles7 = c->kf_tiles7; p.q4 = c->q4; p.seed_idx = c->kf_use_seed ? c->idx : nullptr; p.keys = c->keys;
+	p.tiles7 = c->kf_tiles7; p.q4 = c->q4; p.seed_idx = c->kf_use_seed ? c->seed : nullptr; p.keys = c->keys;
 	p.n = c->n; p.m = c->m; p.nt = c->kf_nt;
 	const int nb = (c->n + SB - 1) / SB;
 	p.units = (long long)nb * p.nt;

@@ -84,7 +84,7 @@ __device__ __forceinline__ int resolve_idx(const ReduceParams& p, int i)
 	// (src/ICP_point_to_point.cu:51-55 leaves idx[i] unwritten).
 	const u64 key = p.keys[i];
 	int j = p.idx[i];
-	if (key != KEY_UNMATCHED) { j = (int)(uint32_t)(key & 0xffffffffull); p.idx[i] = j; }
+	if (key != KEY_UNMATCHED) { j = (int)(uint32_t)(key & 0xffffffffull); p.idx[i] = j; p.seed[i] = j; }
 	return j;
 }
 
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(RB) transform_kernel(const ReduceParams p)
 // ------------------------------------------------------------------------------------------------
 // Layout kernels: AoS xyz <-> SoA, and the target re-tiling done once per registration
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_source_kernel(const float* __restrict__ xyz, int n, int n_cap, float* px, float* py, float* pz, u64* keys, int* idx)
+__global__ void pack_source_kernel(const float* __restrict__ xyz, int n, int n_cap, float* px, float* py, float* pz, u64* keys, int* idx, int* seed, int reset_seed)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_cap) return;
@@ -216,6 +216,7 @@ __global__ void pack_source_kernel(const float* __restrict__ xyz, int n, int n_c
 	if (i < n) { x = xyz[3 * (size_t)i]; y = xyz[3 * (size_t)i + 1]; z = xyz[3 * (size_t)i + 2]; }
 	px[i] = x; py[i] = y; pz[i] = z;
 	keys[i] = KEY_UNMATCHED; idx[i] = 0;
+	if (reset_seed) seed[i] = 0;
 }
 __global__ void unpack_source_kernel(const float* px, const float* py, const float* pz, int n, float* __restrict__ xyz)
 {
@@ -235,12 +236,12 @@ __global__ void pack_target_kernel(const float* __restrict__ xyz, int m, int m_p
 }
 
 // after a stand-alone matching step: keys -> idx (+ the winning distance)
-__global__ void resolve_kernel(const u64* keys, int* idx, float* dmin, int n, float sentinel)
+__global__ void resolve_kernel(const u64* keys, int* idx, int* seed, float* dmin, int n, float sentinel)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const u64 key = keys[i];
-	if (key != KEY_UNMATCHED) { idx[i] = (int)(uint32_t)(key & 0xffffffffull); dmin[i] = __uint_as_float((uint32_t)(key >> 32)); }
+	if (key != KEY_UNMATCHED) { idx[i] = (int)(uint32_t)(key & 0xffffffffull); seed[i] = idx[i]; dmin[i] = __uint_as_float((uint32_t)(key >> 32)); }
 	else dmin[i] = sentinel;
 }
 
@@ -268,7 +269,7 @@ static ReduceParams make_params(Ctx* c, int metric)
 	ReduceParams p;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
 	p.ox = c->px; p.oy = c->py; p.oz = c->pz;
-	p.q4 = c->q4; p.nrm4 = c->nrm4; p.keys = c->keys; p.idx = c->idx; p.n = c->n;
+	p.q4 = c->q4; p.nrm4 = c->nrm4; p.keys = c->keys; p.idx = c->idx; p.seed = c->seed; p.n = c->n;
 	p.partials = c->partials; p.st = c->st; p.errors = c->errors;
 	p.fuse_tail = (c->world == 1) ? 1 : 0;
 	p.metric = metric;
@@ -317,14 +318,14 @@ int launch_finish(Ctx* c)
 int launch_resolve(Ctx* c, float sentinel)
 {
 	if (c->n <= 0) return ICPB_OK;
-	resolve_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->keys, c->idx, c->dmin, c->n, sentinel);
+	resolve_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->keys, c->idx, c->seed, c->dmin, c->n, sentinel);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	return ICPB_OK;
 }
-int launch_pack_source(Ctx* c, const float* d_xyz, int n)
+int launch_pack_source(Ctx* c, const float* d_xyz, int n, bool reset_seed)
 {
-	pack_source_kernel<<<(c->n_cap + 255) / 256, 256, 0, c->stream>>>(d_xyz, n, c->n_cap, c->px, c->py, c->pz, c->keys, c->idx);
+	pack_source_kernel<<<(c->n_cap + 255) / 256, 256, 0, c->stream>>>(d_xyz, n, c->n_cap, c->px, c->py, c->pz, c->keys, c->idx, c->seed, reset_seed ? 1 : 0);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	return ICPB_OK;
