@@ -153,6 +153,8 @@ struct Ctx {
 	float   kf_rq = 0.f;                // >= max |q - centre|
 	int     kf_nt = 0;
 	unsigned long long* kf_stats = nullptr;
+	int*    kf_work_counter = nullptr;
+	int     kf_chunk_override = 0;      // ICPB_KF_CHUNK: tiles per work chunk
 	bool    kf_use_seed = true;         // warm start from the previous correspondences
 	double  kf_min_pairs = 1e9;         // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS)
 	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)

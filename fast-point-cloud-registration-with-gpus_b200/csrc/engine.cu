@@ -144,6 +144,7 @@ static int create_common(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_SEED")) c->kf_use_seed = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
+	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
 	*out = c;
 	return ICPB_OK;
 }
@@ -227,7 +228,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_stats);
+	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	if (c->st_host) cudaFreeHost(c->st_host);
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	for (int k = 0; k < 4; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
