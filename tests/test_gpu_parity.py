@@ -335,3 +335,18 @@ def test_graph_replay_equals_plain_loop(ctx, ib, orc, metric):
         assert np.array_equal(o[0], out[0][0]) and o[1:5] == out[0][1:5]
     assert out[0][5] == 0.0 and out[2][5] > 0.0, "match_ms is only measured in the plain loop"
     assert out[0][2] == (5 if metric else 27)
+
+
+def test_1m_full_registration_properties(ctx, ib, orc):
+    """BASELINE.json config 4 on one GPU: the whole 1M x 1M registration (45 iterations, more than the reference's
+    MAX_ITER 40): identity correspondences, ground-truth pose, monotone error."""
+    import icp_synth
+    D, M = icp_synth.p2p_clouds(1000)
+    ctx.set_target(M); ctx.set_source(D)
+    err, res = ctx.run(ib.default_params(max_iter=64))
+    assert res.iterations_run == 45
+    assert np.array_equal(ctx.correspondences(), np.arange(1000000))
+    assert np.abs(np.array(res.R[:]) - orc.euler_matrix([0.2, -0.2, 0.05])).max() < 1e-5
+    assert np.abs(np.array(res.t[:]) - [0.8, -0.3, 0.2]).max() < 1e-5
+    e = err[1: res.iterations_run + 1]
+    assert np.all(np.diff(e) < 1e-6) and e[-1] < 1e-5
