@@ -87,23 +87,28 @@ static int check_params(Ctx* c, const icpb_params* p)
 int launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel);   // nn dispatch (grid variant in grid_nn.cu)
 
 // one loop body, enqueued on the stream
-static int enqueue_iteration(Ctx* c, const icpb_params* p, cudaEvent_t e0, cudaEvent_t e1)
+// `ev`: nullptr, or 2 events (around the matching step), or — `phases` — 4 events bracketing matching, minimisation and
+// transformation + error, the phases the reference's instrumented programs time with dsecnd()
+// (src/CUDA/ICP_point_to_point_clean.cu:320-457).
+static int enqueue_iteration(Ctx* c, const icpb_params* p, cudaEvent_t* ev, bool phases)
 {
 	int rc;
-	if (e0) ICPB_CUDA(c, cudaEventRecord(e0, c->stream));
+	if (ev) ICPB_CUDA(c, cudaEventRecord(ev[0], c->stream));
 	if ((rc = launch_match(c, p->dist_mode, p->nn_method, p->sentinel)) != ICPB_OK) return rc;
-	if (e1) ICPB_CUDA(c, cudaEventRecord(e1, c->stream));
+	if (ev) ICPB_CUDA(c, cudaEventRecord(ev[1], c->stream));
 	if ((rc = launch_moments(c, p->metric)) != ICPB_OK) return rc;
 	if (c->world > 1) {
 		const int cnt = (p->metric == ICPB_POINT_TO_PLANE) ? 28 : 16;
 		if ((rc = dist_allreduce_f64(c->dist, c->st->moments, cnt, c->stream, c->err, sizeof c->err)) != ICPB_OK) return rc;
 		if ((rc = launch_solve(c, p->metric)) != ICPB_OK) return rc;
 	}
+	if (ev && phases) ICPB_CUDA(c, cudaEventRecord(ev[2], c->stream));
 	if ((rc = launch_transform(c)) != ICPB_OK) return rc;
 	if (c->world > 1) {
 		if ((rc = dist_allreduce_f64(c->dist, &c->st->err_sum, 1, c->stream, c->err, sizeof c->err)) != ICPB_OK) return rc;
 		if ((rc = launch_finish(c)) != ICPB_OK) return rc;
 	}
+	if (ev && phases) ICPB_CUDA(c, cudaEventRecord(ev[3], c->stream));
 	return ICPB_OK;
 }
 
@@ -444,8 +449,11 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	if ((rc = reset_state(c, &p)) != ICPB_OK) return rc;
 	if ((rc = launch_key_reset(c)) != ICPB_OK) return rc;
 
-	// one (start, stop) event pair per iteration around the matching kernel
-	const int want = 2 * p.max_iter;
+	// one (start, stop) event pair per iteration around the matching kernel; with ICPB_FLAG_PROFILE two more events
+	// split the rest of the iteration into minimisation and transformation + error
+	const bool phases = (p.flags & ICPB_FLAG_PROFILE) != 0;
+	const int epi = phases ? 4 : 2;
+	const int want = epi * p.max_iter;
 	if (want > c->ev_match_cap && want <= 4096) {
 		cudaEvent_t* ne = (cudaEvent_t*)realloc(c->ev_match, sizeof(cudaEvent_t) * (size_t)want);
 		if (ne) {
@@ -468,7 +476,7 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	bool timed_iterations = true;
 	if (use_graph) {
 		timed_iterations = false;
-		if ((rc = enqueue_iteration(c, &p, nullptr, nullptr)) != ICPB_OK) return rc;
+		if ((rc = enqueue_iteration(c, &p, nullptr, false)) != ICPB_OK) return rc;
 		enq = 1;
 		if ((rc = read_state(c)) != ICPB_OK) return rc;
 		if (!c->st_host->done) {
@@ -480,7 +488,7 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 				const long long l0 = c->launches;
 				cudaGraph_t g = nullptr;
 				ICPB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-				for (int b = 0; b < p.sync_every && rc == ICPB_OK; b++) rc = enqueue_iteration(c, &p, nullptr, nullptr);
+				for (int b = 0; b < p.sync_every && rc == ICPB_OK; b++) rc = enqueue_iteration(c, &p, nullptr, false);
 				cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
 				if (rc != ICPB_OK) { if (g) cudaGraphDestroy(g); return rc; }
 				if (ce != cudaSuccess) return fail_cuda(c, ce, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -504,9 +512,8 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	} else {
 		while (true) {
 			for (int b = 0; b < p.sync_every && enq < p.max_iter; b++, enq++) {
-				cudaEvent_t e0 = (2 * enq + 1 < c->ev_match_cap) ? c->ev_match[2 * enq] : nullptr;
-				cudaEvent_t e1 = e0 ? c->ev_match[2 * enq + 1] : nullptr;
-				if ((rc = enqueue_iteration(c, &p, e0, e1)) != ICPB_OK) return rc;
+				cudaEvent_t* ev = (epi * enq + epi - 1 < c->ev_match_cap) ? c->ev_match + epi * enq : nullptr;
+				if ((rc = enqueue_iteration(c, &p, ev, phases)) != ICPB_OK) return rc;
 			}
 			if ((rc = read_state(c)) != ICPB_OK) return rc;
 			if (c->st_host->done || enq >= p.max_iter) break;
@@ -524,12 +531,15 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 		memcpy(result->R, h->Rtot, sizeof h->Rtot); memcpy(result->t, h->ttot, sizeof h->ttot);
 		memcpy(result->last_R, h->R, sizeof h->R); memcpy(result->last_T, h->T, sizeof h->T);
 		cudaEventElapsedTime(&result->elapsed_ms, c->ev[0], c->ev[1]);
-		float mm = 0.f;
-		for (int k = 0; timed_iterations && k < h->iters_run && 2 * k + 1 < c->ev_match_cap; k++) {
+		float mm = 0.f, mn = 0.f, mt = 0.f;
+		for (int k = 0; timed_iterations && k < h->iters_run && epi * k + epi - 1 < c->ev_match_cap; k++) {
 			float ms = 0.f;
-			if (cudaEventElapsedTime(&ms, c->ev_match[2 * k], c->ev_match[2 * k + 1]) == cudaSuccess) mm += ms;
+			cudaEvent_t* ev = c->ev_match + epi * k;
+			if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) mm += ms;
+			if (phases && cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) mn += ms;
+			if (phases && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) mt += ms;
 		}
-		result->match_ms = mm;
+		result->match_ms = mm; result->minimize_ms = mn; result->transform_ms = mt;
 		result->nn_pairs = (double)h->iters_run * (double)c->n * (double)c->m;
 	}
 	return ICPB_OK;

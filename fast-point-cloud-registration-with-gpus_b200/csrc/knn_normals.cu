@@ -56,6 +56,10 @@ __device__ __forceinline__ void cand_insert(float (&kd)[KNN_CAND], int (&ki)[KNN
 	}
 }
 
+// SQRT_RANK: the canonical program ranks sqrt.rn distances (src/ICP_point_to_plane.cu:54-57); the dataset programs and the
+// "clean" variant rank the squared chain itself (src/CUDA/GPU_point_to_plane_bunny.cu:63,72), for which the candidate
+// list ordered by (d^2, index) already is the answer and no certificate is needed.
+template <bool SQRT_RANK>
 __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restrict__ qtiles, const float4* __restrict__ q4, int m, int nt, int k1,
                                                            int* __restrict__ nbr, int* __restrict__ flags)
 {
@@ -109,6 +113,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
 	}
 	if (!valid) return;
 
+	if constexpr (!SQRT_RANK) {
+		for (int p = 0; p < k1; p++) nbr[(size_t)i * k1 + p] = (kd[p] < 10000.0f && ki[p] != INT_MAX) ? ki[p] : 0;
+		flags[i] = 0;
+	} else {
 	// re-rank the candidates by (sqrt.rn distance, index), certify, emit
 	float ks[KNN_CAND];
 #pragma unroll
@@ -127,6 +135,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
 	}
 	for (int p = 0; p < k1; p++) nbr[(size_t)i * k1 + p] = (ks[p] < 10000.0f && ki[p] != INT_MAX) ? ki[p] : 0;
 	flags[i] = certified ? 0 : 1;
+	}
 }
 
 // Literal restatement of the reference procedure (src/ICP_point_to_plane.cu:30-44,61-69) for the queries
@@ -256,10 +265,13 @@ static int kn_stage(Ctx* c, size_t bytes)
 
 extern "C" {
 
-int icpb_estimate_normals(icpb_ctx* ctx, int k, float* elapsed_ms)
+int icpb_estimate_normals(icpb_ctx* ctx, int k, float* elapsed_ms) { return icpb_estimate_normals_ex(ctx, k, ICPB_DIST_SQRT, elapsed_ms); }
+
+int icpb_estimate_normals_ex(icpb_ctx* ctx, int k, int knn_dist_mode, float* elapsed_ms)
 {
 	if (!ctx) return ICPB_ERR_BADARG;
 	Ctx* c = C(ctx);
+	if (knn_dist_mode != ICPB_DIST_SQ && knn_dist_mode != ICPB_DIST_SQRT) { snprintf(c->err, sizeof c->err, "icpb_estimate_normals_ex: knn_dist_mode must be ICPB_DIST_SQ or ICPB_DIST_SQRT"); return ICPB_ERR_BADARG; }
 	ICPB_CUDA(c, cudaSetDevice(c->device));
 	if (c->m <= 0) { snprintf(c->err, sizeof c->err, "icpb_estimate_normals: set the target first"); return ICPB_ERR_STATE; }
 	if (k < 1 || k + 1 >= KNN_CAND) { snprintf(c->err, sizeof c->err, "icpb_estimate_normals: k must be in [1,%d]", KNN_CAND - 2); return ICPB_ERR_BADARG; }
@@ -270,10 +282,14 @@ int icpb_estimate_normals(icpb_ctx* ctx, int k, float* elapsed_ms)
 	if ((rc = kn_stage(c, sizeof(int) * (size_t)c->m)) != ICPB_OK) return rc;
 	int* flags = reinterpret_cast<int*>(c->stage_xyz);
 	ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-	knn_kernel<<<(c->m + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, c->stream>>>(c->qtiles, c->q4, c->m, c->nt, k1, c->nbr, flags);
-	c->launches++;
-	ICPB_CUDA(c, cudaGetLastError());
-	knn_exact_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->q4, c->m, k1, c->nbr, flags);
+	if (knn_dist_mode == ICPB_DIST_SQRT) {
+		knn_kernel<true><<<(c->m + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, c->stream>>>(c->qtiles, c->q4, c->m, c->nt, k1, c->nbr, flags);
+		c->launches++;
+		ICPB_CUDA(c, cudaGetLastError());
+		knn_exact_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->q4, c->m, k1, c->nbr, flags);
+	} else {
+		knn_kernel<false><<<(c->m + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, c->stream>>>(c->qtiles, c->q4, c->m, c->nt, k1, c->nbr, flags);
+	}
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	normals_kernel<<<(c->m + 127) / 128, 128, 0, c->stream>>>(c->q4, c->nbr, c->m, k, c->nrm4);

@@ -25,7 +25,7 @@ class Params(C.Structure):
 class Result(C.Structure):
     _fields_ = [("iterations", C.c_int), ("iterations_run", C.c_int), ("R", C.c_double * 9), ("t", C.c_double * 3),
                 ("last_R", C.c_float * 9), ("last_T", C.c_float * 3), ("elapsed_ms", C.c_float), ("match_ms", C.c_float),
-                ("nn_pairs", C.c_double)]
+                ("nn_pairs", C.c_double), ("minimize_ms", C.c_float), ("transform_ms", C.c_float)]
 
 
 def _load():
@@ -55,6 +55,10 @@ def _load():
         "icpb_transform": (C.c_int, [vp, fp]),
         "icpb_get_moments": (C.c_int, [vp, dp, C.c_int]),
         "icpb_estimate_normals": (C.c_int, [vp, C.c_int, fp]),
+        "icpb_estimate_normals_ex": (C.c_int, [vp, C.c_int, C.c_int, fp]),
+        "icpb_lidar_convert": (C.c_int, [vp, vp, C.c_int, C.c_ulonglong, fp, fp, C.c_int, C.c_int, C.c_int, vp, C.c_int, fp]),
+        "icpb_apply_transform": (C.c_int, [vp, fp, fp, vp, C.c_int, vp, C.c_int, fp]),
+        "icpb_scale_cloud": (C.c_int, [vp, C.c_float, vp, C.c_int, C.c_int]),
         "icpb_get_neighbors": (C.c_int, [vp, vp, C.c_int]),
         "icpb_get_normals": (C.c_int, [vp, vp, C.c_int]),
         "icpb_set_normals": (C.c_int, [vp, vp, C.c_int]),
@@ -172,10 +176,35 @@ class Context:
         self._ck(lib.icpb_get_moments(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), count), "get_moments")
         return out
 
-    def estimate_normals(self, k=4):
+    def estimate_normals(self, k=4, knn_dist_mode=DIST_SQRT):
         ms = C.c_float()
-        self._ck(lib.icpb_estimate_normals(self.h, k, C.byref(ms)), "estimate_normals")
+        self._ck(lib.icpb_estimate_normals_ex(self.h, k, knn_dist_mode, C.byref(ms)), "estimate_normals")
         return ms.value
+
+    def lidar_convert(self, ranges, encoder_count, altitude, azimuth, ticks_per_block=88, ticks_per_rev=90112):
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        altitude = np.ascontiguousarray(altitude, dtype=np.float32)
+        azimuth = np.ascontiguousarray(azimuth, dtype=np.float32)
+        out = np.empty((ranges.shape[0], 3), dtype=np.float32)
+        ms = C.c_float()
+        fpp = C.POINTER(C.c_float)
+        self._ck(lib.icpb_lidar_convert(self.h, _ptr(ranges), ranges.shape[0], int(encoder_count), altitude.ctypes.data_as(fpp),
+                                        azimuth.ctypes.data_as(fpp), altitude.shape[0], ticks_per_block, ticks_per_rev, _ptr(out), 0, C.byref(ms)), "lidar_convert")
+        return out, ms.value
+
+    def apply_transform(self, R, T, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        R = np.ascontiguousarray(R, dtype=np.float32).reshape(9)
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(3)
+        out = np.empty_like(xyz)
+        fpp = C.POINTER(C.c_float)
+        self._ck(lib.icpb_apply_transform(self.h, R.ctypes.data_as(fpp), T.ctypes.data_as(fpp), _ptr(xyz), xyz.shape[0], _ptr(out), 0, None), "apply_transform")
+        return out
+
+    def scale_cloud(self, alpha, xyz):
+        out = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3).copy()
+        self._ck(lib.icpb_scale_cloud(self.h, float(alpha), _ptr(out), out.shape[0], 0), "scale_cloud")
+        return out
 
     def neighbors(self, k=4):
         out = np.empty((self.m, k + 1), dtype=np.int32)

@@ -53,7 +53,8 @@ extern "C" {
 #define ICPB_FLAG_FIX_REFLECTION 1   /* if det(U*V^T) < 0 flip the singular vector of the smallest singular value (Kabsch);
                                         the reference keeps the reflection (src/ICP_point_to_point.cu:379-381) */
 
-#define ICPB_FLAG_PROFILE 2          /* per-iteration matching times wanted: never replay the loop from a CUDA graph */
+#define ICPB_FLAG_PROFILE 2          /* per-iteration phase times wanted (match_ms, minimize_ms, transform_ms): never replay the
+                                        loop from a CUDA graph */
 #define ICPB_FLAG_GRAPH   4          /* replay batches of `sync_every` iterations from a CUDA graph (problems below 4e9 pairs
                                         per pass, one GPU). Identical results; match_ms is then reported as 0. Pays off only
                                         when many registrations of one size reuse the instantiated graph. */
@@ -85,6 +86,9 @@ typedef struct icpb_result {
 	float  match_ms;        /* part of elapsed_ms spent in the matching kernels (0 when the loop was replayed from a
 	                           CUDA graph, see ICPB_FLAG_GRAPH) */
 	double nn_pairs;        /* source x target pairs evaluated by brute-force matching (this rank) */
+	float  minimize_ms;     /* with ICPB_FLAG_PROFILE: time of the minimisation step (moments, allreduce, solve) and of the */
+	float  transform_ms;    /* fused transformation + error + stop test — the phases the reference's instrumented programs
+	                           report (src/CUDA/ICP_point_to_point_clean.cu:464-481); 0 without the flag */
 } icpb_result;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -139,6 +143,10 @@ int  icpb_get_moments(icpb_ctx* ctx, double* mom, int count);
  * on the target: exact k+1 nearest (self first, lowest index first on ties, over sqrt'ed float
  * distances), PCA normal = eigenvector of the eigenvalue of smallest magnitude. No MxM matrix. */
 int  icpb_estimate_normals(icpb_ctx* ctx, int k, float* elapsed_ms);
+/* Same with the distance the k-NN ranks by: ICPB_DIST_SQRT = the canonical program (above); ICPB_DIST_SQ = the squared
+ * chain without sqrt, as the dataset programs and the "clean" variant do (src/CUDA/GPU_point_to_plane_bunny.cu:47-82,
+ * src/CUDA/ICP_point_to_plane_clean.cu) — the two orders differ where sqrt.rn merges neighbouring squares. */
+int  icpb_estimate_normals_ex(icpb_ctx* ctx, int k, int knn_dist_mode, float* elapsed_ms);
 int  icpb_get_neighbors(icpb_ctx* ctx, int* nbr /* m*(k+1), row-major */, int on_device);
 int  icpb_get_normals(icpb_ctx* ctx, float* normals /* 3*m AoS */, int on_device);
 int  icpb_set_normals(icpb_ctx* ctx, const float* normals, int on_device);
@@ -160,6 +168,25 @@ int  icpb_iterate_host(icpb_ctx* ctx, const icpb_params* params, const float* so
 int  icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int batch, const float* sources, int n,
                       const float* targets, int m, float* errors, int* iterations, double* R, double* t,
                       float* elapsed_ms);
+
+/* ---- dataset front ends ----------------------------------------------- */
+/* These work on caller buffers (host, or device when `on_device` != 0), not on the context's clouds; the context only
+ * supplies the device and the stream. `elapsed_ms` (optional) is the CUDA-event time of the kernel, which the
+ * reference prints ("Conversion kernel's elapsed time", src/CUDA/GPU_point_to_point_real.cu:557). */
+/* `Conversion<<<>>>` (src/CUDA/GPU_point_to_point_real.cu:20-36): polar -> Cartesian for an Ouster OS1 capture.
+ * Point i is beam i % beams of azimuth block i / beams; the encoder advances `ticks_per_block` (88) per block modulo
+ * `ticks_per_rev` (90112); theta = 2*pi*(count/ticks_per_rev + azimuth_deg[beam]/360), phi = 2*pi*altitude_deg[beam]/360
+ * in double rounded to float, then x = r*cos(theta)*cos(phi), y = -r*sin(theta)*cos(phi), z = r*sin(phi) in float.
+ * range: n floats (millimetres in the reference's capture); xyz_out: 3*n floats AoS. */
+int  icpb_lidar_convert(icpb_ctx* ctx, const float* range, int n, unsigned long long encoder_count, const float* altitude_deg,
+                        const float* azimuth_deg, int beams, int ticks_per_block, int ticks_per_rev, float* xyz_out, int on_device,
+                        float* elapsed_ms);
+/* `RyT<<<>>>` on an arbitrary cloud (src/CUDA/GPU_point_to_point_real.cu:113-123, used at :604 to synthesise the target
+ * from the scan): out = R*p + T with R column-major; same arithmetic as the loop's transformation step. in == out allowed. */
+int  icpb_apply_transform(icpb_ctx* ctx, const float R[9], const float T[3], const float* xyz_in, int n, float* xyz_out, int on_device,
+                          float* elapsed_ms);
+/* `cublasSscal(3*n, alpha)` (src/CUDA/GPU_point_to_point_real.cu:169-171, millimetres -> metres): xyz *= alpha in place. */
+int  icpb_scale_cloud(icpb_ctx* ctx, float alpha, float* xyz, int n, int on_device);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* Register-resident FFMA loop on every SM: the measured FP32 roofline denominator (TFLOP/s). */

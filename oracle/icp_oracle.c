@@ -455,7 +455,7 @@ ORC_API int orc_icp_cpu_f64(double* pt, int n, const double* q, int m, int max_i
  * (:406): distances are sqrt.rn.f32 of the Matching chain; k1 successive argmin scans with strict
  * `<` from 10000.0 (lowest index first on ties), each winner invalidated with 10000.0.
  * nbr is m x k1 row-major (:62). No m x m matrix is materialised here. */
-ORC_API void orc_knn_f32(const float* Q, int m, int k1, int* nbr)
+ORC_API void orc_knn_mode_f32(const float* Q, int m, int k1, int mode, int* nbr)
 {
 #pragma omp parallel
 	{
@@ -463,7 +463,7 @@ ORC_API void orc_knn_f32(const float* Q, int m, int k1, int* nbr)
 #pragma omp for schedule(static)
 		for (int i = 0; i < m; i++) {
 			float xp = Q[3 * (size_t)i], yp = Q[3 * (size_t)i + 1], zp = Q[3 * (size_t)i + 2];
-			for (int j = 0; j < m; j++) d[j] = orc_dist(ORC_MODE_SQRT, xp, yp, zp, Q[3 * (size_t)j], Q[3 * (size_t)j + 1], Q[3 * (size_t)j + 2]);
+			for (int j = 0; j < m; j++) d[j] = orc_dist(mode, xp, yp, zp, Q[3 * (size_t)j], Q[3 * (size_t)j + 1], Q[3 * (size_t)j + 2]);
 			for (int r = 0; r < k1; r++) {
 				float min = 10000.0f; int best = 0;
 				for (int j = 0; j < m; j++) if (d[j] < min) { min = d[j]; best = j; }
@@ -474,6 +474,11 @@ ORC_API void orc_knn_f32(const float* Q, int m, int k1, int* nbr)
 		free(d);
 	}
 }
+
+/* The canonical program's sqrt'ed distances (src/ICP_point_to_plane.cu:54-57). The dataset programs and the "clean"
+ * variant rank SQUARED distances instead (src/CUDA/GPU_point_to_plane_bunny.cu:63,72: same FADD/FMUL/FFMA/FFMA chain in
+ * SASS, no sqrt): orc_knn_mode_f32(..., ORC_MODE_SQ, ...). */
+ORC_API void orc_knn_f32(const float* Q, int m, int k1, int* nbr) { orc_knn_mode_f32(Q, m, k1, ORC_MODE_SQRT, nbr); }
 
 /* `Normals` steps 1-2 (src/ICP_point_to_plane.cu:80-101) + host eigen-solve (:431-439):
  * centroid bar = sum_{j=1..k} q_nbr/(float)k added term by term in float (:83-85, neighbour 0 = the
@@ -548,7 +553,7 @@ ORC_API int orc_plane_rt(const double C[36], const double b[6], float Rf[9], flo
 /* Whole point-to-plane loop, src/ICP_point_to_plane.cu:517-631 (normals computed before, :378-447).
  * Same conventions as orc_icp_p2p_f32; matching in SQRT mode (:172-174); the reported error is the
  * point-to-POINT RMS (:618-622). */
-ORC_API int orc_icp_p2plane_f32(float* P, int n, const float* Q, int m, const float* normals, float sentinel, int max_iter, double tol,
+ORC_API int orc_icp_p2plane_mode_f32(float* P, int n, const float* Q, int m, const float* normals, int mode, float sentinel, int max_iter, double tol,
 	float* errors, int* idx, double Rtot[9], double ttot[3], int* iters_run)
 {
 	for (int k = 0; k < 9; k++) Rtot[k] = (k % 4 == 0); for (int k = 0; k < 3; k++) ttot[k] = 0;
@@ -556,7 +561,7 @@ ORC_API int orc_icp_p2plane_f32(float* P, int n, const float* Q, int m, const fl
 	int iteration = 0, run = 0;
 	while (iteration < max_iter) {
 		double C[36], b[6], R[9], T[3]; float Rf[9], Tf[3];
-		orc_match_f32(P, n, Q, m, ORC_MODE_SQRT, sentinel, idx);
+		orc_match_f32(P, n, Q, m, mode, sentinel, idx);
 		orc_cxb(P, Q, idx, normals, n, C, b);
 		if (orc_plane_rt(C, b, Rf, Tf)) break;
 		for (int k = 0; k < 9; k++) R[k] = Rf[k]; for (int k = 0; k < 3; k++) T[k] = Tf[k];
@@ -570,4 +575,102 @@ ORC_API int orc_icp_p2plane_f32(float* P, int n, const float* Q, int m, const fl
 	}
 	if (iters_run) *iters_run = run;
 	return iteration;
+}
+
+/* The canonical program matches on sqrt'ed distances; the dataset programs on squared ones
+ * (src/CUDA/GPU_point_to_plane_bunny.cu:201,214): orc_icp_p2plane_mode_f32(..., ORC_MODE_SQ, ...). */
+ORC_API int orc_icp_p2plane_f32(float* P, int n, const float* Q, int m, const float* normals, float sentinel, int max_iter, double tol,
+	float* errors, int* idx, double Rtot[9], double ttot[3], int* iters_run)
+{
+	return orc_icp_p2plane_mode_f32(P, n, Q, m, normals, ORC_MODE_SQRT, sentinel, max_iter, tol, errors, idx, Rtot, ttot, iters_run);
+}
+
+/* ------------------------------------------------------------------------------------
+ * Dataset front ends
+ * ---------------------------------------------------------------------------------- */
+#include <stdio.h>
+
+/* `readData`, src/CUDA/GPU_point_to_point_bunny.cu:463-497: every whitespace-separated token of every line
+ * (separators " \n", lines of at most 2047 characters) becomes one float via strtof, in file order: x0 y0 z0 x1 ...
+ * Returns the number of floats stored (at most `cap`), or -1 when the file cannot be opened. */
+ORC_API int orc_read_cloud_text(const char* path, float* out, int cap)
+{
+	FILE* f = fopen(path, "r");
+	if (!f) return -1;
+	char line[2048]; int i = 0;
+	while (fgets(line, sizeof line, f) != NULL) {
+		char* save = NULL;
+		for (char* tok = strtok_r(line, " \n", &save); tok != NULL; tok = strtok_r(NULL, " \n", &save)) {
+			if (i < cap) out[i] = strtof(tok, NULL);
+			i++;
+		}
+	}
+	fclose(f);
+	return i < cap ? i : cap;
+}
+
+/* `Read_data` block 1, src/CUDA/GPU_point_to_point_real.cu:432-488: the capture is a text file with ONE BYTE of
+ * 64 Ouster OS1-16 UDP packets per line (12608 lines per packet, 788 per azimuth block). Lines 13-14 (1-based) of the
+ * first packet are the low bytes of its first encoder count; the 20-bit range word of channel c of block b of packet k
+ * sits on lines 17+12c+788b+12608k .. +2 (little endian, the third byte masked to 4 bits); the OS1-16 fires channels
+ * 2,6,...,62 of the 64-channel packet layout. A range is stored when the line AFTER its third byte has been read
+ * (`j > idx_line + 2`, :468), so the scan needs one more line than the last byte. Returns the number of ranges stored. */
+ORC_API int orc_lidar_parse_packets(const char* path, float* ranges, int n, unsigned long long* encoder_count)
+{
+	FILE* f = fopen(path, "r");
+	if (!f) return -1;
+	char line[128];
+	unsigned long enc = 0, word = 0;
+	int offset = 0, channel = 2, block = 0, packet = 0, j = 1;
+	while (fgets(line, sizeof line, f) != NULL) {
+		if (j == 13) enc = (unsigned long)atoi(line);
+		if (j == 14) enc = (unsigned long)(atoi(line) << 8) | enc;
+		int at = 17 + 12 * channel + 788 * block + 12608 * packet;
+		if (j == at) word = (unsigned long)atoi(line);
+		if (j == at + 1) word = (unsigned long)(atoi(line) << 8) | word;
+		if (j == at + 2) word = (unsigned long)((atoi(line) & 0xF) << 16) | word;
+		if (j > at + 2) { if (offset < n) ranges[offset] = (float)word; offset++; channel += 4; }
+		if (channel >= 64) { channel = 2; block++; }
+		if (block >= 16) { block = 0; packet++; }
+		if (packet >= 64) break;
+		j++;
+	}
+	fclose(f);
+	*encoder_count = enc;
+	return offset < n ? offset : n;
+}
+
+/* Beam angles, src/CUDA/GPU_point_to_point_real.cu:490-528: a 64-beam table under a header line; the 16 fitted beams
+ * are every 4th entry: altitude from lines 4,8,...,64, azimuth from lines 70,74,...,130 (1-based). */
+ORC_API int orc_lidar_read_beams(const char* path, float altitude[16], float azimuth[16])
+{
+	FILE* f = fopen(path, "r");
+	if (!f) return -1;
+	char line[128]; int j = 1, offset = 0;
+	while (fgets(line, sizeof line, f) != NULL) {
+		if (j == 2) offset = 0;
+		if (j >= 2 && j <= 65 && j % 4 == 0 && offset < 16) altitude[offset++] = (float)atof(line);
+		if (j == 68) offset = 0;
+		if (j >= 68 && j <= 131 && (j - 66) % 4 == 0 && offset < 16) azimuth[offset++] = (float)atof(line);
+		j++;
+	}
+	fclose(f);
+	return 0;
+}
+
+/* `Conversion`, src/CUDA/GPU_point_to_point_real.cu:20-36: point i = channel i%16 of azimuth block i/16; encoder
+ * ticks advance 88 per block modulo 90112 per revolution; theta and phi are evaluated in double and rounded to float;
+ * the products are float with the float cos/sin overloads (device code: cosf/sinf, <= 2 ulp; glibc's here), so this
+ * restatement agrees with the GPU kernels to a few ulp, not bit for bit: compare with a tolerance. */
+ORC_API void orc_lidar_convert(const float* r, int n, unsigned long long encoder_count, const float altitude[16], const float azimuth[16], float* xyz)
+{
+	for (int i = 0; i < n; i++) {
+		int block = i / 16, channel = i % 16;
+		unsigned long long counter = (encoder_count + (unsigned long long)block * 88ull) % 90112ull;
+		float theta = (float)(2 * M_PI * ((double)counter / 90112.0 + (double)azimuth[channel] / 360.0));
+		float phi = (float)(2 * M_PI * (double)altitude[channel] / 360.0);
+		xyz[3 * (size_t)i + 0] = r[i] * cosf(theta) * cosf(phi);
+		xyz[3 * (size_t)i + 1] = -r[i] * sinf(theta) * cosf(phi);
+		xyz[3 * (size_t)i + 2] = r[i] * sinf(phi);
+	}
 }

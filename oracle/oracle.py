@@ -39,6 +39,10 @@ def _ip(a): return a.ctypes.data_as(_i)
 _lib.orc_num_threads.restype = C.c_int
 _lib.orc_icp_p2p_f32.restype = C.c_int
 _lib.orc_icp_p2plane_f32.restype = C.c_int
+_lib.orc_icp_p2plane_mode_f32.restype = C.c_int
+_lib.orc_read_cloud_text.restype = C.c_int
+_lib.orc_lidar_parse_packets.restype = C.c_int
+_lib.orc_lidar_read_beams.restype = C.c_int
 _lib.orc_icp_cpu_f64.restype = C.c_int
 _lib.orc_rms.restype = C.c_double
 _lib.orc_plane_rt.restype = C.c_int
@@ -145,10 +149,10 @@ def icp_cpu_f64(width=100, max_iter=200, tol=1e-5):
     return {"iterations": it, "errors": E, "idx": idx, "R": R, "t": t, "D": D, "M": M, "pt": pt}
 
 
-def knn(Q, k1=5):
+def knn(Q, k1=5, mode=MODE_SQRT):
     Q = np.ascontiguousarray(Q, np.float32)
     nbr = np.zeros((Q.shape[0], k1), np.int32)
-    _lib.orc_knn_f32(_fp(Q), C.c_int(Q.shape[0]), C.c_int(k1), _ip(nbr))
+    _lib.orc_knn_mode_f32(_fp(Q), C.c_int(Q.shape[0]), C.c_int(k1), C.c_int(mode), _ip(nbr))
     return nbr
 
 
@@ -173,11 +177,63 @@ def plane_rt(Cm, b):
     return info, R, T
 
 
-def icp_p2plane(P, Q, nrm, sentinel=100000.0, max_iter=50, tol=1e-6):
+def icp_p2plane(P, Q, nrm, sentinel=100000.0, max_iter=50, tol=1e-6, mode=MODE_SQRT):
     P = np.ascontiguousarray(P, np.float32).copy(); Q = np.ascontiguousarray(Q, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
     n = P.shape[0]
     errors = np.zeros(max_iter + 1, np.float32); idx = np.zeros(n, np.int32)
     R = np.zeros(9); t = np.zeros(3); run = C.c_int()
-    it = _lib.orc_icp_p2plane_f32(_fp(P), C.c_int(n), _fp(Q), C.c_int(Q.shape[0]), _fp(nrm), C.c_float(sentinel), C.c_int(max_iter),
+    it = _lib.orc_icp_p2plane_mode_f32(_fp(P), C.c_int(n), _fp(Q), C.c_int(Q.shape[0]), _fp(nrm), C.c_int(mode), C.c_float(sentinel), C.c_int(max_iter),
                                   C.c_double(tol), _fp(errors), _ip(idx), _dp(R), _dp(t), C.byref(run))
     return {"iterations": it, "iterations_run": run.value, "errors": errors, "idx": idx, "R": R, "t": t, "P": P}
+
+
+# ---- dataset front ends ----------------------------------------------------
+def read_cloud_text(path, max_points=1 << 20):
+    buf = np.zeros(3 * max_points, np.float32)
+    n = _lib.orc_read_cloud_text(os.fsencode(path), _fp(buf), C.c_int(buf.size))
+    if n < 0:
+        raise OSError("cannot open %s" % path)
+    return buf[:n].copy()
+
+
+def lidar_parse_packets(path, n=16384):
+    r = np.zeros(n, np.float32)
+    enc = C.c_ulonglong()
+    k = _lib.orc_lidar_parse_packets(os.fsencode(path), _fp(r), C.c_int(n), C.byref(enc))
+    if k < 0:
+        raise OSError("cannot open %s" % path)
+    return r[:k].copy(), int(enc.value)
+
+
+def lidar_read_beams(path):
+    alt = np.zeros(16, np.float32); az = np.zeros(16, np.float32)
+    if _lib.orc_lidar_read_beams(os.fsencode(path), _fp(alt), _fp(az)) != 0:
+        raise OSError("cannot open %s" % path)
+    return alt, az
+
+
+def lidar_convert(ranges, encoder_count, altitude, azimuth):
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    out = np.zeros((ranges.shape[0], 3), np.float32)
+    _lib.orc_lidar_convert(_fp(ranges), C.c_int(ranges.shape[0]), C.c_ulonglong(encoder_count),
+                           _fp(np.ascontiguousarray(altitude, np.float32)), _fp(np.ascontiguousarray(azimuth, np.float32)), _fp(out))
+    return out
+
+
+def lidar_clouds(data_dir, n=16384):
+    """Read_data of the LiDAR programs (src/CUDA/GPU_point_to_point_real.cu:432-620) + the mm -> m scaling (:169-171):
+    source = converted scan, target = RyT(scan) with t = (0.001,-0.0202,0.02), r = (0.01,-0.003,0.05)."""
+    r, enc = lidar_parse_packets(os.path.join(data_dir, "Donut_1024x16.csv"), n)
+    alt, az = lidar_read_beams(os.path.join(data_dir, "beam_intrinsics.csv"))
+    P = lidar_convert(r, enc, alt, az)
+    Q = transform(P, euler_matrix([0.01, -0.003, 0.05]), np.array([0.001, -0.0202, 0.02], np.float32))
+    a = np.float32(1.0 / 1000.0)
+    return P * a, Q * a, (r, enc, alt, az, P, Q)
+
+
+def bunny_clouds(data_dir, n=8171):
+    """src/CUDA/GPU_point_to_point_bunny.cu:109-166: the data cloud and its copy moved by t = (0.01,-0.04,0.02),
+    r = (0.15,-0.1,0.05)."""
+    D = read_cloud_text(os.path.join(data_dir, "Bunny_res.csv"))[:3 * n].reshape(n, 3)
+    M = rigid_move(D, euler_matrix([0.15, -0.1, 0.05]), np.array([0.01, -0.04, 0.02], np.float32))
+    return D, M

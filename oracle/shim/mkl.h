@@ -223,4 +223,12 @@ static inline lapack_int LAPACKE_ssyev(int layout, char jobz, char uplo, lapack_
 	}
 	return 0;
 }
+
+/* ---- MSVC-only CRT calls used by the reference's dataset programs (src/CUDA/GPU_point_to_point_bunny.cu:468,480) ---- */
+#ifndef _MSC_VER
+#include <stdio.h>
+static inline int oracle_fopen_s(FILE** pf, const char* name, const char* mode) { *pf = fopen(name, mode); return *pf ? 0 : 1; }
+#define fopen_s(pf, name, mode) oracle_fopen_s((pf), (name), (mode))
+#define strtok_s(str, delim, ctx) strtok_r((str), (delim), (ctx))
+#endif
 #endif
