@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[3], the configuration its metric and target are 
 GPU): synthetic z = x^2 - y^2 saddle, 1 000 000 source x 1 000 000 target points, point-to-point ICP with
 exact brute-force nearest neighbours. A step = one ICP iteration (matching -> moments -> 3x3 SVD ->
 transform -> error). With N GPUs the SOURCE is sharded over the ranks, the target replicated, and the 16
-moment sums are combined by ncclAllReduce inside the library: total work is fixed => "scaling": "strong".
+moment sums are exchanged inside the library (in the reduction kernels over NVLink peer memory; ICPB_PEER=0
+selects ncclAllReduce launches instead): total work is fixed => "scaling": "strong".
 
 One JSON line on stdout (rank 0):
   value      NN pairs/s, whole job, inputs resident in HBM, device time (CUDA events on the engine's
@@ -298,7 +299,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic z=x^2-y^2, %dx%d points, point-to-point ICP, exact brute-force NN (BASELINE configs[3])" % (n_total, m),
                        "width": args.width, "step": "one ICP iteration: matching + moments + 3x3 SVD + transform + error",
-                       "parallelism": "source sharded x%d, target replicated, ncclAllReduce of 16 FP64 moments" % world,
+                       "parallelism": "source sharded x%d, target replicated, 16 FP64 moment sums %s" % (
+                           world, "exchanged inside the reduction kernels over NVLink peer memory (no collective launch)" if ctx.dist_info()["peer_exchange"]
+                           else ("combined with ncclAllReduce" if world > 1 else "(single GPU: no exchange)")),
                        "l2": "256 MiB device write between timed steps (untimed); timing = CUDA events per step on the engine stream"},
             "icp_iters_per_sec": args.steps / (total_ms * 1e-3),
             "match_ms_per_step": match_total_ms / args.steps,

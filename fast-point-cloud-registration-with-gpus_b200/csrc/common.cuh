@@ -58,6 +58,16 @@ struct K1Params {
 	const int*   count_dev;
 };
 
+// ---- peer-memory exchange (peer_exchange.cuh, dist.cpp) ---------------------------------------
+constexpr int PEER_MAX     = 8;     // ranks of one NVSwitch domain served by the fused exchange (more: NCCL path)
+constexpr int PEER_PAYLOAD = 32;    // doubles per row
+constexpr int PEER_ROW     = 40;    // payload + flag (u64) + pad: 320 B, a row never shares a 32 B sector with another rank's row
+struct PeerXchg {
+	int     rank, world;            // world == 0: exchange disabled (single GPU, or NCCL fallback)
+	u64*    seq;                    // device counter of completed exchanges (this rank)
+	double* mailbox[PEER_MAX];      // mailbox[r] = rank r's mailbox as mapped in this process (mailbox[rank] is local)
+};
+
 struct ReduceParams {
 	const float* px; const float* py; const float* pz;
 	float*       ox; float* oy; float* oz;               // transform output (in place allowed)
@@ -70,8 +80,10 @@ struct ReduceParams {
 	double*      partials;                                // [grid][32]
 	IterState*   st;
 	float*       errors;                                  // [max_iter + 1]
-	int          fuse_tail;                               // single GPU: the last block also runs the solve / bookkeeping
+	int          fuse_tail;                               // the last block also runs the solve / bookkeeping (single GPU, or
+	                                                      // several GPUs with the peer-memory exchange fused in)
 	int          metric;
+	PeerXchg     peer;                                    // peer.world > 1: exchange the sums inside the last block
 };
 
 // ---- error handling -----------------------------------------------------------------------------
@@ -101,6 +113,9 @@ struct Dist;
 int  dist_unique_id(void* id128);
 int  dist_init(Dist** out, int rank, int world, const void* id128, char* err, size_t errlen);
 int  dist_allreduce_f64(Dist* d, double* dev_buf, int count, cudaStream_t s, char* err, size_t errlen);
+// Maps every rank's mailbox into this process (CUDA IPC, handles exchanged with ncclAllGather); all ranks agree
+// (ncclAllReduce min) on whether the fused exchange can be used. out->world stays 0 when it cannot.
+int  dist_peer_init(Dist* d, int device, cudaStream_t s, PeerXchg* out, char* err, size_t errlen);
 void dist_destroy(Dist* d);
 
 // ---- the context ---------------------------------------------------------------------------------
@@ -114,6 +129,8 @@ struct Ctx {
 	// distributed
 	int rank = 0, world = 1;
 	Dist* dist = nullptr;
+	double n_total = 0.0; bool n_total_valid = false;   // global source count (all ranks), refreshed after icpb_set_source
+	PeerXchg peer = {};           // peer.world > 1: moments / residual sums are exchanged inside K2/K7/K4 over peer memory
 
 	// target
 	int m = 0, nt = 0;

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace icpb {
@@ -21,6 +22,7 @@ struct NcclApi {
 	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
@@ -38,9 +40,10 @@ static NcclApi& nccl_api()
 		api.GetUniqueId    = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
 		api.CommInitRank   = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
 		api.AllReduce      = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+		api.AllGather      = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
 		api.CommDestroy    = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
 		api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-		api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+		api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.AllGather && api.CommDestroy && api.GetErrorString;
 		if (!api.ok) snprintf(api.why, sizeof api.why, "libnccl is missing a required symbol");
 	});
 	return api;
@@ -49,6 +52,10 @@ static NcclApi& nccl_api()
 struct Dist {
 	ncclComm_t comm = nullptr;
 	int rank = 0, world = 1;
+	// peer-memory exchange (peer_exchange.cuh)
+	double* mailbox = nullptr;                 // this rank's mailbox (cudaMalloc)
+	u64*    seq = nullptr;
+	void*   peer_ptr[PEER_MAX] = {nullptr};    // cudaIpcOpenMemHandle mappings of the other ranks' mailboxes
 };
 
 static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
@@ -85,9 +92,63 @@ int dist_allreduce_f64(Dist* d, double* dev_buf, int count, cudaStream_t s, char
 	return ICPB_OK;
 }
 
+// One mailbox per rank, mapped into every peer with CUDA IPC. The handles travel through ncclAllGather (the only
+// channel the C ABI has between ranks), and an ncclAllReduce(min) makes the decision unanimous: the fused exchange is
+// used only if EVERY rank could map EVERY mailbox (one process per GPU on one NVLink/NVSwitch node). ICPB_PEER=0
+// forces the NCCL path (A/B measurements).
+int dist_peer_init(Dist* d, int device, cudaStream_t s, PeerXchg* out, char* err, size_t errlen)
+{
+	memset(out, 0, sizeof *out);
+	if (!d || d->world < 2) return ICPB_OK;
+	NcclApi& a = nccl_api();
+	int mine = (d->world <= PEER_MAX) ? 1 : 0;
+	if (const char* e = getenv("ICPB_PEER")) if (atoi(e) == 0) mine = 0;
+	const size_t mbytes = sizeof(double) * 2 * PEER_MAX * PEER_ROW;
+	cudaIpcMemHandle_t* d_handles = nullptr;      // [world] on the device for the allgather
+	int* d_flag = nullptr;
+	cudaIpcMemHandle_t h_handles[PEER_MAX];
+	memset(h_handles, 0, sizeof h_handles);
+	auto cleanup = [&] { cudaFree(d_handles); cudaFree(d_flag); };
+	if (cudaMalloc((void**)&d_flag, sizeof(int)) != cudaSuccess) { snprintf(err, errlen, "dist_peer_init: cudaMalloc failed"); return ICPB_ERR_NOMEM; }
+	if (mine) {
+		if (cudaMalloc((void**)&d->mailbox, mbytes) != cudaSuccess || cudaMalloc((void**)&d->seq, sizeof(u64)) != cudaSuccess ||
+		    cudaMalloc((void**)&d_handles, sizeof(cudaIpcMemHandle_t) * PEER_MAX) != cudaSuccess) mine = 0;
+	}
+	if (mine) {
+		cudaMemsetAsync(d->mailbox, 0, mbytes, s); cudaMemsetAsync(d->seq, 0, sizeof(u64), s);
+		if (cudaIpcGetMemHandle(&h_handles[d->rank], d->mailbox) != cudaSuccess) { cudaGetLastError(); mine = 0; }
+	}
+	// every rank takes part in both collectives whatever its own state: the calls must match across ranks
+	if (!d_handles && cudaMalloc((void**)&d_handles, sizeof(cudaIpcMemHandle_t) * PEER_MAX) != cudaSuccess) { cleanup(); snprintf(err, errlen, "dist_peer_init: cudaMalloc failed"); return ICPB_ERR_NOMEM; }
+	cudaMemcpyAsync(d_handles + d->rank, &h_handles[d->rank], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, s);
+	if (d->world <= PEER_MAX) {
+		ncclResult_t r = a.AllGather(d_handles + d->rank, d_handles, sizeof(cudaIpcMemHandle_t), ncclChar, d->comm, s);
+		if (r != ncclSuccess) { cleanup(); snprintf(err, errlen, "ncclAllGather: %s", a.GetErrorString(r)); return ICPB_ERR_NCCL; }
+		cudaMemcpyAsync(h_handles, d_handles, sizeof(cudaIpcMemHandle_t) * d->world, cudaMemcpyDeviceToHost, s);
+	}
+	if (cudaStreamSynchronize(s) != cudaSuccess) { cleanup(); snprintf(err, errlen, "dist_peer_init: stream error"); return ICPB_ERR_CUDA; }
+	for (int r = 0; mine && r < d->world; r++) {
+		if (r == d->rank) continue;
+		if (cudaIpcOpenMemHandle(&d->peer_ptr[r], h_handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peer_ptr[r] = nullptr; mine = 0; }
+	}
+	cudaMemcpyAsync(d_flag, &mine, sizeof(int), cudaMemcpyHostToDevice, s);
+	ncclResult_t r = a.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, d->comm, s);
+	if (r != ncclSuccess) { cleanup(); snprintf(err, errlen, "ncclAllReduce: %s", a.GetErrorString(r)); return ICPB_ERR_NCCL; }
+	int all = 0;
+	cudaMemcpyAsync(&all, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+	if (cudaStreamSynchronize(s) != cudaSuccess) { cleanup(); snprintf(err, errlen, "dist_peer_init: stream error"); return ICPB_ERR_CUDA; }
+	cleanup();
+	if (!all) return ICPB_OK;                 // somebody could not: everybody stays on ncclAllReduce
+	out->rank = d->rank; out->world = d->world; out->seq = d->seq;
+	for (int k = 0; k < d->world; k++) out->mailbox[k] = (k == d->rank) ? d->mailbox : reinterpret_cast<double*>(d->peer_ptr[k]);
+	return ICPB_OK;
+}
+
 void dist_destroy(Dist* d)
 {
 	if (!d) return;
+	for (int r = 0; r < PEER_MAX; r++) if (d->peer_ptr[r]) cudaIpcCloseMemHandle(d->peer_ptr[r]);
+	cudaFree(d->mailbox); cudaFree(d->seq);
 	NcclApi& a = nccl_api();
 	if (a.ok && d->comm) a.CommDestroy(d->comm);
 	delete d;

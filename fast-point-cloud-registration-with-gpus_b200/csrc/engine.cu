@@ -60,10 +60,18 @@ static int reset_state(Ctx* c, const icpb_params* p)
 	h->n_total = (double)c->n;
 	for (int k = 0; k < 9; k++) h->Rtot[k] = (k % 4 == 0) ? 1.0 : 0.0;
 	for (int k = 0; k < 9; k++) h->R[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+	// the global point count changes only when a rank uploads a shard of another size: one allreduce per such upload
+	// (every rank calls icpb_set_source the same number of times), not one per run
+	const bool count_known = c->world > 1 && c->n_total_valid;
+	if (count_known) h->n_total = c->n_total;
 	ICPB_CUDA(c, cudaMemcpyAsync(c->st, h, sizeof *h, cudaMemcpyHostToDevice, c->stream));
-	if (c->world > 1) {
+	if (c->world > 1 && !count_known) {
 		int rc = dist_allreduce_f64(c->dist, &c->st->n_total, 1, c->stream, c->err, sizeof c->err);
 		if (rc != ICPB_OK) return rc;
+		double nt = 0.0;
+		ICPB_CUDA(c, cudaMemcpyAsync(&nt, &c->st->n_total, sizeof nt, cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->n_total = nt; c->n_total_valid = true;
 	}
 	int rc = ensure_errors(c, p->max_iter + 2);
 	if (rc != ICPB_OK) return rc;
@@ -97,14 +105,15 @@ static int enqueue_iteration(Ctx* c, const icpb_params* p, cudaEvent_t* ev, bool
 	if ((rc = launch_match(c, p->dist_mode, p->nn_method, p->sentinel)) != ICPB_OK) return rc;
 	if (ev) ICPB_CUDA(c, cudaEventRecord(ev[1], c->stream));
 	if ((rc = launch_moments(c, p->metric)) != ICPB_OK) return rc;
-	if (c->world > 1) {
+	const bool nccl_exchange = c->world > 1 && c->peer.world < 2;   // otherwise the exchange happens inside K2/K7/K4
+	if (nccl_exchange) {
 		const int cnt = (p->metric == ICPB_POINT_TO_PLANE) ? 28 : 16;
 		if ((rc = dist_allreduce_f64(c->dist, c->st->moments, cnt, c->stream, c->err, sizeof c->err)) != ICPB_OK) return rc;
 		if ((rc = launch_solve(c, p->metric)) != ICPB_OK) return rc;
 	}
 	if (ev && phases) ICPB_CUDA(c, cudaEventRecord(ev[2], c->stream));
 	if ((rc = launch_transform(c)) != ICPB_OK) return rc;
-	if (c->world > 1) {
+	if (nccl_exchange) {
 		if ((rc = dist_allreduce_f64(c->dist, &c->st->err_sum, 1, c->stream, c->err, sizeof c->err)) != ICPB_OK) return rc;
 		if ((rc = launch_finish(c)) != ICPB_OK) return rc;
 	}
@@ -216,6 +225,7 @@ int icpb_create_dist(icpb_ctx** out, int device, int rank, int world, const void
 	if (world > 1) {
 		if (!nccl_unique_id) { icpb_destroy(reinterpret_cast<icpb_ctx*>(c)); return ICPB_ERR_BADARG; }
 		rc = dist_init(&c->dist, rank, world, nccl_unique_id, c->err, sizeof c->err);
+		if (rc == ICPB_OK) rc = dist_peer_init(c->dist, device, c->stream, &c->peer, c->err, sizeof c->err);
 		if (rc != ICPB_OK) { icpb_destroy(reinterpret_cast<icpb_ctx*>(c)); return rc; }
 	}
 	*out = reinterpret_cast<icpb_ctx*>(c);
@@ -256,6 +266,15 @@ int icpb_device_info(const icpb_ctx* ctx, int* sm_count, int* sm_clock_khz, char
 }
 
 long long icpb_launch_count(const icpb_ctx* ctx) { return ctx ? C(ctx)->launches : 0; }
+
+int icpb_dist_info(const icpb_ctx* ctx, int* rank, int* world, int* peer_exchange)
+{
+	if (!ctx) return ICPB_ERR_BADARG;
+	if (rank) *rank = C(ctx)->rank;
+	if (world) *world = C(ctx)->world;
+	if (peer_exchange) *peer_exchange = C(ctx)->peer.world > 1 ? 1 : 0;
+	return ICPB_OK;
+}
 
 // ---- clouds ---------------------------------------------------------------------------------------
 int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
@@ -305,6 +324,7 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 		c->n_cap = cap;
 	}
 	c->n = n; c->step_state_ready = false;   // the control block caches the global point count
+	c->n_total_valid = false;
 	c->graph_gen++;
 	const float* src = xyz;
 	if (!on_device && n > 0) {
@@ -395,11 +415,12 @@ int icpb_minimize(icpb_ctx* ctx, int metric, float R[9], float T[3])
 	int rc;
 	if ((rc = ensure_step_state(c)) != ICPB_OK) return rc;
 	if ((rc = launch_moments(c, metric)) != ICPB_OK) return rc;
-	if (c->world > 1) {
+	if (c->world > 1 && c->peer.world < 2) {
 		if ((rc = dist_allreduce_f64(c->dist, c->st->moments, metric == ICPB_POINT_TO_PLANE ? 28 : 16, c->stream, c->err, sizeof c->err)) != ICPB_OK) return rc;
 		if ((rc = launch_solve(c, metric)) != ICPB_OK) return rc;
 	}
 	if ((rc = read_state(c)) != ICPB_OK) return rc;
+	if (c->st_host->numeric_error == 100) return fail(c, ICPB_ERR_NCCL, "peer-memory exchange timed out: a rank never published its moment sums");
 	if (c->st_host->numeric_error) return fail(c, ICPB_ERR_NUMERIC, "6x6 normal equations are not positive definite");
 	if (R) memcpy(R, c->st_host->R, sizeof(float) * 9);
 	if (T) memcpy(T, c->st_host->T, sizeof(float) * 3);
@@ -414,7 +435,7 @@ int icpb_transform(icpb_ctx* ctx, float* rms)
 	int rc;
 	if ((rc = ensure_step_state(c)) != ICPB_OK) return rc;
 	if ((rc = launch_transform(c)) != ICPB_OK) return rc;
-	if (c->world > 1) {
+	if (c->world > 1 && c->peer.world < 2) {
 		if ((rc = dist_allreduce_f64(c->dist, &c->st->err_sum, 1, c->stream, c->err, sizeof c->err)) != ICPB_OK) return rc;
 		if ((rc = launch_finish(c)) != ICPB_OK) return rc;
 	}
@@ -523,6 +544,7 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	ICPB_CUDA(c, cudaMemcpyAsync(c->errors_host, c->errors, sizeof(float) * (size_t)(p.max_iter + 1), cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	const IterState* h = c->st_host;
+	if (h->numeric_error == 100) return fail(c, ICPB_ERR_NCCL, "peer-memory exchange timed out: a rank never published its moment sums");
 	if (h->numeric_error) return fail(c, ICPB_ERR_NUMERIC, "6x6 normal equations are not positive definite");
 	if (errors) memcpy(errors, c->errors_host, sizeof(float) * (size_t)(p.max_iter + 1));
 	if (result) {

@@ -16,6 +16,7 @@
 // can be combined with one ncclAllReduce; centring is done afterwards: W = sum q p^T - N qbar pbar^T.
 #include "common.cuh"
 #include "solve_device.cuh"
+#include "peer_exchange.cuh"
 
 namespace icpb {
 
@@ -109,9 +110,12 @@ __global__ void __launch_bounds__(RB) moments_p2p_kernel(const ReduceParams p)
 	double* row = p.partials + (size_t)blockIdx.x * 32;
 	block_reduce<15>(acc, red, row);
 	if (last_block_sum<15>(p.partials, &p.st->ticket_a, p.st->moments)) {
+		if (threadIdx.x == 0) p.st->moments[15] = (double)p.n;
+		bool ok = true;
+		if (p.peer.world > 1) { __syncthreads(); ok = peer_allreduce_block(p.peer, p.st->moments, 16); }
 		if (threadIdx.x == 0) {
-			p.st->moments[15] = (double)p.n;
-			if (p.fuse_tail) solve_p2p(p.st);
+			if (!ok) { p.st->numeric_error = 100; p.st->done = 1; }
+			else if (p.fuse_tail) solve_p2p(p.st);
 		}
 	}
 }
@@ -147,9 +151,12 @@ __global__ void __launch_bounds__(RB) moments_p2plane_kernel(const ReduceParams 
 	double* row = p.partials + (size_t)blockIdx.x * 32;
 	block_reduce<27>(acc, red, row);
 	if (last_block_sum<27>(p.partials, &p.st->ticket_a, p.st->moments)) {
+		if (threadIdx.x == 0) p.st->moments[27] = (double)p.n;
+		bool ok = true;
+		if (p.peer.world > 1) { __syncthreads(); ok = peer_allreduce_block(p.peer, p.st->moments, 28); }
 		if (threadIdx.x == 0) {
-			p.st->moments[27] = (double)p.n;
-			if (p.fuse_tail) solve_p2plane(p.st);
+			if (!ok) { p.st->numeric_error = 100; p.st->done = 1; }
+			else if (p.fuse_tail) solve_p2plane(p.st);
 		}
 	}
 }
@@ -201,7 +208,12 @@ __global__ void __launch_bounds__(RB) transform_kernel(const ReduceParams p)
 	double* row = p.partials + (size_t)blockIdx.x * 32;
 	block_reduce<1>(acc, red, row);
 	if (last_block_sum<1>(p.partials, &p.st->ticket_b, &p.st->err_sum)) {
-		if (threadIdx.x == 0 && p.fuse_tail) finish_iteration(p.st, p.errors);
+		bool ok = true;
+		if (p.peer.world > 1) ok = peer_allreduce_block(p.peer, &p.st->err_sum, 1);
+		if (threadIdx.x == 0) {
+			if (!ok) { p.st->numeric_error = 100; p.st->done = 1; }
+			else if (p.fuse_tail) finish_iteration(p.st, p.errors);
+		}
 	}
 }
 
@@ -271,7 +283,8 @@ static ReduceParams make_params(Ctx* c, int metric)
 	p.ox = c->px; p.oy = c->py; p.oz = c->pz;
 	p.q4 = c->q4; p.nrm4 = c->nrm4; p.keys = c->keys; p.idx = c->idx; p.seed = c->seed; p.n = c->n;
 	p.partials = c->partials; p.st = c->st; p.errors = c->errors;
-	p.fuse_tail = (c->world == 1) ? 1 : 0;
+	p.peer = c->peer;
+	p.fuse_tail = (c->world == 1 || c->peer.world > 1) ? 1 : 0;
 	p.metric = metric;
 	return p;
 }

@@ -42,6 +42,7 @@ def _load():
         "icpb_create": (C.c_int, [C.POINTER(vp), C.c_int]),
         "icpb_nccl_unique_id": (C.c_int, [vp]),
         "icpb_create_dist": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]),
+        "icpb_dist_info": (C.c_int, [vp, ip, ip, ip]),
         "icpb_destroy": (C.c_int, [vp]),
         "icpb_last_error": (C.c_char_p, [vp]),
         "icpb_device_info": (C.c_int, [vp, ip, ip, C.c_char_p]),
@@ -272,6 +273,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(lib.icpb_get_filter_stats(self.h, C.byref(a), C.byref(b)), "get_filter_stats")
         return {"subtile_tests": a.value, "subtile_exact": b.value}
+
+    def dist_info(self):
+        r, w, p = C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib.icpb_dist_info(self.h, C.byref(r), C.byref(w), C.byref(p)), "dist_info")
+        return {"rank": r.value, "world": w.value, "peer_exchange": bool(p.value)}
 
     def launch_count(self):
         return int(lib.icpb_launch_count(self.h))

@@ -104,10 +104,15 @@ int         icpb_device_count(int* count);
 int  icpb_create(icpb_ctx** out, int device);
 /* Multi-GPU: one context per process/GPU. Source points are sharded (each rank passes its own
  * shard to icpb_set_source), the target is replicated, and the per-iteration moment partials are
- * combined with ncclAllReduce. `nccl_unique_id` is the 128-byte ncclUniqueId made by rank 0 with
+ * combined across ranks (inside the kernels over peer memory, or with ncclAllReduce). `nccl_unique_id` is the 128-byte ncclUniqueId made by rank 0 with
  * icpb_nccl_unique_id and handed to every rank by the caller (MPI, torch.distributed, a file...). */
 int  icpb_nccl_unique_id(void* id128);
 int  icpb_create_dist(icpb_ctx** out, int device, int rank, int world, const void* nccl_unique_id);
+/* `peer_exchange` = 1 when the per-iteration sums are exchanged INSIDE the reduction kernels through peer memory
+ * (NVLink/NVSwitch; every rank's mailbox mapped into every process with CUDA IPC at icpb_create_dist time), 0 when
+ * they go through ncclAllReduce launches between the kernels (more than 8 ranks, ranks that cannot map each other's
+ * memory, or ICPB_PEER=0 in the environment). All ranks always agree on the choice. */
+int  icpb_dist_info(const icpb_ctx* ctx, int* rank, int* world, int* peer_exchange);
 int  icpb_destroy(icpb_ctx* ctx);
 const char* icpb_last_error(const icpb_ctx* ctx);
 int  icpb_device_info(const icpb_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name64);

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _rank(rank, world, uid, W, metric, q):
+def _rank(rank, world, uid, W, metric, q, peer=1):
+    os.environ["ICPB_PEER"] = str(peer)
     sys.path.insert(0, os.path.join(ROOT, "fast-point-cloud-registration-with-gpus_b200", "python"))
     import icp_b200 as ib
     import icp_dist
@@ -25,13 +26,17 @@ def _rank(rank, world, uid, W, metric, q):
     mode = ib.DIST_SQRT if metric else ib.DIST_SQ
     if metric:
         ctx.estimate_normals(4)
+    launches0 = ctx.launch_count()
     err, res = ctx.run(ib.default_params(metric=metric, dist_mode=mode, max_iter=50))
-    q.put((rank, lo, hi, err, res.iterations, res.iterations_run, list(res.R), list(res.t), ctx.correspondences()))
+    launches = ctx.launch_count() - launches0
+    q.put((rank, lo, hi, err, res.iterations, res.iterations_run, list(res.R), list(res.t), ctx.correspondences(),
+           ctx.dist_info()["peer_exchange"], launches))
     ctx.close()
 
 
-@pytest.mark.parametrize("metric,W", [(0, 128), (1, 128), (0, 300)])
-def test_two_gpus_reproduce_one_gpu(ib, metric, W):
+@pytest.mark.parametrize("metric,W,peer", [(0, 128, 1), (1, 128, 1), (0, 300, 1), (0, 128, 0), (1, 128, 0)])
+def test_two_gpus_reproduce_one_gpu(ib, metric, W, peer):
+    """peer=1: sums exchanged inside K2/K7/K4 over peer memory (the default); peer=0: ncclAllReduce between kernels."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -40,7 +45,7 @@ def test_two_gpus_reproduce_one_gpu(ib, metric, W):
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     uid = ib.nccl_unique_id()
-    procs = [mpc.Process(target=_rank, args=(r, 2, uid, W, metric, q)) for r in range(2)]
+    procs = [mpc.Process(target=_rank, args=(r, 2, uid, W, metric, q, peer)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=300) for _ in procs])
@@ -56,7 +61,10 @@ def test_two_gpus_reproduce_one_gpu(ib, metric, W):
             ctx.estimate_normals(4)
         err, res = ctx.run(ib.default_params(metric=metric, dist_mode=mode, max_iter=50))
         idx = ctx.correspondences()
-    for rank, lo, hi, e, it, run, R, t, sub_idx in out:
+    for rank, lo, hi, e, it, run, R, t, sub_idx, peer_on, launches in out:
+        assert peer_on == bool(peer), "fused peer-memory exchange %s" % ("not active" if peer else "active despite ICPB_PEER=0")
+        # fused: 3 kernels per iteration as on one GPU (+ the key reset); NCCL path: 5 of ours per iteration + 2 allreduces
+        assert launches <= (3 if peer else 5) * (run + 4) + 8, (launches, run)       # up to sync_every = 4 iterations are enqueued past the stop flag
         assert (it, run) == (res.iterations, res.iterations_run)
         k = res.iterations + 2
         assert np.all(np.abs(e[:k] - err[:k]) <= 1e-6 * np.abs(err[:k]) + 1e-7)
