@@ -286,6 +286,7 @@ def main():
     achieved = 8.0 * pairs_rank / (sum(match_ms) * 1e-3) * 1e-12
     achieved = allmax(-achieved) * -1.0 if world > 1 else achieved      # the slowest rank's figure
 
+    fcfg = ctx.filter_config()
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
@@ -313,11 +314,11 @@ def main():
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
-                         "kernel": "k1_filter (brute-force NN: 3-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)",
-                         "flop_per_pair": 8, "traffic": traffic,
+                         "kernel": "k1_filter (brute-force NN: a %d-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)" % fcfg["dims_last"],
+                         "flop_per_pair": 8, "filter": fcfg, "traffic": traffic,
                          "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "note": "compute-bound (FP32 pipe / register-file bandwidth); algorithmic 8 FLOP per pair as SURVEY.md 8(d) defines; "
-                                 "the direct form needs 6 FP32 ops per pair (ceiling 66.7% of FFMA peak), the filter 3"},
+                         "note": "compute-bound (FP32 issue slots); `achieved` counts the ALGORITHMIC 8 FLOP per pair SURVEY.md 8(d) defines, so frac can exceed 1: "
+                                 "the direct form executes 6 FP32 ops per pair (ceiling 66.7% of FFMA peak), the filter 3 (full bound) or 2 (planar bound) FMAs per pair"},
             "roofline_direct_kernel": {"kernel": "k1_match (reference chain on every pair)", "ms_per_launch": direct_ms,
                                        "achieved": 8.0 * float(hi - lo) * m / (direct_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
                                        "frac": 8.0 * float(hi - lo) * m / (direct_ms * 1e-3) * 1e-12 / fp32_peak},

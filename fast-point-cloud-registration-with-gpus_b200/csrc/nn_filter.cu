@@ -18,22 +18,33 @@
 // sub-tile order => lowest index). thr starts from the exact distance to the previous iteration's
 // correspondence (ICP warm start; any index is a valid upper bound, so this only affects speed).
 // Everything the answer depends on is computed by the exact chain; the filter only decides what to skip.
+//
+// DIMS = 2 (the default once a registration is warm): |p-q|^2 >= the squared distance of the projections onto two
+// coordinate axes, so the same bound with one coordinate dropped is still a rigorous lower bound and costs 2 FMAs per
+// pair instead of 3 (measured on B200, tools/ubench_filter.cu: 13.5-14.3 cycles per source x 4 targets per SMSP
+// instead of 17.2-17.5). The derivation is the 3-D one restricted to the kept plane: e~_j = fma(aA, qA_j, fma(aB, qB_j,
+// w2_j)), w2 = |(q-c)_AB|^2, |pc|^2 taken in the plane; Rq (3-D) and eps over-estimate the planar quantities. What it
+// gives up is tightness: more sub-tiles reach the exact pass (all those whose SHADOW on the kept plane comes within
+// thr of the source). The dropped axis is chosen per target cloud as the one whose projection keeps the sub-tiles
+// best separated (kf_score_kernel), and the host watches the exact-pass rate (kf_policy_update): above 10 % it goes
+// back to the 3-D bound, below 1 % it tries the planar one again. Either way the returned indices are those of the
+// exact chain.
 #include "common.cuh"
 #include "k1_device.cuh"
 #include <cmath>
 
 namespace icpb {
 
-constexpr int KF_TT     = 512;                 // targets per shared-memory tile (7 float arrays: X Y Z | Xc Yc Zc W)
+constexpr int KF_TT     = 512;                 // targets per shared-memory tile (8 float arrays: X Y Z | Xc Yc Zc | W3 W2)
 constexpr int KF_TRK    = 128;                 // filter / tracking sub-tile
 constexpr int KF_STAGES = 3;
-constexpr int KF_TILE_FLOATS = 7 * KF_TT;
+constexpr int KF_TILE_FLOATS = 8 * KF_TT;
 constexpr int KF_TILE_BYTES  = KF_TILE_FLOATS * 4;
 constexpr float KF_U = 5.9604644775390625e-08f;            // 2^-24
 
 struct KFParams {
 	const float* px; const float* py; const float* pz;
-	const float* tiles7;      // [nt][7][KF_TT]
+	const float* tiles7;      // [nt][8][KF_TT]
 	const float4* q4;         // for the warm-start gather
 	const int*   seed_idx;    // previous correspondences (may hold anything in [0, m))
 	u64*         keys;
@@ -45,6 +56,7 @@ struct KFParams {
 	float        thr0;
 	float        cx, cy, cz;  // centre removed from both clouds for the filter quantities
 	float        rq;          // upper bound of max_j |q_j - c|
+	int          drop;        // DIMS == 2: the coordinate axis (0,1,2) left out of the bound
 	const int*   done;
 	unsigned long long* stats;   // [0] sub-tile x warp x source filter tests, [1] of which evaluated exactly
 };
@@ -68,25 +80,64 @@ __global__ void kf_bbox_kernel(const float4* __restrict__ q4, int m, unsigned* m
 }
 
 // tiles7 + the radius bound (max of the float chain value of |q-c|^2, as ordered uint)
-__global__ void kf_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, float cx, float cy, float cz, float* __restrict__ tiles7, unsigned* __restrict__ r2max)
+__global__ void kf_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, float cx, float cy, float cz, int drop, float* __restrict__ tiles7, unsigned* __restrict__ r2max)
 {
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= m_pad) return;
-	float x = __int_as_float(0x7f800000), y = x, z = x, xc = 1e18f, yc = 1e18f, zc = 1e18f, w = 3e36f;
+	float x = __int_as_float(0x7f800000), y = x, z = x, xc = 1e18f, yc = 1e18f, zc = 1e18f, w = 3e36f, w2 = 3e36f;
 	if (j < m) {
 		const float4 q = q4[j];
 		x = q.x; y = q.y; z = q.z;
 		xc = __fsub_rn(x, cx); yc = __fsub_rn(y, cy); zc = __fsub_rn(z, cz);
 		w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
+		const float a = (drop == 0) ? yc : xc, b = (drop == 2) ? yc : zc;     // the two kept axes, in axis order
+		w2 = __fmaf_rn(a, a, __fmul_rn(b, b));
 		atomicMax(r2max, __float_as_uint(w));        // w >= 0: uint order = float order
 	}
 	float* t = tiles7 + (size_t)(j / KF_TT) * KF_TILE_FLOATS + (j % KF_TT);
-	t[0] = x; t[KF_TT] = y; t[2 * KF_TT] = z; t[3 * KF_TT] = xc; t[4 * KF_TT] = yc; t[5 * KF_TT] = zc; t[6 * KF_TT] = w;
+	t[0] = x; t[KF_TT] = y; t[2 * KF_TT] = z; t[3 * KF_TT] = xc; t[4 * KF_TT] = yc; t[5 * KF_TT] = zc; t[6 * KF_TT] = w; t[7 * KF_TT] = w2;
 }
 
-template <int S, int THREADS, int MODE, int MINB>
+// Which axis to leave out of the planar bound: for each of the three choices, count how many (sub-tile, sample point)
+// pairs have the sample inside the sub-tile's bounding rectangle on the kept plane — an estimate of how many sub-tiles
+// a source lying on the cloud cannot be separated from. 512 samples (every m/512-th target); one block per sub-tile.
+__global__ void __launch_bounds__(KF_TRK) kf_score_kernel(const float4* __restrict__ q4, int m, unsigned long long* __restrict__ score /* [3] */)
+{
+	__shared__ float lo[3], hi[3];
+	__shared__ unsigned cnt[3];
+	const int j = blockIdx.x * KF_TRK + threadIdx.x;
+	float4 q = make_float4(INFINITY, INFINITY, INFINITY, 0.f), r = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+	if (j < m) { q = q4[j]; r = q; }
+	float l[3] = { q.x, q.y, q.z }, h[3] = { r.x, r.y, r.z };
+	if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
+	for (int k = 0; k < 3; k++) {
+		for (int o = 16; o > 0; o >>= 1) { l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o)); h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o)); }
+	}
+	__shared__ float wl[KF_TRK / 32][3], wh[KF_TRK / 32][3];
+	if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; k++) { wl[threadIdx.x >> 5][k] = l[k]; wh[threadIdx.x >> 5][k] = h[k]; }
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		float a = INFINITY, b = -INFINITY;
+		for (int w = 0; w < KF_TRK / 32; w++) { a = fminf(a, wl[w][threadIdx.x]); b = fmaxf(b, wh[w][threadIdx.x]); }
+		lo[threadIdx.x] = a; hi[threadIdx.x] = b;
+	}
+	__syncthreads();
+	const int stride = max(1, m / 512);
+	unsigned c0 = 0, c1 = 0, c2 = 0;
+	for (int s = threadIdx.x; s * (long long)stride < m && s < 512; s += KF_TRK) {
+		const float4 v = q4[(size_t)s * stride];
+		const bool ix = v.x >= lo[0] && v.x <= hi[0], iy = v.y >= lo[1] && v.y <= hi[1], iz = v.z >= lo[2] && v.z <= hi[2];
+		c0 += (iy && iz); c1 += (ix && iz); c2 += (ix && iy);
+	}
+	atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); atomicAdd(&cnt[2], c2);
+	__syncthreads();
+	if (threadIdx.x < 3) atomicAdd(score + threadIdx.x, (unsigned long long)cnt[threadIdx.x]);
+}
+
+template <int S, int THREADS, int MODE, int MINB, int DIMS>
 __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 {
+	static_assert(DIMS == 2 || DIMS == 3, "planar or full bound");
 	constexpr int SB   = S * THREADS;
 	constexpr int SUBS = KF_TT / KF_TRK;
 	if (p.done != nullptr && *p.done) return;
@@ -113,7 +164,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 	__syncthreads();
 	int it = 0;                  // tiles consumed so far by this CTA: ring stage and mbarrier parity follow it across chunks
 
-	float ax[S], ay[S], az[S], tau[S], kk[S];
+	float ax[S], ay[S], az[S], tau[S], kk[S];     // DIMS == 2: (ax, ay) hold the two kept axes, az is unused
+	const int axA = (DIMS == 2 && p.drop == 0) ? 1 : 0, axB = (DIMS == 2 && p.drop != 2) ? 2 : 1;
 	unsigned long long n_tests = 0, n_exact = 0;
 	const float inf = __int_as_float(0x7f800000);
 	const float one8u = 1.0f + 8.0f * KF_U;
@@ -176,8 +228,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 				const float x = p.px[i], y = p.py[i], z = p.pz[i];
 				ox_s[s * THREADS] = x; oy_s[s * THREADS] = y; oz_s[s * THREADS] = z;
 				const float pcx = __fsub_rn(x, p.cx), pcy = __fsub_rn(y, p.cy), pcz = __fsub_rn(z, p.cz);
-				ax[s] = -2.0f * pcx; ay[s] = -2.0f * pcy; az[s] = -2.0f * pcz;
-				const float p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
+				float p2;
+				if (DIMS == 3) {
+					ax[s] = -2.0f * pcx; ay[s] = -2.0f * pcy; az[s] = -2.0f * pcz;
+					p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
+				} else {
+					const float pa = (axA == 0) ? pcx : pcy, pb = (axB == 2) ? pcz : pcy;
+					ax[s] = -2.0f * pa; ay[s] = -2.0f * pb; az[s] = 0.0f;
+					p2 = __fmaf_rn(pa, pa, __fmul_rn(pb, pb));
+				}
 				const float p2lo = __fmul_rd(p2, 1.0f - 8.0f * KF_U);
 				const float rp = __fmul_ru(__fsqrt_ru(p2), 1.0f + 8.0f * KF_U);
 				// eps = 1.05 u (8 Rq^2 + 10 Rp Rq + 2 Rp^2), every operation rounded up
@@ -221,10 +280,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 		const float4* X4  = reinterpret_cast<const float4*>(tile);
 		const float4* Y4  = X4 + KF_TT / 4;
 		const float4* Z4  = Y4 + KF_TT / 4;
-		const float4* XC4 = Z4 + KF_TT / 4;
-		const float4* YC4 = XC4 + KF_TT / 4;
-		const float4* ZC4 = YC4 + KF_TT / 4;
-		const float4* W4  = ZC4 + KF_TT / 4;
+		// filter operands: DIMS == 3: Xc Yc Zc W3;  DIMS == 2: the two kept centred coordinates and W2
+		const float4* XC4 = Z4 + (size_t)(1 + axA) * (KF_TT / 4);
+		const float4* YC4 = Z4 + (size_t)(1 + axB) * (KF_TT / 4);
+		const float4* ZC4 = Z4 + 3 * (KF_TT / 4);
+		const float4* W4  = Z4 + (size_t)(DIMS == 3 ? 4 : 5) * (KF_TT / 4);
 
 #pragma unroll 1
 		for (int sub = 0; sub < SUBS; sub++) {
@@ -232,24 +292,41 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 			float em[S];
 #pragma unroll
 			for (int s = 0; s < S; s++) em[s] = inf;
-			float4 X = XC4[j0], Y = YC4[j0], Z = ZC4[j0], W = W4[j0];
+			float4 X = XC4[j0], Y = YC4[j0], Z = (DIMS == 3) ? ZC4[j0] : make_float4(0.f, 0.f, 0.f, 0.f), W = W4[j0];
 #pragma unroll 2
 			for (int j = j0; j < j1; j++) {
-				const float4 Xn = XC4[j + 1], Yn = YC4[j + 1], Zn = ZC4[j + 1], Wn = W4[j + 1];   // stays inside the ring (+ pad)
+				// prefetch of the next quad: j + 1 may be the first quad of the next array (never past the ring + pad)
+				const float4 Xn = XC4[j + 1], Yn = YC4[j + 1], Wn = W4[j + 1];
+				float4 Zn = Z;
+				if (DIMS == 3) Zn = ZC4[j + 1];
 				const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
 				const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
-				const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
 				const u64 w01 = pack2(W.x, W.y), w23 = pack2(W.z, W.w);
+				if (DIMS == 3) {
+					const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
 #pragma unroll
-				for (int s = 0; s < S; s++) {
-					const u64 AX = bcast2v(ax[s]), AY = bcast2v(ay[s]), AZ = bcast2v(az[s]);
-					u64 e = fma2(AX, x01, fma2(AY, y01, fma2(AZ, z01, w01)));
-					float a, b;
-					unpack2(e, a, b);
-					em[s] = min3(em[s], a, b);
-					e = fma2(AX, x23, fma2(AY, y23, fma2(AZ, z23, w23)));
-					unpack2(e, a, b);
-					em[s] = min3(em[s], a, b);
+					for (int s = 0; s < S; s++) {
+						const u64 AX = bcast2v(ax[s]), AY = bcast2v(ay[s]), AZ = bcast2v(az[s]);
+						u64 e = fma2(AX, x01, fma2(AY, y01, fma2(AZ, z01, w01)));
+						float a, b;
+						unpack2(e, a, b);
+						em[s] = min3(em[s], a, b);
+						e = fma2(AX, x23, fma2(AY, y23, fma2(AZ, z23, w23)));
+						unpack2(e, a, b);
+						em[s] = min3(em[s], a, b);
+					}
+				} else {
+#pragma unroll
+					for (int s = 0; s < S; s++) {
+						const u64 AX = bcast2v(ax[s]), AY = bcast2v(ay[s]);
+						u64 e = fma2(AX, x01, fma2(AY, y01, w01));
+						float a, b;
+						unpack2(e, a, b);
+						em[s] = min3(em[s], a, b);
+						e = fma2(AX, x23, fma2(AY, y23, w23));
+						unpack2(e, a, b);
+						em[s] = min3(em[s], a, b);
+					}
 				}
 				X = Xn; Y = Yn; Z = Zn; W = Wn;
 			}
@@ -305,18 +382,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
+// Filter data of the current target: bounding box -> centre, the axis the planar bound leaves out, the 8-array tiles
+// and the radius bound. Every buffer is kept across targets of the same size (a host-driven loop uploads the target at
+// every step: no cudaMalloc / cudaFree there — they cost up to hundreds of milliseconds when they hit).
 static int build_filter_data(Ctx* c)
 {
 	const int m = c->m;
 	const int nt = (m + KF_TT - 1) / KF_TT;
-	unsigned* scratch = nullptr;
-	ICPB_CUDA(c, cudaMalloc((void**)&scratch, 8 * sizeof(unsigned)));
-	unsigned init[8] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u };
+	if (!c->kf_scratch) ICPB_CUDA(c, cudaMalloc((void**)&c->kf_scratch, 16 * sizeof(unsigned long long)));
+	unsigned* scratch = reinterpret_cast<unsigned*>(c->kf_scratch);                    // [0..5] bbox, [6] r2max
+	unsigned long long* score = c->kf_scratch + 8;                                     // [3]
+	unsigned init[16];
+	memset(init, 0, sizeof init);
+	init[0] = init[1] = init[2] = 0xffffffffu;
 	ICPB_CUDA(c, cudaMemcpyAsync(scratch, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+	ICPB_CUDA(c, cudaMemsetAsync(score, 0, 3 * sizeof(unsigned long long), c->stream));
 	kf_bbox_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->q4, m, scratch);
 	c->launches++;
+	// the axis the planar bound leaves out: the projection that keeps the sub-tiles best separated
+	kf_score_kernel<<<(m + KF_TRK - 1) / KF_TRK, KF_TRK, 0, c->stream>>>(c->q4, m, score);
+	c->launches++;
 	unsigned h[8];
+	unsigned long long hs[3] = { 0, 0, 0 };
 	ICPB_CUDA(c, cudaMemcpyAsync(h, scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaMemcpyAsync(hs, score, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	auto dec = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
 	for (int k = 0; k < 3; k++) {
@@ -325,21 +414,38 @@ static int build_filter_data(Ctx* c)
 		if (!std::isfinite(ctr)) ctr = 0.0f;       // non-finite coordinates: any centre is valid, only the bound's tightness changes
 		c->kf_center[k] = ctr;
 	}
-	cudaFree(c->kf_tiles7); c->kf_tiles7 = nullptr;
-	ICPB_CUDA(c, cudaMalloc((void**)&c->kf_tiles7, sizeof(float) * (size_t)nt * KF_TILE_FLOATS));
-	kf_pack_kernel<<<(nt * KF_TT + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * KF_TT, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_tiles7, scratch + 6);
+	int drop = 2;
+	if (hs[1] < hs[drop]) drop = 1;
+	if (hs[0] < hs[drop]) drop = 0;
+	if (c->kf_drop_forced >= 0 && c->kf_drop_forced <= 2) drop = c->kf_drop_forced;
+	c->kf_drop = drop;
+	for (int k = 0; k < 3; k++) c->kf_score[k] = (double)hs[k];
+	if (nt > c->kf_tiles_cap) {
+		cudaFree(c->kf_tiles7); c->kf_tiles7 = nullptr; c->kf_tiles_cap = 0;
+		ICPB_CUDA(c, cudaMalloc((void**)&c->kf_tiles7, sizeof(float) * (size_t)nt * KF_TILE_FLOATS));
+		c->kf_tiles_cap = nt;
+	}
+	kf_pack_kernel<<<(nt * KF_TT + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * KF_TT, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_drop, c->kf_tiles7, scratch + 6);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	ICPB_CUDA(c, cudaMemcpyAsync(h, scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-	cudaFree(scratch);
 	float r2; memcpy(&r2, &h[6], 4);
 	// Rq >= max |q - c|: the float chain value is within (1 +- 3u) of the real one
 	c->kf_rq = nextafterf(sqrtf(r2) * (1.0f + 8.0f * KF_U), INFINITY);
 	c->kf_nt = nt;
+	c->kf_dims = 2; c->kf_bounces = 0; c->kf_hold = 0;     // a new target: optimistic again
 	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 2 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 2 * sizeof(unsigned long long), c->stream)); }
 	c->kf_ready = true;
 	return ICPB_OK;
+}
+
+// Builds whatever the matching method of the coming run needs, OUTSIDE the timed loop (icpb_run calls this before it
+// records its first event; launch_match_filter still builds lazily for the step-wise API).
+int prepare_match_filter(Ctx* c)
+{
+	if (c->kf_ready || c->m <= 0) return ICPB_OK;
+	return build_filter_data(c);
 }
 
 static float sqrt_domain_threshold_f(float sentinel)
@@ -372,11 +478,21 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	p.cx = c->kf_center[0]; p.cy = c->kf_center[1]; p.cz = c->kf_center[2]; p.rq = c->kf_rq;
 	p.done = &c->st->done;
 	p.stats = c->kf_stats;
+	p.drop = c->kf_drop;
+	// planar bound once the thresholds are warm (a pass that starts from the sentinel sends ~6 % of the tests to the exact
+	// chain even with the full bound); ICPB_KF_DIMS=2|3 forces one of them
+	int dims = (c->kf_use_seed && c->kf_seeded) ? c->kf_dims : 3;
+	if (c->kf_dims_forced == 2 || c->kf_dims_forced == 3) dims = c->kf_dims_forced;
+	c->kf_dims_last = dims;
+	if (dims == 3 && c->kf_hold > 0) c->kf_hold--;
+	c->kf_seeded = true;
 	c->pairs_acc += (double)c->n * (double)c->m;
 	const size_t smem = (size_t)KF_STAGES * KF_TILE_BYTES + 64 + (size_t)5 * S * THREADS * 4;
-	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB>;
-	static int cached_per_sm[2][64] = {};
-	int& per_sm = cached_per_sm[dist_mode == ICPB_DIST_SQRT ? 1 : 0][c->device & 63];
+	const bool sq = dist_mode == ICPB_DIST_SQRT;
+	auto kern = (dims == 3) ? (sq ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB, 3> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB, 3>)
+	                        : (sq ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB, 2> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB, 2>);
+	static int cached_per_sm[4][64] = {};
+	int& per_sm = cached_per_sm[(sq ? 1 : 0) + (dims == 3 ? 2 : 0)][c->device & 63];
 	if (per_sm == 0) {
 		ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -405,7 +521,40 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	return ICPB_OK;
 }
 
+// Called by the engine whenever it has synchronised with the stream anyway (read_state): looks at the share of
+// (warp, source, sub-tile) tests that needed the exact chain since the last look and picks the bound for the next
+// launches. Planar -> full above 10 %; full -> planar below 1 %, but only after 16, 32, 64 launches on the full bound
+// and at most 3 times per target: a cloud for which the planar bound keeps failing stays on the full one. Results
+// never depend on this choice.
+int kf_policy_update(Ctx* c)
+{
+	if (!c->kf_ready || !c->kf_stats) return ICPB_OK;
+	unsigned long long h[2] = { 0, 0 };
+	ICPB_CUDA(c, cudaMemcpyAsync(h, c->kf_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	const double dt = (double)(h[0] - c->kf_stats_seen[0]), de = (double)(h[1] - c->kf_stats_seen[1]);
+	c->kf_stats_seen[0] = h[0]; c->kf_stats_seen[1] = h[1];
+	if (dt <= 0.0) return ICPB_OK;
+	const double frac = de / dt;
+	c->kf_last_frac = frac;
+	if (c->kf_dims_last == 2 && frac > 0.10) { c->kf_dims = 3; c->kf_bounces++; c->kf_hold = 8 << c->kf_bounces; }
+	else if (c->kf_dims_last == 3 && c->kf_dims == 3 && frac < 0.01 && c->kf_bounces < 3 && c->kf_hold <= 0) c->kf_dims = 2;
+	return ICPB_OK;
+}
+
 } // namespace icpb
+
+extern "C" int icpb_get_filter_config(icpb_ctx* ctx, int* dims_next, int* dims_last, int* drop_axis, double* last_exact_fraction)
+{
+	using namespace icpb;
+	if (!ctx) return ICPB_ERR_BADARG;
+	Ctx* c = reinterpret_cast<Ctx*>(ctx);
+	if (dims_next) *dims_next = (c->kf_dims_forced == 2 || c->kf_dims_forced == 3) ? c->kf_dims_forced : c->kf_dims;
+	if (dims_last) *dims_last = c->kf_dims_last;
+	if (drop_axis) *drop_axis = c->kf_ready ? c->kf_drop : -1;
+	if (last_exact_fraction) *last_exact_fraction = c->kf_last_frac;
+	return ICPB_OK;
+}
 
 extern "C" int icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile_exact)
 {

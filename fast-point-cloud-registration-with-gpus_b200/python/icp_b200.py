@@ -70,6 +70,7 @@ def _load():
         "icpb_time_match": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, C.c_int, fp, fp]),
         "icpb_get_grid_stats": (C.c_int, [vp, dp, ip, ip, fp]),
         "icpb_get_filter_stats": (C.c_int, [vp, dp, dp]),
+        "icpb_get_filter_config": (C.c_int, [vp, ip, ip, ip, dp]),
         "icpb_launch_count": (C.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -273,6 +274,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(lib.icpb_get_filter_stats(self.h, C.byref(a), C.byref(b)), "get_filter_stats")
         return {"subtile_tests": a.value, "subtile_exact": b.value}
+
+    def filter_config(self):
+        a, b, d, f = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self._ck(lib.icpb_get_filter_config(self.h, C.byref(a), C.byref(b), C.byref(d), C.byref(f)), "get_filter_config")
+        return {"dims_next": a.value, "dims_last": b.value, "drop_axis": d.value, "last_exact_fraction": f.value}
 
     def dist_info(self):
         r, w, p = C.c_int(), C.c_int(), C.c_int()

@@ -205,6 +205,12 @@ int  icpb_get_grid_stats(icpb_ctx* ctx, double* candidates_visited, int* last_op
 /* ICPB_NN_BRUTE statistics since the target was set: (warp x source x 128-target sub-tile) bound tests, and
  * how many of them had to be evaluated with the exact chain. */
 int  icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile_exact);
+/* The lower bound ICPB_NN_BRUTE evaluates per pair is either the full 3-FMA one or its planar 2-FMA restriction (one
+ * coordinate axis left out; still a rigorous lower bound, weaker, cheaper). dims_next / dims_last: 2 or 3 for the next /
+ * the last launch (chosen from the measured exact-pass rate; ICPB_KF_DIMS forces it); drop_axis: the axis the planar
+ * bound leaves out for the current target (-1 before the first launch); last_exact_fraction: share of sub-tile tests
+ * that needed the exact chain, as last sampled. Results never depend on any of this. */
+int  icpb_get_filter_config(icpb_ctx* ctx, int* dims_next, int* dims_last, int* drop_axis, double* last_exact_fraction);
 /* Number of kernels this context has launched since creation. */
 long long icpb_launch_count(const icpb_ctx* ctx);
 

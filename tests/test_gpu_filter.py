@@ -7,18 +7,33 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx(ib):
+def _context(ib, **env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return ib.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+# every test runs with the bound chosen automatically (full on cold passes, planar on warm ones, switched by the
+# measured exact-pass rate), with the planar bound forced for each choice of the dropped axis, and with the full one
+@pytest.fixture(scope="module", params=["auto", "planar-x", "planar-y", "planar-z", "full"])
+def ctx(ib, request):
     """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
     use the direct kernel, which would make most of these small cases vacuous)."""
-    import os
-    old = os.environ.get("ICPB_K1_FILTER_MIN_PAIRS")
-    os.environ["ICPB_K1_FILTER_MIN_PAIRS"] = "0"
-    c = ib.Context(0)
-    if old is None:
-        del os.environ["ICPB_K1_FILTER_MIN_PAIRS"]
-    else:
-        os.environ["ICPB_K1_FILTER_MIN_PAIRS"] = old
+    env = {"ICPB_K1_FILTER_MIN_PAIRS": 0}
+    if request.param.startswith("planar"):
+        env.update(ICPB_KF_DIMS=2, ICPB_KF_DROP="xyz".index(request.param[-1]))
+    elif request.param == "full":
+        env.update(ICPB_KF_DIMS=3)
+    c = _context(ib, **env)
+    c.variant = request.param
     yield c
     c.close()
 
@@ -30,6 +45,12 @@ def _check(ctx, ib, orc, P, Q, modes=(0, 1), sentinel=100000.0, oracle=True, exp
             s0 = ctx.filter_stats()["subtile_tests"]
             a = ctx.match(mode, ib.NN_BRUTE, sentinel); da = ctx.min_distances()
             assert (ctx.filter_stats()["subtile_tests"] > s0) == expect_filter, "which kernel ran is part of the test"
+            if expect_filter:
+                cfg = ctx.filter_config()
+                want = {"planar": 2, "full": 3}.get(ctx.variant.split("-")[0])
+                assert want is None or cfg["dims_last"] == want, (ctx.variant, cfg)
+                if ctx.variant.startswith("planar"):
+                    assert cfg["drop_axis"] == "xyz".index(ctx.variant[-1])
             b = ctx.match(mode, ib.NN_BRUTE_DIRECT, sentinel); db = ctx.min_distances()
             assert np.array_equal(a, b), (mode, rep)
             assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), (mode, rep)
@@ -120,3 +141,32 @@ def test_full_run_filter_is_bitwise_the_direct_run(ctx, ib, orc):
         out.append((e.copy(), r.iterations, list(r.R), list(r.t), ctx.correspondences(), r.match_ms))
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1:4] == out[1][1:4]
     assert np.array_equal(out[0][4], out[1][4])
+
+
+def test_planar_bound_policy(ib, orc):
+    """Automatic choice: on the 1M-point saddle the planar bound stays in use once the pass is warm (few sub-tiles
+    reach the exact chain); on a small volumetric cloud whose thresholds are of the order of the point spacing its
+    exact-pass rate is high and the engine goes back to the full bound. Same indices either way."""
+    c = _context(ib, ICPB_K1_FILTER_MIN_PAIRS=0)
+    try:
+        D, M = orc.synth_p2p(1000)
+        c.set_target(M); c.set_source(D)
+        e, r = c.run(ib.default_params(max_iter=4, stop_early=0, sync_every=1))
+        cfg = c.filter_config()
+        assert cfg["drop_axis"] in (0, 1, 2) and cfg["dims_last"] == 2 and cfg["dims_next"] == 2, cfg
+        assert 0 < cfg["last_exact_fraction"] < 0.10
+        idx_planar = c.correspondences()
+        c.set_source(D)
+        e2, r2 = c.run(ib.default_params(max_iter=4, stop_early=0, sync_every=1, nn_method=ib.NN_BRUTE_DIRECT))
+        assert np.array_equal(idx_planar, c.correspondences()) and np.array_equal(e, e2) and list(r.R) == list(r2.R)
+        rng = np.random.default_rng(5)
+        Q = rng.random((20000, 3)).astype(np.float32)
+        P = rng.random((20000, 3)).astype(np.float32)          # unrelated to Q: thresholds of the order of the point spacing
+        c.set_target(Q); c.set_source(P)
+        e, r = c.run(ib.default_params(max_iter=6, stop_early=0, sync_every=1))
+        cfg = c.filter_config()
+        assert cfg["dims_next"] == 3 and cfg["dims_last"] == 3, cfg
+        c.set_source(P)
+        assert np.array_equal(c.match(0, ib.NN_BRUTE), orc.match(P, Q, 0))
+    finally:
+        c.close()

@@ -38,6 +38,50 @@ template<int S, int FORM, int TT> __global__ void __launch_bounds__(256,2) filt(
           m[s]=min3(m[s],e0,e1); m[s]=min3(m[s],e2,e3);
         }
       }
+    } else if (FORM==4) {
+      // 2-D bound (one coordinate dropped), packed: 4 FFMA2 + 2 FMNMX3 per source x 4 targets
+      #pragma unroll 2
+      for (int j=0;j<NQ;j++){
+        float4 X=sm[j],Y=sm[NQ+j],W=sm[3*NQ+j];
+        u64 x01=pack2(X.x,X.y),x23=pack2(X.z,X.w),y01=pack2(Y.x,Y.y),y23=pack2(Y.z,Y.w),w01=pack2(W.x,W.y),w23=pack2(W.z,W.w);
+        #pragma unroll
+        for(int s=0;s<S;s++){
+          u64 AX=bcast2v(ax[s]),AY=bcast2v(ay[s]);
+          u64 e=fma2(AX,x01,fma2(AY,y01,w01));
+          float a,b; unpack2(e,a,b); m[s]=min3(m[s],a,b);
+          e=fma2(AX,x23,fma2(AY,y23,w23));
+          unpack2(e,a,b); m[s]=min3(m[s],a,b);
+        }
+      }
+    } else if (FORM==5) {
+      // 2-D bound, scalar: 8 FFMA + 2 FMNMX3
+      #pragma unroll 2
+      for (int j=0;j<NQ;j++){
+        float4 X=sm[j],Y=sm[NQ+j],W=sm[3*NQ+j];
+        #pragma unroll
+        for(int s=0;s<S;s++){
+          float e0=fmaf(ax[s],X.x,fmaf(ay[s],Y.x,W.x));
+          float e1=fmaf(ax[s],X.y,fmaf(ay[s],Y.y,W.y));
+          float e2=fmaf(ax[s],X.z,fmaf(ay[s],Y.z,W.z));
+          float e3=fmaf(ax[s],X.w,fmaf(ay[s],Y.w,W.w));
+          m[s]=min3(m[s],e0,e1); m[s]=min3(m[s],e2,e3);
+        }
+      }
+    } else if (FORM==6) {
+      // 1-D bound, packed: 2 FFMA2 + 2 FMNMX3 (how much do the mins alone cost?)
+      #pragma unroll 2
+      for (int j=0;j<NQ;j++){
+        float4 X=sm[j],W=sm[3*NQ+j];
+        u64 x01=pack2(X.x,X.y),x23=pack2(X.z,X.w),w01=pack2(W.x,W.y),w23=pack2(W.z,W.w);
+        #pragma unroll
+        for(int s=0;s<S;s++){
+          u64 AX=bcast2v(ax[s]);
+          u64 e=fma2(AX,x01,w01);
+          float a,b; unpack2(e,a,b); m[s]=min3(m[s],a,b);
+          e=fma2(AX,x23,w23);
+          unpack2(e,a,b); m[s]=min3(m[s],a,b);
+        }
+      }
     } else if (FORM==2) {
       // smem holds per target x,y,z,w as 4 SoA float arrays; each step takes 2 targets (scalars), sources packed in pairs
       const float* X=(const float*)sm; const float* Y=X+TT; const float* Z=Y+TT; const float* W=Z+TT;
@@ -101,5 +145,12 @@ int main(){
   run<4,2,1024>(tiles,M,src,out,N,"packed sources, bcast target");
   run<16,2,1024>(tiles,M,src,out,N,"packed sources, bcast target");
   run<16,0,1024>(tiles,M,src,out,N,"bcast-scalar a, packed targets");
+  run<8,4,1024>(tiles,M,src,out,N,"2-D bound, packed");
+  run<16,4,1024>(tiles,M,src,out,N,"2-D bound, packed");
+  run<4,4,1024>(tiles,M,src,out,N,"2-D bound, packed");
+  run<8,5,1024>(tiles,M,src,out,N,"2-D bound, scalar FFMA");
+  run<16,5,1024>(tiles,M,src,out,N,"2-D bound, scalar FFMA");
+  run<8,6,1024>(tiles,M,src,out,N,"1-D bound, packed");
+  run<16,6,1024>(tiles,M,src,out,N,"1-D bound, packed");
   return 0;
 }
