@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-ref-binary", action="store_true")
+    ap.add_argument("--balance", type=int, default=1, help="N > 1: deal source blocks in proportion to each GPU's measured matching rate (0: even deal)")
+    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
+                    help="how the source is dealt to the ranks (N > 1): blocks of 2048 points round-robin, or contiguous ranges")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -222,8 +225,12 @@ def main():
     ctx = ib.Context(local_rank, rank, world, nccl_id)
     D, M = icp_synth.p2p_clouds(args.width)
     n_total, m = D.shape[0], M.shape[0]
-    lo, hi = icp_dist.shard_bounds(n_total, rank, world)
-    shard = np.ascontiguousarray(D[lo:hi])
+    if args.shard == "contiguous":
+        lo, hi = icp_dist.shard_bounds(n_total, rank, world)
+        shard = np.ascontiguousarray(D[lo:hi])
+    else:                                   # blocks of 2048 sources dealt round-robin: balances the ranks' matching cost
+        shard = np.ascontiguousarray(D[icp_dist.shard_indices(n_total, rank, world)])
+    n_rank = shard.shape[0]
 
     fp32_peak = ctx.fp32_peak_tflops()
     ctx.set_target(M)
@@ -239,6 +246,19 @@ def main():
         err, res = ctx.run(ib.default_params(max_iter=1, stop_early=0))
         return res
 
+    # N > 1: the step ends when the slowest rank ends, and B200s of one box differ by a few per cent in sustained speed.
+    # Two untimed calibration steps measure every rank's matching rate; the blocks are then dealt in proportion to it
+    # (icp_dist.deal_blocks) and the registration restarts from the original cloud. --balance 0 keeps the even deal.
+    balance_weights = None
+    if world > 1 and args.balance and args.shard != "contiguous":
+        one_step(); r1 = one_step(); r2 = one_step()
+        speed = torch.zeros(world, dtype=torch.float64, device="cuda")
+        speed[rank] = float(n_rank) / max(1e-6, r1.match_ms + r2.match_ms)
+        dist.all_reduce(speed)
+        balance_weights = [float(v) for v in speed.cpu().tolist()]
+        shard = np.ascontiguousarray(D[icp_dist.shard_indices_weighted(n_total, rank, balance_weights)])
+        n_rank = shard.shape[0]
+        ctx.set_source(shard)
     for _ in range(args.warmup):
         one_step()
     barrier()
@@ -256,6 +276,7 @@ def main():
 
     total_ms = allmax(sum(step_ms))
     match_total_ms = allmax(sum(match_ms))
+    match_fastest_rank_ms = -allmax(-sum(match_ms))
     launches_all = int(allsum(launches))
     pairs_total = float(n_total) * m * args.steps
     value = pairs_total / (total_ms * 1e-3)
@@ -282,7 +303,7 @@ def main():
     d2h = allsum(float(idx.nbytes + R.nbytes + T.nbytes + 4 + cur.nbytes))
 
     # per-GPU roofline of the dominant kernel (brute-force matching)
-    pairs_rank = float(hi - lo) * m * args.steps
+    pairs_rank = float(n_rank) * m * args.steps
     achieved = 8.0 * pairs_rank / (sum(match_ms) * 1e-3) * 1e-12
     achieved = allmax(-achieved) * -1.0 if world > 1 else achieved      # the slowest rank's figure
 
@@ -300,12 +321,16 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic z=x^2-y^2, %dx%d points, point-to-point ICP, exact brute-force NN (BASELINE configs[3])" % (n_total, m),
                        "width": args.width, "step": "one ICP iteration: matching + moments + 3x3 SVD + transform + error",
-                       "parallelism": "source sharded x%d, target replicated, 16 FP64 moment sums %s" % (
-                           world, "exchanged inside the reduction kernels over NVLink peer memory (no collective launch)" if ctx.dist_info()["peer_exchange"]
+                       "parallelism": "source sharded x%d (%s), target replicated, 16 FP64 moment sums %s" % (
+                           world, "contiguous shards" if args.shard == "contiguous" else "blocks of 2048 points dealt round-robin", "exchanged inside the reduction kernels over NVLink peer memory (no collective launch)" if ctx.dist_info()["peer_exchange"]
                            else ("combined with ncclAllReduce" if world > 1 else "(single GPU: no exchange)")),
                        "l2": "256 MiB device write between timed steps (untimed); timing = CUDA events per step on the engine stream"},
             "icp_iters_per_sec": args.steps / (total_ms * 1e-3),
             "match_ms_per_step": match_total_ms / args.steps,
+            "match_ms_per_step_fastest_rank": match_fastest_rank_ms / args.steps,
+            "rank_balance": ({"weights": [w / (sum(balance_weights) / world) for w in balance_weights],
+                              "how": "2 untimed calibration steps; blocks of 2048 sources dealt in proportion to each rank's measured matching rate"}
+                             if balance_weights else None),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": "icpb_iterate_host (pinned host clouds -> idx, R, T, rms) + icpb_get_source; host-driven loop, each step uploads the previous step's transformed source", "steps": args.e2e_steps},
@@ -320,8 +345,8 @@ def main():
                          "note": "compute-bound (FP32 issue slots); `achieved` counts the ALGORITHMIC 8 FLOP per pair SURVEY.md 8(d) defines, so frac can exceed 1: "
                                  "the direct form executes 6 FP32 ops per pair (ceiling 66.7% of FFMA peak), the filter 3 (full bound) or 2 (planar bound) FMAs per pair"},
             "roofline_direct_kernel": {"kernel": "k1_match (reference chain on every pair)", "ms_per_launch": direct_ms,
-                                       "achieved": 8.0 * float(hi - lo) * m / (direct_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
-                                       "frac": 8.0 * float(hi - lo) * m / (direct_ms * 1e-3) * 1e-12 / fp32_peak},
+                                       "achieved": 8.0 * float(n_rank) * m / (direct_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                                       "frac": 8.0 * float(n_rank) * m / (direct_ms * 1e-3) * 1e-12 / fp32_peak},
         }
         if world == 1 and not args.skip_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

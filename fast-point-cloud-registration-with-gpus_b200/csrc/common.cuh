@@ -174,7 +174,7 @@ struct Ctx {
 	float   kf_rq = 0.f;                // >= max |q - centre|
 	int     kf_nt = 0;
 	unsigned long long* kf_stats = nullptr;
-	int*    kf_work_counter = nullptr;
+	unsigned long long* kf_work_counter = nullptr;
 	int     kf_chunk_override = 0;      // ICPB_KF_CHUNK: tiles per work chunk
 	int     kf_drop = 2;                // axis left out of the planar (2-FMA) bound, chosen per target (kf_score_kernel)
 	int     kf_drop_forced = -1;        // ICPB_KF_DROP=0|1|2

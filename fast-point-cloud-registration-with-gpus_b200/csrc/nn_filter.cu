@@ -49,10 +49,9 @@ struct KFParams {
 	const int*   seed_idx;    // previous correspondences (may hold anything in [0, m))
 	u64*         keys;
 	int          n, m, nt;
-	int          chunk_tiles;   // tiles per work chunk
-	int          chunks_per_sb; // ceil(nt / chunk_tiles)
-	int          total_chunks;  // source blocks x chunks_per_sb
-	int*         work_counter;  // zeroed before the launch; CTAs draw chunks from it (dynamic scheduling)
+	long long    total_units;   // source blocks x nt: (source block, target tile) work units, source-block major
+	int          min_chunk, max_chunk;   // tiles per grab: guided self-scheduling between these bounds
+	unsigned long long* work_counter;    // zeroed before the launch; CTAs draw ranges of units from it
 	float        thr0;
 	float        cx, cy, cz;  // centre removed from both clouds for the filter quantities
 	float        rq;          // upper bound of max_j |q_j - c|
@@ -153,10 +152,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 	float* oy_s   = thr_s + 3 * S * THREADS;
 	float* oz_s   = thr_s + 4 * S * THREADS;
 
-	// Work = chunks of `chunk_tiles` consecutive tiles of one source block, drawn from a global counter: sub-tiles that
-	// need the exact pass cluster where a source block's neighbours live, so a static split would leave the blocks
-	// that own those tiles running long after the others (measured: 12 % at 125k sources per GPU).
-	__shared__ int s_chunk;
+	// Work = ranges of consecutive (source block, target tile) units drawn from a global counter: sub-tiles that need
+	// the exact pass cluster where a source block's neighbours live, so a static split would leave the blocks that own
+	// those tiles running long after the others (measured: 12 % at 125k sources per GPU). Guided self-scheduling: a
+	// grab takes 1/(4 x grid) of what is left, between min_chunk and max_chunk tiles — large ranges while there is
+	// plenty (the per-range source reload and index re-scan stay negligible), small ones at the end (the tail is a few
+	// tiles, not a whole chunk: at 125k sources per GPU fixed 8-tile chunks left 4 % on the table).
+	__shared__ unsigned long long s_u0;
+	__shared__ int s_len;
 	if (tid == 0) {
 		for (int s = 0; s < KF_STAGES; s++) mbar_init(&full_bar[s], 1);
 		fence_mbar_init();
@@ -205,14 +208,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 	};
 
 	while (true) {
-		__syncthreads();                                   // previous chunk fully consumed (ring, s_chunk)
-		if (tid == 0) s_chunk = atomicAdd(p.work_counter, 1);
+		__syncthreads();                                   // previous range fully consumed (s_u0, s_len)
+		if (tid == 0) {
+			const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(p.work_counter);   // may be stale: only sizes the grab
+			const long long left = p.total_units - (long long)seen;
+			long long len = left / (4ll * (long long)gridDim.x);
+			if (len < p.min_chunk) len = p.min_chunk;
+			if (len > p.max_chunk) len = p.max_chunk;
+			s_len = (int)len;
+			s_u0 = atomicAdd(p.work_counter, (unsigned long long)len);
+		}
 		__syncthreads();
-		const int chunk = s_chunk;
-		if (chunk >= p.total_chunks) break;
-		const int sb = chunk / p.chunks_per_sb;
-		const int t0 = (chunk % p.chunks_per_sb) * p.chunk_tiles;
-		const int t1 = min(p.nt, t0 + p.chunk_tiles);
+		if ((long long)s_u0 >= p.total_units) break;
+		long long u = (long long)s_u0;
+		const long long u_end = min(p.total_units, u + (long long)s_len);
+		// a range may run over the end of a source block: one segment per source block
+		while (u < u_end) {
+		const int sb = (int)(u / p.nt);
+		const int t0 = (int)(u - (long long)sb * p.nt);
+		const int t1 = (int)min((long long)p.nt, (long long)t0 + (u_end - u));
+		u += t1 - t0;
+		__syncthreads();                                   // previous segment fully consumed (ring, per-thread slots)
 		int next_load = t0;                                // producer cursor (thread 0 only)
 		if (tid == 0) {
 			for (int k = 0; k < KF_STAGES - 1 && next_load < t1; k++, next_load++) {
@@ -372,6 +388,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 		}
 		}
 		flush(sb);
+		}
 	}
 	if (p.stats != nullptr) {
 		for (int o = 16; o > 0; o >>= 1) { n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o); n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o); }
@@ -500,21 +517,18 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	}
 	long long grid = (long long)c->sm_count * per_sm;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
-	// ~64 chunks per CTA, at least 8 tiles (4096 targets per source) each: fine enough to even out the exact passes
-	// and the tail, coarse enough that the per-chunk source reload and index re-scan stay below ~2 %
-	// (measured at 1M x 1M: 16-64 tiles per chunk 118 ms, 256: 120 ms, 1024: 126 ms)
-	long long ct = ((long long)nb * p.nt) / (64 * grid);
-	if (c->kf_chunk_override > 0) ct = c->kf_chunk_override;
-	if (ct < 8) ct = 8;
-	if (ct > p.nt) ct = p.nt;
-	p.chunks_per_sb = (int)((p.nt + ct - 1) / ct);
-	p.chunk_tiles = (int)((p.nt + p.chunks_per_sb - 1) / p.chunks_per_sb);
-	p.chunks_per_sb = (p.nt + p.chunk_tiles - 1) / p.chunk_tiles;
-	p.total_chunks = nb * p.chunks_per_sb;
-	if (grid > p.total_chunks) grid = p.total_chunks;
-	if (!c->kf_work_counter) ICPB_CUDA(c, cudaMalloc((void**)&c->kf_work_counter, sizeof(int)));
+	// guided self-scheduling between 2 and 64 tiles per grab (measured at 1M x 1M with fixed chunks: 16-64 tiles 118 ms,
+	// 256: 120 ms, 1024: 126 ms); ICPB_KF_CHUNK=k pins both bounds to k (fixed chunks, for experiments)
+	p.total_units = (long long)nb * p.nt;
+	p.min_chunk = 2; p.max_chunk = 64;
+	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
+	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
+	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
+	const long long max_ctas = (p.total_units + p.min_chunk - 1) / p.min_chunk;
+	if (grid > max_ctas) grid = max_ctas;
+	if (!c->kf_work_counter) ICPB_CUDA(c, cudaMalloc((void**)&c->kf_work_counter, sizeof(unsigned long long)));
 	p.work_counter = c->kf_work_counter;
-	ICPB_CUDA(c, cudaMemsetAsync(c->kf_work_counter, 0, sizeof(int), c->stream));
+	ICPB_CUDA(c, cudaMemsetAsync(c->kf_work_counter, 0, sizeof(unsigned long long), c->stream));
 	kern<<<(unsigned)grid, THREADS, smem, c->stream>>>(p);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());

@@ -85,3 +85,36 @@ def test_shard_bounds_cover_everything():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_interleaved_shards_partition_the_cloud():
+    """Blocks of 2048 sources dealt round-robin (bench.py's default): a partition, block-coherent, balanced to a block."""
+    sys.path.insert(0, os.path.join(ROOT, "fast-point-cloud-registration-with-gpus_b200", "python"))
+    import icp_dist
+    for n in (1, 2047, 2048, 2049, 100000, 1000000):
+        for w in (1, 2, 3, 8):
+            parts = [icp_dist.shard_indices(n, r, w) for r in range(w)]
+            allidx = np.concatenate(parts)
+            assert allidx.size == n and np.array_equal(np.sort(allidx), np.arange(n))
+            sizes = [p.size for p in parts]
+            assert max(sizes) - min(sizes) <= 2048
+            for r, p in enumerate(parts):
+                assert np.all(np.diff(p) > 0)
+                assert np.all((p // 2048) % w == r)
+
+
+def test_weighted_deal_is_a_partition_and_proportional():
+    sys.path.insert(0, os.path.join(ROOT, "fast-point-cloud-registration-with-gpus_b200", "python"))
+    import icp_dist
+    assert np.array_equal(icp_dist.deal_blocks(16, [1, 1, 1, 1]), np.arange(16) % 4)      # equal speeds: round-robin
+    w = [1.0, 0.96, 1.04, 1.0, 0.9, 1.1, 1.0, 1.0]
+    owner = icp_dist.deal_blocks(489, w)
+    counts = np.bincount(owner, minlength=8)
+    assert counts.sum() == 489 and np.abs(counts - 489 * np.array(w) / sum(w)).max() <= 1.0
+    for r in range(8):                       # spread over the whole cloud, not bunched
+        mine = np.nonzero(owner == r)[0]
+        assert np.diff(mine).max() <= 2 * 8 / min(w)
+    n = 1000000
+    parts = [icp_dist.shard_indices_weighted(n, r, w) for r in range(8)]
+    allidx = np.concatenate(parts)
+    assert allidx.size == n and np.array_equal(np.sort(allidx), np.arange(n))
