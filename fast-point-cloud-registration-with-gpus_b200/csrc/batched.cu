@@ -8,7 +8,8 @@
 //   3x3 Jacobi SVD by one thread (solve_device.cuh) -> transform of the registers with RyT's arithmetic ->
 //   FP64 block reduction of the squared residual -> the reference's stop test,
 // with __syncthreads() as the only synchronisation: no kernel launches, no host round trips, no global
-// memory traffic inside the loop except the final results. Two CTAs (16 warps) share an SM.
+// memory traffic inside the loop except the final results. Two CTAs (16 warps) share an SM; registrations are drawn
+// from an atomic counter because their iteration counts differ (static round-robin left CTAs idle at the end).
 #include "common.cuh"
 #include "k1_device.cuh"
 #include "solve_device.cuh"
@@ -32,6 +33,7 @@ struct BatchParams {
 	double* R;              // [batch][9]
 	double* t;              // [batch][3]
 	int* idx;               // [batch][n] or nullptr
+	int* next;              // zeroed before the launch: CTAs draw registrations from it (their iteration counts differ)
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red /* [THREADS/32] */)
@@ -62,8 +64,13 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchP
 	const int tid = threadIdx.x;
 	const float inf = __int_as_float(0x7f800000);
 
-	for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+	__shared__ int s_b;
+	while (true) {
 		__syncthreads();
+		if (tid == 0) s_b = atomicAdd(p.next, 1);
+		__syncthreads();
+		const int b = s_b;
+		if (b >= p.batch) break;
 		const float* T = p.targets + (size_t)b * p.m * 3;
 		for (int j = tid; j < mpad + 4; j += K9_THREADS) {
 			const bool ok = j < p.m;
@@ -239,8 +246,8 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 
 	const size_t sb = sizeof(float) * 3 * (size_t)batch * n, tb = sizeof(float) * 3 * (size_t)batch * m;
 	const size_t eb = sizeof(float) * (size_t)batch * (params->max_iter + 1);
-	float *d_s = nullptr, *d_t = nullptr, *d_e = nullptr; int *d_it = nullptr, *d_run = nullptr; double *d_R = nullptr, *d_tt = nullptr;
-	auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_t); cudaFree(d_e); cudaFree(d_it); cudaFree(d_run); cudaFree(d_R); cudaFree(d_tt); };
+	float *d_s = nullptr, *d_t = nullptr, *d_e = nullptr; int *d_it = nullptr, *d_run = nullptr, *d_next = nullptr; double *d_R = nullptr, *d_tt = nullptr;
+	auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_t); cudaFree(d_e); cudaFree(d_it); cudaFree(d_run); cudaFree(d_next); cudaFree(d_R); cudaFree(d_tt); };
 #define K9_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(c, e__, #call, __FILE__, __LINE__); } } while (0)
 	K9_TRY(cudaMalloc((void**)&d_s, sb)); K9_TRY(cudaMalloc((void**)&d_t, tb)); K9_TRY(cudaMalloc((void**)&d_e, eb));
 	K9_TRY(cudaMalloc((void**)&d_it, sizeof(int) * batch)); K9_TRY(cudaMalloc((void**)&d_run, sizeof(int) * batch));
@@ -248,13 +255,15 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 	K9_TRY(cudaMemcpyAsync(d_s, sources, sb, cudaMemcpyHostToDevice, c->stream));
 	K9_TRY(cudaMemcpyAsync(d_t, targets, tb, cudaMemcpyHostToDevice, c->stream));
 	K9_TRY(cudaMemsetAsync(d_e, 0, eb, c->stream));
+	K9_TRY(cudaMalloc((void**)&d_next, sizeof(int)));
+	K9_TRY(cudaMemsetAsync(d_next, 0, sizeof(int), c->stream));
 
 	BatchParams p;
 	p.sources = d_s; p.targets = d_t; p.batch = batch; p.n = n; p.m = m;
 	p.max_iter = params->max_iter; p.stop_early = params->stop_early; p.mode = params->dist_mode; p.flags = params->flags;
 	p.sentinel = params->sentinel; p.tol = params->tol;
 	p.thr0 = (params->dist_mode == ICPB_DIST_SQRT) ? sqrt_threshold_host(params->sentinel) : params->sentinel;
-	p.errors = d_e; p.iterations = d_it; p.iterations_run = d_run; p.R = d_R; p.t = d_tt; p.idx = nullptr;
+	p.errors = d_e; p.iterations = d_it; p.iterations_run = d_run; p.R = d_R; p.t = d_tt; p.idx = nullptr; p.next = d_next;
 	const int mpad = ((m + K9_TRK - 1) / K9_TRK) * K9_TRK;
 	const size_t smem = sizeof(float) * 3 * (size_t)(mpad + 4);
 	auto kern = (params->dist_mode == ICPB_DIST_SQRT) ? icp_batched_kernel<ICPB_DIST_SQRT> : icp_batched_kernel<ICPB_DIST_SQ>;
