@@ -285,17 +285,19 @@ def main():
     hD = torch.from_numpy(shard).pin_memory()
     hM = torch.from_numpy(M).pin_memory()
     hD_np, hM_np = hD.numpy(), hM.numpy()
+    # every host buffer of the loop is pinned: the clouds that go up and the results that come down
+    h_cur = [torch.empty_like(hD).pin_memory(), torch.empty_like(hD).pin_memory()]
+    h_idx = torch.empty(shard.shape[0], dtype=torch.int32).pin_memory()
     p = ib.default_params()
     # a genuine host-driven loop: every step uploads the CURRENT source and the target from pinned host memory, runs one
     # iteration, and downloads the correspondences, the transform and the transformed source (which feeds the next step)
-    cur = hD_np
-    idx, R, T, rms = ctx.iterate_host(p, cur, hM_np)            # warm
-    cur = ctx.get_source()
+    idx, R, T, rms = ctx.iterate_host(p, hD_np, hM_np, idx_out=h_idx.numpy())            # warm
+    cur = ctx.get_source(out=h_cur[0].numpy())
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        idx, R, T, rms = ctx.iterate_host(p, cur, hM_np)
-        cur = ctx.get_source()
+    for k in range(args.e2e_steps):
+        idx, R, T, rms = ctx.iterate_host(p, cur, hM_np, idx_out=h_idx.numpy())
+        cur = ctx.get_source(out=h_cur[(k + 1) & 1].numpy())
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
     e2e_value = float(n_total) * m * args.e2e_steps / e2e_s

@@ -176,6 +176,7 @@ struct Ctx {
 	unsigned long long* kf_stats = nullptr;
 	unsigned long long* kf_work_counter = nullptr;
 	int     kf_chunk_override = 0;      // ICPB_KF_CHUNK: tiles per work chunk
+	int     kf_s = 8;                   // sources per thread of the filter kernel (ICPB_KF_S=8|16)
 	int     kf_drop = 2;                // axis left out of the planar (2-FMA) bound, chosen per target (kf_score_kernel)
 	int     kf_drop_forced = -1;        // ICPB_KF_DROP=0|1|2
 	double  kf_score[3] = {0, 0, 0};

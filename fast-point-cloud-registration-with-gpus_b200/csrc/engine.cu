@@ -160,6 +160,7 @@ static int create_common(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
 	if (const char* e = getenv("ICPB_KF_DIMS")) c->kf_dims_forced = atoi(e);
+	if (const char* e = getenv("ICPB_KF_S")) c->kf_s = (atoi(e) == 16) ? 16 : 8;
 	if (const char* e = getenv("ICPB_KF_DROP")) c->kf_drop_forced = atoi(e);
 	*out = c;
 	return ICPB_OK;

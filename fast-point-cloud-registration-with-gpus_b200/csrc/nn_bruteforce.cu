@@ -263,6 +263,7 @@ int k1_max_block_sources()
 {
 	int mx = 0;
 	for (int k = 0; k < K1_NUM_CFG; k++) { int sbs = k1_table[k].S * k1_table[k].threads; if (sbs > mx) mx = sbs; }
+	if (mx < 16 * 256) mx = 16 * 256;       // the filter kernel's largest source block (nn_filter.cu, S = 16)
 	return mx;
 }
 

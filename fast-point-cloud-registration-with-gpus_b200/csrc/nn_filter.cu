@@ -475,16 +475,11 @@ static float sqrt_domain_threshold_f(float sentinel)
 	return y;
 }
 
-int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
+// S sources per thread: 8 (two CTAs per SM, <= 128 registers) or 16 (one CTA per SM, the register file to itself;
+// ICPB_KF_S=16 — the bare planar loop is ~5 % faster with 16 in tools/ubench_filter.cu).
+template <int S, int MINB> static int launch_filter_cfg(Ctx* c, int dist_mode, float sentinel)
 {
-	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
-	int rc;
-	if (!c->kf_ready) { if ((rc = build_filter_data(c)) != ICPB_OK) return rc; }
-	// The bound's error analysis is relative (u = 2^-24 per operation): it needs finite magnitudes whose squares stay
-	// in the normal range. Anything else (non-finite coordinates, clouds of radius > 1e15 or < 1e-15) goes through
-	// the direct kernel.
-	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f || c->kf_rq < 1e-15f) return launch_match_brute(c, dist_mode, sentinel);
-	constexpr int S = 8, THREADS = 256, MINB = 2;
+	constexpr int THREADS = 256;
 	constexpr int SB = S * THREADS;
 	KFParams p;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
@@ -508,7 +503,7 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	const bool sq = dist_mode == ICPB_DIST_SQRT;
 	auto kern = (dims == 3) ? (sq ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB, 3> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB, 3>)
 	                        : (sq ? k1_filter<S, THREADS, ICPB_DIST_SQRT, MINB, 2> : k1_filter<S, THREADS, ICPB_DIST_SQ, MINB, 2>);
-	static int cached_per_sm[4][64] = {};
+	static int cached_per_sm[4][64] = {};     // one table per <S, MINB> instantiation
 	int& per_sm = cached_per_sm[(sq ? 1 : 0) + (dims == 3 ? 2 : 0)][c->device & 63];
 	if (per_sm == 0) {
 		ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -533,6 +528,18 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	return ICPB_OK;
+}
+
+int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
+{
+	if (c->n <= 0 || c->m <= 0) return ICPB_OK;
+	int rc;
+	if (!c->kf_ready) { if ((rc = build_filter_data(c)) != ICPB_OK) return rc; }
+	// The bound's error analysis is relative (u = 2^-24 per operation): it needs finite magnitudes whose squares stay
+	// in the normal range. Anything else (non-finite coordinates, clouds of radius > 1e15 or < 1e-15) goes through
+	// the direct kernel.
+	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f || c->kf_rq < 1e-15f) return launch_match_brute(c, dist_mode, sentinel);
+	return (c->kf_s == 16) ? launch_filter_cfg<16, 1>(c, dist_mode, sentinel) : launch_filter_cfg<8, 2>(c, dist_mode, sentinel);
 }
 
 // Called by the engine whenever it has synchronised with the stream anyway (read_state): looks at the share of

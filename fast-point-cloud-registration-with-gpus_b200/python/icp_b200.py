@@ -143,8 +143,11 @@ class Context:
         self.n = p.shape[0]
         self._ck(lib.icpb_set_source(self.h, _ptr(p), self.n, 0), "set_source")
 
-    def get_source(self):
-        out = np.empty((self.n, 3), dtype=np.float32)
+    def get_source(self, out=None):
+        """`out`: optional C-contiguous float32 [n,3] array to fill (e.g. a view of pinned host memory)."""
+        if out is None:
+            out = np.empty((self.n, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.size == 3 * self.n
         self._ck(lib.icpb_get_source(self.h, _ptr(out), 0), "get_source")
         return out
 
@@ -228,11 +231,13 @@ class Context:
         self._ck(lib.icpb_run(self.h, C.byref(params), errors.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)), "run")
         return errors, res
 
-    def iterate_host(self, params, p, q, want_idx=True):
+    def iterate_host(self, params, p, q, want_idx=True, idx_out=None):
+        """`idx_out`: optional int32 [n] array to receive the correspondences (e.g. a view of pinned host memory)."""
         p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, 3)
         self.n, self.m = p.shape[0], q.shape[0]
-        idx = np.empty(self.n, dtype=np.int32) if want_idx else None
+        idx = (idx_out if idx_out is not None else np.empty(self.n, dtype=np.int32)) if want_idx else None
+        assert idx is None or (idx.dtype == np.int32 and idx.flags["C_CONTIGUOUS"] and idx.size == self.n)
         R = np.zeros(9, dtype=np.float32)
         T = np.zeros(3, dtype=np.float32)
         rms = C.c_float()

@@ -47,6 +47,23 @@ def p2p_clouds(width, npts=None):
     return D, M
 
 
+def cpu_clouds(width=100):
+    """The clouds of src/ICP_CPU.c:51-149 (BASELINE.json config 0/1: double precision, its own pose t = (1,-0.3,0.2),
+    r = (1,-0.5,0.05) with transposed-sign elementary rotations, R = rx*ry*rz), rounded to the float32 AoS layout the
+    GPU engine takes."""
+    i = np.arange(width, dtype=np.float64)
+    lin = -2.0 + i * 4.0 / (float(width) - 1.0)
+    k = np.arange(width * width)
+    x, y = lin[k // width], lin[k % width]
+    D = np.stack([x, y, x ** 2 - y ** 2], axis=0)
+    a, b, c = 1.0, -0.5, 0.05
+    rx = np.array([[1, 0, 0], [0, np.cos(a), np.sin(a)], [0, -np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, -np.sin(b)], [0, 1, 0], [np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(c), np.sin(c), 0], [-np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    M = (rx @ ry @ rz) @ D + np.array([1.0, -0.3, 0.2])[:, None]
+    return np.ascontiguousarray(D.T, np.float32), np.ascontiguousarray(M.T, np.float32)
+
+
 # ---- BASELINE.json config 5: batched independent pairs (SURVEY.md §8d) ---------------------------------
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 

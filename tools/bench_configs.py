@@ -2,14 +2,11 @@
 import os, sys, json, time, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "fast-point-cloud-registration-with-gpus_b200", "python"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import icp_b200 as ib, icp_synth
 out = {}
 ctx = ib.Context(0)
 # config 1: src/ICP_CPU.c's own clouds (100x100, its pose), tol 1e-5, MAX_ITER 200 — on the GPU engine
-import oracle as orc
-Dd, Md = orc.synth_cpu_f64(100)
-D = np.ascontiguousarray(Dd.reshape(3, -1).T, np.float32); M = np.ascontiguousarray(Md.reshape(3, -1).T, np.float32)
+D, M = icp_synth.cpu_clouds(100)
 ctx.set_target(M); ctx.set_source(D); ctx.run(ib.default_params(max_iter=200, tol=1e-5))
 ctx.set_source(D); e, r = ctx.run(ib.default_params(max_iter=200, tol=1e-5))
 out["config1_icp_cpu_clouds_10k"] = {"iterations_run": r.iterations_run, "elapsed_ms": r.elapsed_ms, "final_rms": float(e[r.iterations + 1]),
