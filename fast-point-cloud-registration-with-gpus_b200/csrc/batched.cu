@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "k1_device.cuh"
 #include "solve_device.cuh"
+#include <cstdlib>
 
 namespace icpb {
 
@@ -216,6 +217,310 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchP
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K9F: the same loop with K1F's lower-bound filter in front of the exact chain (nn_filter.cu; derivation in
+// DESIGN.md §K1F). Per registration the target is centred on its bounding box once (Xc, Yc, Zc, W = |q-c|^2 next to
+// X, Y, Z in shared memory, Rq = max |q-c|); per iteration every source starts from the exact distance to its
+// previous correspondence (strictly above it, so that match — or an equal one with a lower index — is found again),
+// a 64-target sub-tile is skipped when the 3-FMA bound proves every chain value in it exceeds the running exact
+// threshold, and the sub-tiles that cannot be excluded are evaluated by the whole warp with K1's packed chain. Every
+// index therefore comes from the exact chain with the reference's tie rule: trajectories are bitwise those of the
+// direct kernel above (tests/test_gpu_batched.py::test_batched_filter_is_bitwise_the_direct_kernel). Degenerate
+// targets (non-finite coordinates, radius outside [1e-15, 1e15]) skip the filter: every sub-tile takes the exact pass.
+// Sources, thresholds and indices live in per-thread shared-memory slots so that the inner loop fits 128 registers.
+// ------------------------------------------------------------------------------------------------
+constexpr float K9_U = 5.9604644775390625e-08f;            // 2^-24
+
+template <int MODE>
+__global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_filter_kernel(const BatchParams p)
+{
+	extern __shared__ __align__(16) unsigned char k9_smem[];
+	constexpr int S = K9_S, T_ = K9_THREADS;
+	const int mpad = ((p.m + K9_TRK - 1) / K9_TRK) * K9_TRK;
+	const int stride = mpad + 4;                           // +4 floats: the quad prefetch of the last sub-tile stays in bounds
+	float* tx  = reinterpret_cast<float*>(k9_smem);
+	float* ty  = tx + stride;
+	float* tz  = ty + stride;
+	float* txc = tz + stride;
+	float* tyc = txc + stride;
+	float* tzc = tyc + stride;
+	float* tw  = tzc + stride;
+	const int tid = threadIdx.x;
+	float* slots  = tw + stride;                           // [6][S][T_] per-thread slots
+	float* thr_s  = slots + tid;
+	int*   best_s = reinterpret_cast<int*>(slots + S * T_) + tid;
+	float* ox_s   = slots + 2 * S * T_ + tid;
+	float* oy_s   = slots + 3 * S * T_ + tid;
+	float* oz_s   = slots + 4 * S * T_ + tid;
+	int*   idx_s  = reinterpret_cast<int*>(slots + 5 * S * T_) + tid;
+	__shared__ double red[K9_THREADS / 32];
+	__shared__ double mom[16];
+	__shared__ IterState st;
+	__shared__ float err_prev;
+	__shared__ int s_b;
+	__shared__ float s_lo[K9_THREADS / 32][3], s_hi[K9_THREADS / 32][3];
+	__shared__ unsigned s_r2[K9_THREADS / 32];
+	__shared__ float s_ctr[3], s_rq;
+	__shared__ int s_filter_ok;
+	const float inf = __int_as_float(0x7f800000);
+	const float one8u = 1.0f + 8.0f * K9_U;
+	const int lane = tid & 31, warp = tid >> 5;
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) s_b = atomicAdd(p.next, 1);
+		__syncthreads();
+		const int b = s_b;
+		if (b >= p.batch) break;
+
+		// ---- target: originals, bounding box -> centre, centred copy + W, radius bound ----
+		const float* Tg = p.targets + (size_t)b * p.m * 3;
+		float lo[3] = { inf, inf, inf }, hi[3] = { -inf, -inf, -inf };
+		for (int j = tid; j < stride; j += T_) {
+			const bool ok = j < p.m;
+			const float x = ok ? Tg[3 * (size_t)j] : inf, y = ok ? Tg[3 * (size_t)j + 1] : inf, z = ok ? Tg[3 * (size_t)j + 2] : inf;
+			tx[j] = x; ty[j] = y; tz[j] = z;
+			if (ok) { lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z); hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z); }
+		}
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+			if (lane == 0) { s_lo[warp][k] = lo[k]; s_hi[warp][k] = hi[k]; }
+		}
+		__syncthreads();
+		if (tid < 3) {
+			float a = inf, c = -inf;
+			for (int w = 0; w < K9_THREADS / 32; w++) { a = fminf(a, s_lo[w][tid]); c = fmaxf(c, s_hi[w][tid]); }
+			float ctr = 0.5f * a + 0.5f * c;
+			if (!isfinite(ctr)) ctr = 0.0f;
+			s_ctr[tid] = ctr;
+		}
+		__syncthreads();
+		const float cx = s_ctr[0], cy = s_ctr[1], cz = s_ctr[2];
+		unsigned r2 = 0u;
+		for (int j = tid; j < stride; j += T_) {
+			float xc = 1e18f, yc = 1e18f, zc = 1e18f, w = 3e36f;
+			if (j < p.m) {
+				xc = __fsub_rn(tx[j], cx); yc = __fsub_rn(ty[j], cy); zc = __fsub_rn(tz[j], cz);
+				w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
+				r2 = max(r2, __float_as_uint(w));          // w >= 0 or NaN: uint order = float order, NaN on top
+			}
+			txc[j] = xc; tyc[j] = yc; tzc[j] = zc; tw[j] = w;
+		}
+		for (int o = 16; o > 0; o >>= 1) r2 = max(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+		if (lane == 0) s_r2[warp] = r2;
+		__syncthreads();
+		if (tid == 0) {
+			unsigned m2 = 0u;
+			for (int w = 0; w < K9_THREADS / 32; w++) m2 = max(m2, s_r2[w]);
+			const float rq = __fmul_ru(__fsqrt_ru(__uint_as_float(m2)), one8u);
+			s_rq = rq;
+			s_filter_ok = (isfinite(rq) && rq <= 1e15f && rq >= 1e-15f) ? 1 : 0;
+			st.done = 0; st.iteration = 0; st.iters_run = 0; st.flags = p.flags;
+			for (int k = 0; k < 9; k++) st.Rtot[k] = (k % 4 == 0) ? 1.0 : 0.0;
+			for (int k = 0; k < 3; k++) st.ttot[k] = 0.0;
+			err_prev = 0.f;
+			p.errors[(size_t)b * (p.max_iter + 1)] = 0.f;
+		}
+		const float* Sg = p.sources + (size_t)b * p.n * 3;
+#pragma unroll
+		for (int s = 0; s < S; s++) {
+			const int i = s * T_ + tid;
+			const bool ok = i < p.n;
+			ox_s[s * T_] = ok ? Sg[3 * (size_t)i] : 0.f; oy_s[s * T_] = ok ? Sg[3 * (size_t)i + 1] : 0.f; oz_s[s * T_] = ok ? Sg[3 * (size_t)i + 2] : 0.f;
+			idx_s[s * T_] = 0;
+		}
+		__syncthreads();
+		const float rq = s_rq;
+		const bool filter_ok = s_filter_ok != 0;
+		const float4* X4  = reinterpret_cast<const float4*>(tx);
+		const float4* Y4  = reinterpret_cast<const float4*>(ty);
+		const float4* Z4  = reinterpret_cast<const float4*>(tz);
+		const float4* XC4 = reinterpret_cast<const float4*>(txc);
+		const float4* YC4 = reinterpret_cast<const float4*>(tyc);
+		const float4* ZC4 = reinterpret_cast<const float4*>(tzc);
+		const float4* W4  = reinterpret_cast<const float4*>(tw);
+		const int nsub = mpad / K9_TRK;
+
+		while (true) {
+			// ---- matching ----
+			float ax[S], ay[S], az[S], tau[S], kk[S];
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				const float x = ox_s[s * T_], y = oy_s[s * T_], z = oz_s[s * T_];
+				const float pcx = __fsub_rn(x, cx), pcy = __fsub_rn(y, cy), pcz = __fsub_rn(z, cz);
+				ax[s] = -2.0f * pcx; ay[s] = -2.0f * pcy; az[s] = -2.0f * pcz;
+				const float p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
+				const float p2lo = __fmul_rd(p2, 1.0f - 8.0f * K9_U);
+				const float rp = __fmul_ru(__fsqrt_ru(p2), one8u);
+				float e = __fmul_ru(8.0f * rq, rq);
+				e = __fmaf_ru(10.0f * rp, rq, e);
+				e = __fmaf_ru(2.0f * rp, rp, e);
+				e = __fmul_ru(e, 1.05f * K9_U);
+				kk[s] = __fsub_ru(e, p2lo);
+				// warm start from the previous correspondence (index 0 in the first iteration: any index is an upper bound)
+				float th = p.thr0;
+				const int j0 = idx_s[s * T_];
+				const float us = dist_chain(x, y, z, tx[j0], ty[j0], tz[j0]);
+				const float up = (MODE == ICPB_DIST_SQRT) ? __fmul_ru(us, one8u) : us;
+				const float nx = __uint_as_float(__float_as_uint(up) + 1u);
+				if (us == us && nx < th) th = nx;
+				thr_s[s * T_] = th; best_s[s * T_] = -1;
+				tau[s] = __fadd_ru(__fmul_ru(th, one8u), kk[s]);
+			}
+#pragma unroll 1
+			for (int sub = 0; sub < nsub; sub++) {
+				const int j0 = sub * (K9_TRK / 4), j1 = j0 + K9_TRK / 4;
+				unsigned need = (1u << S) - 1u;
+				if (filter_ok) {
+					float em[S];
+#pragma unroll
+					for (int s = 0; s < S; s++) em[s] = inf;
+					float4 X = XC4[j0], Y = YC4[j0], Z = ZC4[j0], W = W4[j0];
+#pragma unroll 2
+					for (int j = j0; j < j1; j++) {
+						const float4 Xn = XC4[j + 1], Yn = YC4[j + 1], Zn = ZC4[j + 1], Wn = W4[j + 1];
+						const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+						const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+						const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+						const u64 w01 = pack2(W.x, W.y), w23 = pack2(W.z, W.w);
+#pragma unroll
+						for (int s = 0; s < S; s++) {
+							const u64 AX = bcast2v(ax[s]), AY = bcast2v(ay[s]), AZ = bcast2v(az[s]);
+							u64 e = fma2(AX, x01, fma2(AY, y01, fma2(AZ, z01, w01)));
+							float a, c;
+							unpack2(e, a, c);
+							em[s] = min3(em[s], a, c);
+							e = fma2(AX, x23, fma2(AY, y23, fma2(AZ, z23, w23)));
+							unpack2(e, a, c);
+							em[s] = min3(em[s], a, c);
+						}
+						X = Xn; Y = Yn; Z = Zn; W = Wn;
+					}
+					need = 0u;
+#pragma unroll
+					for (int s = 0; s < S; s++) {
+						const unsigned bal = __ballot_sync(0xffffffffu, em[s] <= tau[s]);
+						if (bal) need |= (1u << s);
+					}
+				}
+				if (need) {
+#pragma unroll
+					for (int s = 0; s < S; s++) {
+						if (need & (1u << s)) {          // warp-uniform
+							const float sx = ox_s[s * T_], sy = oy_s[s * T_], sz = oz_s[s * T_];
+							const float th = thr_s[s * T_];
+							const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
+							float mm = th;
+#pragma unroll 4
+							for (int j = j0; j < j1; j++) {
+								const float4 Xo = X4[j], Yo = Y4[j], Zo = Z4[j];
+								u64 dx = sub2(PX, pack2(Xo.x, Xo.y)), dy = sub2(PY, pack2(Yo.x, Yo.y)), dz = sub2(PZ, pack2(Zo.x, Zo.y));
+								u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+								float a, c;
+								unpack2(d, a, c);
+								mm = min3(mm, a, c);
+								dx = sub2(PX, pack2(Xo.z, Xo.w)); dy = sub2(PY, pack2(Yo.z, Yo.w)); dz = sub2(PZ, pack2(Zo.z, Zo.w));
+								d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+								unpack2(d, a, c);
+								mm = min3(mm, a, c);
+							}
+							if (mm < th) {
+								const float nt_ = lower_threshold<MODE>(mm);
+								thr_s[s * T_] = nt_; best_s[s * T_] = sub;
+								tau[s] = __fadd_ru(__fmul_ru(nt_, one8u), kk[s]);
+							}
+						}
+					}
+				}
+			}
+			// index recovery: first j of the remembered sub-tile that attains the minimum
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				const int bs = best_s[s * T_];
+				if (bs >= 0) {
+					const float th = thr_s[s * T_];
+					const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
+					const float sx = ox_s[s * T_], sy = oy_s[s * T_], sz = oz_s[s * T_];
+					const int base = bs * K9_TRK;
+					int found = -1;
+					for (int j = 0; j < K9_TRK && found < 0; j++) {
+						float d = dist_chain(sx, sy, sz, tx[base + j], ty[base + j], tz[base + j]);
+						if (MODE == ICPB_DIST_SQRT) d = __fsqrt_rn(d);
+						if (d <= target) found = j;
+					}
+					if (found >= 0) idx_s[s * T_] = base + found;
+				}
+			}
+			// ---- moments (FP64), SVD by thread 0 ----
+			double acc[15];
+#pragma unroll
+			for (int k = 0; k < 15; k++) acc[k] = 0.0;
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				if (s * T_ + tid < p.n) {
+					const int j = idx_s[s * T_];
+					const double x = ox_s[s * T_], y = oy_s[s * T_], z = oz_s[s * T_];
+					const double qx = tx[j], qy = ty[j], qz = tz[j];
+					acc[0] += x; acc[1] += y; acc[2] += z; acc[3] += qx; acc[4] += qy; acc[5] += qz;
+					acc[6] += qx * x; acc[7] += qy * x; acc[8] += qz * x;
+					acc[9] += qx * y; acc[10] += qy * y; acc[11] += qz * y;
+					acc[12] += qx * z; acc[13] += qy * z; acc[14] += qz * z;
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < 15; k++) { const double v = block_sum(acc[k], red); if (tid == 0) mom[k] = v; }
+			if (tid == 0) {
+				for (int k = 0; k < 15; k++) st.moments[k] = mom[k];
+				st.moments[15] = (double)p.n;
+				solve_p2p(&st);
+			}
+			__syncthreads();
+			// ---- transform (RyT arithmetic) + residual against the same correspondences ----
+			const float r0 = st.R[0], r1 = st.R[1], r2_ = st.R[2], r3 = st.R[3], r4 = st.R[4], r5 = st.R[5], r6 = st.R[6], r7 = st.R[7], r8 = st.R[8];
+			const float t0 = st.T[0], t1 = st.T[1], t2 = st.T[2];
+			double e = 0.0;
+#pragma unroll
+			for (int s = 0; s < S; s++) {
+				const float x = ox_s[s * T_], y = oy_s[s * T_], z = oz_s[s * T_];
+				const float nx = __fadd_rn(__fmaf_rn(r6, z, __fmaf_rn(r0, x, __fmul_rn(r3, y))), t0);
+				const float ny = __fadd_rn(__fmaf_rn(r7, z, __fmaf_rn(r1, x, __fmul_rn(r4, y))), t1);
+				const float nz = __fadd_rn(__fmaf_rn(r8, z, __fmaf_rn(r2_, x, __fmul_rn(r5, y))), t2);
+				ox_s[s * T_] = nx; oy_s[s * T_] = ny; oz_s[s * T_] = nz;
+				if (s * T_ + tid < p.n) {
+					const int j = idx_s[s * T_];
+					const float ex = __fsub_rn(nx, tx[j]), ey = __fsub_rn(ny, ty[j]), ez = __fsub_rn(nz, tz[j]);
+					e += (double)ex * (double)ex + (double)ey * (double)ey + (double)ez * (double)ez;
+				}
+			}
+			const double esum = block_sum(e, red);
+			if (tid == 0) {
+				const float err = (float)(sqrt(esum) / sqrt((double)p.n));
+				const int it = st.iteration;
+				p.errors[(size_t)b * (p.max_iter + 1) + it + 1] = err;
+				st.iters_run += 1;
+				const bool stop = p.stop_early && (((double)err < p.tol) || ((double)(float)fabs((double)err - (double)err_prev) < p.tol));
+				err_prev = err;
+				if (stop) st.done = 1;
+				else { st.iteration = it + 1; if (it + 1 >= p.max_iter) st.done = 1; }
+			}
+			__syncthreads();
+			if (st.done) break;
+		}
+		if (tid == 0) {
+			p.iterations[b] = st.iteration;
+			p.iterations_run[b] = st.iters_run;
+			for (int k = 0; k < 9; k++) p.R[(size_t)b * 9 + k] = st.Rtot[k];
+			for (int k = 0; k < 3; k++) p.t[(size_t)b * 3 + k] = st.ttot[k];
+		}
+		if (p.idx) {
+#pragma unroll
+			for (int s = 0; s < S; s++) { const int i = s * T_ + tid; if (i < p.n) p.idx[(size_t)b * p.n + i] = idx_s[s * T_]; }
+		}
+	}
+}
+
 } // namespace icpb
 
 using namespace icpb;
@@ -265,8 +570,14 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 	p.thr0 = (params->dist_mode == ICPB_DIST_SQRT) ? sqrt_threshold_host(params->sentinel) : params->sentinel;
 	p.errors = d_e; p.iterations = d_it; p.iterations_run = d_run; p.R = d_R; p.t = d_tt; p.idx = nullptr; p.next = d_next;
 	const int mpad = ((m + K9_TRK - 1) / K9_TRK) * K9_TRK;
-	const size_t smem = sizeof(float) * 3 * (size_t)(mpad + 4);
-	auto kern = (params->dist_mode == ICPB_DIST_SQRT) ? icp_batched_kernel<ICPB_DIST_SQRT> : icp_batched_kernel<ICPB_DIST_SQ>;
+	// default: the filter kernel (K9F); ICPB_K9_FILTER=0 selects the direct kernel (every pair through the exact chain)
+	bool use_filter = true;
+	if (const char* e = getenv("ICPB_K9_FILTER")) use_filter = atoi(e) != 0;
+	const size_t smem = use_filter ? sizeof(float) * (7 * (size_t)(mpad + 4) + 6 * (size_t)K9_S * K9_THREADS)
+	                               : sizeof(float) * 3 * (size_t)(mpad + 4);
+	const bool sq = params->dist_mode == ICPB_DIST_SQRT;
+	auto kern = use_filter ? (sq ? icp_batched_filter_kernel<ICPB_DIST_SQRT> : icp_batched_filter_kernel<ICPB_DIST_SQ>)
+	                       : (sq ? icp_batched_kernel<ICPB_DIST_SQRT> : icp_batched_kernel<ICPB_DIST_SQ>);
 	K9_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	K9_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K9_THREADS, smem));

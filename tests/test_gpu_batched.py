@@ -46,3 +46,35 @@ def test_batched_argument_checks(ctx, ib):
     big = np.zeros((1, 4097, 3), np.float32)
     with pytest.raises(ib.IcpError, match="larger"):
         ctx.run_batched(ib.default_params(), big, big)
+
+
+def test_batched_filter_is_bitwise_the_direct_kernel(ib):
+    """K9F (lower-bound filter + exact refine, the default) against K9 (exact chain on every pair, ICPB_K9_FILTER=0):
+    identical error trajectories, iteration counts and accumulated transforms, bit for bit — in both distance modes,
+    for ragged sizes (n, m not multiples of anything, n != m), lattice targets full of exact ties, and a degenerate
+    target (non-finite point) that must take the no-filter path."""
+    import os
+    import icp_synth
+    rng = np.random.default_rng(11)
+    cases = []
+    S, T, _, _ = icp_synth.batched_pairs(24)
+    cases.append((S, T))
+    S2, T2, _, _ = icp_synth.batched_pairs(5, n=1500)
+    cases.append((S2, T2[:, :1333].copy()))                                       # n != m, ragged
+    lat_t = (rng.integers(-6, 7, size=(3, 3000, 3)) * 0.25).astype(np.float32)
+    lat_s = (rng.integers(-12, 13, size=(3, 700, 3)) * 0.125 + 0.03).astype(np.float32)
+    cases.append((lat_s, lat_t))
+    bad_t = T[:2].copy(); bad_t[1, 17] = np.inf
+    cases.append((S[:2].copy(), bad_t))
+    out = {}
+    for flt in ("1", "0"):
+        os.environ["ICPB_K9_FILTER"] = flt
+        try:
+            with ib.Context(0) as c:
+                out[flt] = [c.run_batched(ib.default_params(max_iter=30, dist_mode=mode), s, t)[:4]
+                            for (s, t) in cases for mode in (ib.DIST_SQ, ib.DIST_SQRT)]
+        finally:
+            del os.environ["ICPB_K9_FILTER"]
+    for a, b in zip(out["1"], out["0"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
