@@ -44,7 +44,7 @@ def clocks_start(device_index):
     try:
         f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         p = subprocess.Popen(["nvidia-smi", "-i", str(device_index),
-                              "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                              "--query-gpu=timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
                               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
                               "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
@@ -53,7 +53,20 @@ def clocks_start(device_index):
         return None, None
 
 
-def clocks_stop(p, f):
+def _smi_time(text):
+    """nvidia-smi's timestamp ("2026/10/18 11:19:44.901", local time) -> seconds since the epoch, or None."""
+    import datetime
+    try:
+        return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+    except ValueError:
+        return None
+
+
+def clocks_stop(p, f, t_begin=None, t_end=None):
+    """Median SM clock under load and the throttle reasons seen. The sampler is started BEFORE the warm-up (starting
+    nvidia-smi initialises NVML, which stalls kernel launches on the box for tens of milliseconds — inside a timed
+    region of 10 x 12 ms steps that is a 25 % error); only the samples taken between t_begin and t_end (wall clock of
+    the timed region, +- one sampling period) are used when the timestamps parse."""
     if p is None:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
     p.terminate()
@@ -62,16 +75,21 @@ def clocks_stop(p, f):
     except Exception:
         p.kill()
     f.flush(); f.seek(0)
-    sm, mx, reasons = [], [], set()
+    rows = []
     for line in f.read().splitlines():
         c = [x.strip() for x in line.split(",")]
-        if len(c) < 8:
+        if len(c) < 9:
             continue
         try:
-            sm.append(float(c[0])); mx.append(float(c[1]))
+            rows.append((_smi_time(c[0]), float(c[1]), float(c[2]), c[5:9]))
         except ValueError:
             continue
-        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+    inside = [r for r in rows if r[0] is not None and t_begin is not None and t_begin - 0.25 <= r[0] <= t_end + 0.25]
+    window = "timed region" if inside else "warm-up + timed region"
+    sm, mx, reasons = [], [], set()
+    for _, a, b, flags in (inside or rows):
+        sm.append(a); mx.append(b)
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
             if v.lower().startswith("active"):
                 reasons.add(name)
     f.close()
@@ -81,7 +99,7 @@ def clocks_stop(p, f):
         pass
     busy = [s for s in sm if s > 500] or sm
     return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons), "samples": len(sm)}
+            "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_match_rate(orc, D, M, seconds_target, mode=0):
@@ -165,7 +183,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-ref-binary", action="store_true")
-    ap.add_argument("--balance", type=int, default=1, help="N > 1: deal source blocks in proportion to each GPU's measured matching rate (0: even deal)")
+    ap.add_argument("--balance", type=int, default=0, help="N > 1: 1 = deal source blocks in proportion to each GPU's measured matching rate (two extra untimed steps); 0 = even deal (B200s of one box measured within +-1.2 %, so this is off by default)")
     ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
                     help="how the source is dealt to the ranks (N > 1): blocks of 2048 points round-robin, or contiguous ranges")
     args = ap.parse_args()
@@ -223,6 +241,7 @@ def main():
         return float(t.item())
 
     ctx = ib.Context(local_rank, rank, world, nccl_id)
+    clk_p, clk_f = clocks_start(local_rank) if rank == 0 else (None, None)     # seconds before the timed region, see clocks_stop
     D, M = icp_synth.p2p_clouds(args.width)
     n_total, m = D.shape[0], M.shape[0]
     if args.shard == "contiguous":
@@ -262,9 +281,9 @@ def main():
     for _ in range(args.warmup):
         one_step()
     barrier()
-    clk_p, clk_f = clocks_start(local_rank) if rank == 0 else (None, None)
     launches0 = ctx.launch_count()
     step_ms, match_ms = [], []
+    t_epoch0 = time.time()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         res = one_step()
@@ -272,7 +291,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
-    clocks = clocks_stop(clk_p, clk_f) if rank == 0 else None
+    clocks = clocks_stop(clk_p, clk_f, t_epoch0, time.time()) if rank == 0 else None
 
     total_ms = allmax(sum(step_ms))
     match_total_ms = allmax(sum(match_ms))
