@@ -175,6 +175,7 @@ struct Ctx {
 	int     kf_nt = 0;
 	unsigned long long* kf_stats = nullptr;
 	unsigned long long* kf_work_counter = nullptr;
+	int     kf_gss[3] = {0, 0, 0};      // ICPB_KF_GSS=min,max,div: guided self-scheduling parameters (experiments)
 	int     kf_chunk_override = 0;      // ICPB_KF_CHUNK: tiles per work chunk
 	int     kf_s = 8;                   // sources per thread of the filter kernel (ICPB_KF_S=8|16)
 	int     kf_drop = 2;                // axis left out of the planar (2-FMA) bound, chosen per target (kf_score_kernel)

@@ -51,6 +51,7 @@ struct KFParams {
 	int          n, m, nt;
 	long long    total_units;   // source blocks x nt: (source block, target tile) work units, source-block major
 	int          min_chunk, max_chunk;   // tiles per grab: guided self-scheduling between these bounds
+	int          gss_div;                // a grab takes 1/(gss_div x grid) of what is left
 	unsigned long long* work_counter;    // zeroed before the launch; CTAs draw ranges of units from it
 	float        thr0;
 	float        cx, cy, cz;  // centre removed from both clouds for the filter quantities
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_filter(const KFParams p)
 		if (tid == 0) {
 			const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(p.work_counter);   // may be stale: only sizes the grab
 			const long long left = p.total_units - (long long)seen;
-			long long len = left / (4ll * (long long)gridDim.x);
+			long long len = left / ((long long)p.gss_div * (long long)gridDim.x);
 			if (len < p.min_chunk) len = p.min_chunk;
 			if (len > p.max_chunk) len = p.max_chunk;
 			s_len = (int)len;
@@ -512,10 +513,11 @@ template <int S, int MINB> static int launch_filter_cfg(Ctx* c, int dist_mode, f
 	}
 	long long grid = (long long)c->sm_count * per_sm;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
-	// guided self-scheduling between 2 and 64 tiles per grab (measured at 1M x 1M with fixed chunks: 16-64 tiles 118 ms,
+	// guided self-scheduling between 2 and 32 tiles per grab (measured at 1M x 1M with fixed chunks: 16-64 tiles 118 ms,
 	// 256: 120 ms, 1024: 126 ms); ICPB_KF_CHUNK=k pins both bounds to k (fixed chunks, for experiments)
 	p.total_units = (long long)nb * p.nt;
-	p.min_chunk = 2; p.max_chunk = 64;
+	p.min_chunk = 2; p.max_chunk = 32; p.gss_div = 4;      // tools/sweep_gss.py: flat within 1 % around these; 128+ tiles per grab hurts small shards
+	if (c->kf_gss[0] > 0) { p.min_chunk = c->kf_gss[0]; p.max_chunk = c->kf_gss[1]; p.gss_div = c->kf_gss[2]; }     // ICPB_KF_GSS=min,max,div
 	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
 	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
 	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;

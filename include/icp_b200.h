@@ -43,9 +43,9 @@ extern "C" {
 #define ICPB_POINT_TO_POINT 0   /* centroids, 3x3 cross-covariance, SVD, R = U*V^T   src/ICP_point_to_point.cu:313-398 */
 #define ICPB_POINT_TO_PLANE 1   /* 6x6 normal equations, Cholesky, Euler -> R        src/ICP_point_to_plane.cu:537-601 */
 
-#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method): a 3-FMA lower bound is
-                                   evaluated for every pair and the reference's chain wherever the bound cannot exclude
-                                   the pair's 128-target sub-tile; identical indices */
+#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method): a rigorous 2- or 3-FMA lower
+                                   bound is evaluated for every pair and the reference's chain wherever the bound cannot
+                                   exclude the pair's 128-target sub-tile; identical indices (icpb_get_filter_config) */
 #define ICPB_NN_GRID  1         /* exact uniform-grid search, identical indices */
 #define ICPB_NN_BRUTE_DIRECT 2  /* exact brute force, the reference's chain evaluated for every pair (no pruning) */
 
