@@ -1,0 +1,119 @@
+"""CPU suite: the arithmetic of K1F's lower-bound filter (csrc/nn_filter.cu), restated in numpy.
+
+The kernel skips a 128-target sub-tile for a source when  min_j e~_j > tau(thr)  and then never looks at those targets
+again, so correctness rests on one inequality per (source, target) pair:
+
+        e~_j  <=  tau(d_chain_j)                       (if target j is at chain distance d, no threshold >= d lets it be skipped)
+
+with every quantity computed exactly as the kernel computes it in float32 — centring, FMA chains, directed roundings.
+This test evaluates both sides for millions of pairs (full 3-FMA bound and the planar 2-FMA bound for each dropped
+axis) on clouds chosen to stress the error analysis: large offsets from the origin (cancellation), tiny and huge
+scales, coincident and nearly coincident points (relative error of tiny distances), lattices, sources far outside the
+target. float32 FMAs are emulated in extended precision (exact product, one rounding)."""
+import numpy as np
+import pytest
+
+F = np.float32
+U = F(2.0 ** -24)
+ONE8U = F(1.0) + F(8.0) * U
+
+
+def fma(a, b, c):
+    return (a.astype(np.longdouble) * b.astype(np.longdouble) + c.astype(np.longdouble)).astype(np.float32)
+
+
+def _dir(x64, up):
+    """Round float64 values to float32 toward +inf (up) or -inf."""
+    x64 = np.atleast_1d(np.asarray(x64, np.float64))
+    x32 = x64.astype(np.float32)
+    back = x32.astype(np.float64)
+    if up:
+        bad = back < x64
+        x32[bad] = np.nextafter(x32[bad], F(np.inf))
+    else:
+        bad = back > x64
+        x32[bad] = np.nextafter(x32[bad], F(-np.inf))
+    return x32
+
+
+def mul_ru(a, b): return _dir(np.asarray(a, np.float64) * np.asarray(b, np.float64), True)
+def mul_rd(a, b): return _dir(np.asarray(a, np.float64) * np.asarray(b, np.float64), False)
+def add_ru(a, b): return _dir(np.asarray(a, np.float64) + np.asarray(b, np.float64), True)
+def sub_ru(a, b): return _dir(np.asarray(a, np.float64) - np.asarray(b, np.float64), True)
+def fma_ru(a, b, c): return _dir((np.asarray(a, np.longdouble) * np.asarray(b, np.longdouble) + np.asarray(c, np.longdouble)).astype(np.float64), True)
+def sqrt_ru(a): return _dir(np.sqrt(np.asarray(a, np.float64)), True)
+
+
+def chain(dx, dy, dz):
+    return fma(dz, dz, fma(dx, dx, dy * dy))
+
+
+def check_cloud(P, Q, axes_sets=((0, 1, 2), (1, 2), (0, 2), (0, 1))):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    ctr = (F(0.5) * Q.min(axis=0) + F(0.5) * Q.max(axis=0)).astype(np.float32)          # kf_center
+    qc = (Q - ctr).astype(np.float32)
+    w3 = chain(qc[:, 0], qc[:, 1], qc[:, 2])
+    rq = np.nextafter(F(np.sqrt(F(w3.max())) * ONE8U), F(np.inf))                        # kf_rq
+    pc = (P - ctr).astype(np.float32)
+    # exact chain distances, all pairs
+    d = chain((P[:, None, 0] - Q[None, :, 0]).astype(np.float32), (P[:, None, 1] - Q[None, :, 1]).astype(np.float32),
+              (P[:, None, 2] - Q[None, :, 2]).astype(np.float32))
+    worst = {}
+    for axes in axes_sets:
+        if len(axes) == 3:
+            p2 = chain(pc[:, 0], pc[:, 1], pc[:, 2])
+            w = w3
+            e = fma(-2 * pc[:, None, 0], qc[None, :, 0], fma(-2 * pc[:, None, 1], qc[None, :, 1],
+                    fma(-2 * pc[:, None, 2], qc[None, :, 2], np.broadcast_to(w[None, :], d.shape))))
+        else:
+            a, b = axes
+            p2 = fma(pc[:, a], pc[:, a], pc[:, b] * pc[:, b])
+            w = fma(qc[:, a], qc[:, a], qc[:, b] * qc[:, b])
+            e = fma(-2 * pc[:, None, a], qc[None, :, a], fma(-2 * pc[:, None, b], qc[None, :, b], np.broadcast_to(w[None, :], d.shape)))
+        p2lo = mul_rd(p2, F(1.0) - F(8.0) * U)
+        rp = mul_ru(sqrt_ru(p2), ONE8U)
+        eps = mul_ru(F(8.0) * rq, rq) * np.ones_like(rp)
+        eps = fma_ru(F(10.0) * rp, rq * np.ones_like(rp), eps)
+        eps = fma_ru(F(2.0) * rp, rp, eps)
+        eps = mul_ru(eps, F(1.05) * U)
+        kk = sub_ru(eps, p2lo)
+        tau = add_ru(mul_ru(d, ONE8U), np.broadcast_to(kk[:, None], d.shape))          # tau(thr = d_chain_j)
+        ok = e <= tau
+        assert ok.all(), "lower bound violated for axes %s at %d pairs (first: %s)" % (axes, (~ok).sum(), np.argwhere(~ok)[0])
+        worst[axes] = float(np.min((tau.astype(np.float64) - e.astype(np.float64)) / np.maximum(np.abs(tau.astype(np.float64)), 1e-300)))
+    return worst
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_bound_holds_on_random_clouds_offsets_and_scales(seed):
+    rng = np.random.default_rng(seed)
+    base_q = rng.normal(size=(700, 3)); base_p = rng.normal(size=(500, 3))
+    for shift, scale in ((0.0, 1.0), (1000.0, 1.0), (-5e4, 30.0), (3.0, 1e5), (0.0, 1e-4), (7.0, 1e-3), (123456.0, 0.5)):
+        Q = (base_q * scale + shift).astype(np.float32)
+        P = (base_p * scale + shift).astype(np.float32)
+        P[:10] += np.float32(50 * scale)                      # far outside the target
+        check_cloud(P, Q)
+
+
+def test_bound_holds_for_coincident_and_nearly_coincident_points(orc):
+    """ICP at convergence: sources sit on targets (d = 0 exactly, or a few ulps) — the regime where a relative bound
+    on a difference of large numbers is most easily wrong."""
+    D, M = orc.synth_p2p(40)
+    check_cloud(M[:600], M)                                                    # exact coincidence
+    P = M[:600].copy()
+    P = np.nextafter(P, np.float32(np.inf)); P[::2] = np.nextafter(P[::2], np.float32(np.inf))
+    check_cloud(P, M)                                                          # 1-2 ulps away
+    P = orc.icp_p2p(D, M, max_iter=30)["P"]                                    # a registration's last stage
+    check_cloud(P[:800], M)
+    check_cloud(D[:800], M)                                                    # and its first
+
+
+def test_bound_holds_on_lattices_and_flat_clouds():
+    rng = np.random.default_rng(3)
+    Q = (rng.integers(-8, 9, size=(900, 3)) * 0.25).astype(np.float32)
+    P = (rng.integers(-16, 17, size=(600, 3)) * 0.125).astype(np.float32)
+    check_cloud(P, Q)
+    Q[:, 2] = 0.0; P[:, 2] = np.float32(1e-3)                                  # planar target: one centred coordinate is all zeros
+    check_cloud(P, Q)
+    Q[:, 1] = Q[:, 0]                                                          # collinear
+    check_cloud(P, Q)
