@@ -361,7 +361,12 @@ def main():
                          "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
                          "kernel": "k1_filter (brute-force NN: a %d-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)" % fcfg["dims_last"],
-                         "flop_per_pair": 8, "filter": fcfg, "traffic": traffic,
+                         "flop_per_pair": 8, "filter": fcfg,
+                         "executed": {"fma_per_pair": fcfg["dims_last"], "min3_per_pair": 0.5,
+                                      "fma_pipe_frac": (achieved / 8.0) * fcfg["dims_last"] * 2.0 / fp32_peak,
+                                      "note": "FP32 work the filter actually executes per pair (exact re-evaluations of the few unexcluded sub-tiles not counted): "
+                                              "FMAs on the FMA pipe, half a 3-input min on the 16-lane ALU pipe; ncu shows the two pipes never overlapping in this loop"},
+                         "traffic": traffic,
                          "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                          "note": "compute-bound (FP32 issue slots); `achieved` counts the ALGORITHMIC 8 FLOP per pair SURVEY.md 8(d) defines, so frac can exceed 1: "
                                  "the direct form executes 6 FP32 ops per pair (ceiling 66.7% of FFMA peak), the filter 3 (full bound) or 2 (planar bound) FMAs per pair"},
