@@ -64,3 +64,36 @@ def test_my_lib_dropin_matches_reference_library(golden_dir):
     exe = os.path.join(PKG, "apps", "selftest_my_lib")
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     assert out == open(os.path.join(golden_dir, "ref_my_lib_stdout.txt")).read()
+
+
+def test_header_is_plain_c_and_the_integration_stub_compiles(tmp_path):
+    """include/icp_b200.h must be consumable from C (the boundary is a C ABI): compile, as C99 with warnings as errors,
+    a translation unit that does what INTEGRATION.md (b) shows a maintainer of the reference would write, and link it
+    against libicp_b200.so (no call is executed: there is no GPU here)."""
+    src = tmp_path / "stub.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "icp_b200.h"
+int register_clouds(const float* h_D, const float* h_M, int n, float* h_error, int max_iter)
+{
+    icpb_ctx* icp = NULL;
+    if (icpb_create(&icp, 0) != ICPB_OK) { printf("no sm_100 device\n"); return -1; }
+    icpb_set_target(icp, h_M, n, 0);
+    icpb_set_source(icp, h_D, n, 0);
+    icpb_params prm; icpb_default_params(&prm);
+    prm.max_iter = max_iter; prm.flags |= ICPB_FLAG_PROFILE;
+    icpb_result res;
+    int rc = icpb_run(icp, &prm, h_error, &res);
+    if (rc != ICPB_OK) { printf("Error in the ICP loop: %s\n", icpb_last_error(icp)); return -1; }
+    printf("%d iterations, %f ms (matching %f, minimisation %f, transformation %f)\n", res.iterations, res.elapsed_ms, res.match_ms, res.minimize_ms, res.transform_ms);
+    int rank, world, peer; icpb_dist_info(icp, &rank, &world, &peer);
+    float ms; icpb_estimate_normals_ex(icp, 4, ICPB_DIST_SQ, &ms);
+    icpb_destroy(icp);
+    return res.iterations;
+}
+int main(void) { return icpb_version() == ICPB_VERSION ? 0 : 1; }
+''')
+    exe = tmp_path / "stub"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", PKG, "-licp_b200", "-Wl,-rpath," + PKG], check=True, capture_output=True, text=True)
+    assert subprocess.run([str(exe)]).returncode == 0
