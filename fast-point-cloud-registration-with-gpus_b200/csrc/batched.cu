@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchP
 // DESIGN.md §K1F). Per registration the target is centred on its bounding box once (Xc, Yc, Zc, W = |q-c|^2 next to
 // X, Y, Z in shared memory, Rq = max |q-c|); per iteration every source starts from the exact distance to its
 // previous correspondence (strictly above it, so that match — or an equal one with a lower index — is found again),
-// a 64-target sub-tile is skipped when the 3-FMA bound proves every chain value in it exceeds the running exact
+// a 32-target sub-tile is skipped when the 3-FMA bound proves every chain value in it exceeds the running exact
 // threshold, and the sub-tiles that cannot be excluded are evaluated by the whole warp with K1's packed chain. Every
 // index therefore comes from the exact chain with the reference's tie rule: trajectories are bitwise those of the
 // direct kernel above (tests/test_gpu_batched.py::test_batched_filter_is_bitwise_the_direct_kernel). Degenerate
@@ -232,12 +232,12 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchP
 // ------------------------------------------------------------------------------------------------
 constexpr float K9_U = 5.9604644775390625e-08f;            // 2^-24
 
-template <int MODE>
+template <int MODE, int TRK>
 __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_filter_kernel(const BatchParams p)
 {
 	extern __shared__ __align__(16) unsigned char k9_smem[];
 	constexpr int S = K9_S, T_ = K9_THREADS;
-	const int mpad = ((p.m + K9_TRK - 1) / K9_TRK) * K9_TRK;
+	const int mpad = ((p.m + 127) / 128) * 128;            // a multiple of every supported sub-tile size (host: mpad_f)
 	const int stride = mpad + 4;                           // +4 floats: the quad prefetch of the last sub-tile stays in bounds
 	float* tx  = reinterpret_cast<float*>(k9_smem);
 	float* ty  = tx + stride;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_filter_kernel(const
 		const float4* YC4 = reinterpret_cast<const float4*>(tyc);
 		const float4* ZC4 = reinterpret_cast<const float4*>(tzc);
 		const float4* W4  = reinterpret_cast<const float4*>(tw);
-		const int nsub = mpad / K9_TRK;
+		const int nsub = mpad / TRK;
 
 		while (true) {
 			// ---- matching ----
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_filter_kernel(const
 			}
 #pragma unroll 1
 			for (int sub = 0; sub < nsub; sub++) {
-				const int j0 = sub * (K9_TRK / 4), j1 = j0 + K9_TRK / 4;
+				const int j0 = sub * (TRK / 4), j1 = j0 + TRK / 4;
 				unsigned need = (1u << S) - 1u;
 				if (filter_ok) {
 					float em[S];
@@ -443,9 +443,9 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_filter_kernel(const
 					const float th = thr_s[s * T_];
 					const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
 					const float sx = ox_s[s * T_], sy = oy_s[s * T_], sz = oz_s[s * T_];
-					const int base = bs * K9_TRK;
+					const int base = bs * TRK;
 					int found = -1;
-					for (int j = 0; j < K9_TRK && found < 0; j++) {
+					for (int j = 0; j < TRK && found < 0; j++) {
 						float d = dist_chain(sx, sy, sz, tx[base + j], ty[base + j], tz[base + j]);
 						if (MODE == ICPB_DIST_SQRT) d = __fsqrt_rn(d);
 						if (d <= target) found = j;
@@ -573,11 +573,19 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 	// default: the filter kernel (K9F); ICPB_K9_FILTER=0 selects the direct kernel (every pair through the exact chain)
 	bool use_filter = true;
 	if (const char* e = getenv("ICPB_K9_FILTER")) use_filter = atoi(e) != 0;
-	const size_t smem = use_filter ? sizeof(float) * (7 * (size_t)(mpad + 4) + 6 * (size_t)K9_S * K9_THREADS)
+	// K9F's sub-tile (targets per filter test / exact pass): 32 (measured on B200, 2368 pairs of 2048 points: 32 -> 25.5 ms,
+	// 64 -> 27.1 ms, 128 -> 30.7 ms: finer sub-tiles send fewer irrelevant targets through the exact chain);
+	// ICPB_K9_TRK=32|64|128 overrides. mpad is a multiple of 128 so that every choice tiles it.
+	int trk = 32;
+	if (const char* e = getenv("ICPB_K9_TRK")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) trk = v; }
+	const int mpad_f = ((m + 127) / 128) * 128;
+	const size_t smem = use_filter ? sizeof(float) * (7 * (size_t)(mpad_f + 4) + 6 * (size_t)K9_S * K9_THREADS)
 	                               : sizeof(float) * 3 * (size_t)(mpad + 4);
 	const bool sq = params->dist_mode == ICPB_DIST_SQRT;
-	auto kern = use_filter ? (sq ? icp_batched_filter_kernel<ICPB_DIST_SQRT> : icp_batched_filter_kernel<ICPB_DIST_SQ>)
-	                       : (sq ? icp_batched_kernel<ICPB_DIST_SQRT> : icp_batched_kernel<ICPB_DIST_SQ>);
+	auto kern = !use_filter ? (sq ? icp_batched_kernel<ICPB_DIST_SQRT> : icp_batched_kernel<ICPB_DIST_SQ>)
+	          : trk == 64   ? (sq ? icp_batched_filter_kernel<ICPB_DIST_SQRT, 64> : icp_batched_filter_kernel<ICPB_DIST_SQ, 64>)
+	          : trk == 128  ? (sq ? icp_batched_filter_kernel<ICPB_DIST_SQRT, 128> : icp_batched_filter_kernel<ICPB_DIST_SQ, 128>)
+	                        : (sq ? icp_batched_filter_kernel<ICPB_DIST_SQRT, 32> : icp_batched_filter_kernel<ICPB_DIST_SQ, 32>);
 	K9_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	K9_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K9_THREADS, smem));
