@@ -86,6 +86,17 @@ struct ReduceParams {
 	PeerXchg     peer;                                    // peer.world > 1: exchange the sums inside the last block
 };
 
+// ---- uniform grid over the target (grid_nn.cu) and its occupancy pyramid (grid_tree.cuh) -----------------
+struct GridGeom { float ox, oy, oz, inv_h, h; int nx, ny, nz; };
+constexpr int GP_MAX_L = 18;       // pyramid levels: dims up to 2^17 per axis
+struct GridPyramid {
+	int levels;                    // level 0 = the grid's cells, level levels-1 = one root node
+	int nx[GP_MAX_L], ny[GP_MAX_L], nz[GP_MAX_L];
+	long long off[GP_MAX_L];       // offset of each level's occupancy bytes in `occ`
+	const unsigned char* occ;
+	float slack;                   // absolute per-axis slack of the box distance (grid_tree.cuh)
+};
+
 // ---- error handling -----------------------------------------------------------------------------
 struct Ctx;
 int  fail_cuda(Ctx* c, cudaError_t e, const char* what, const char* file, int line);
@@ -153,6 +164,9 @@ struct Ctx {
 	int*    grid_open_list = nullptr;   // sources the grid search left open (finished by brute force)
 	int     grid_open_cap = 0;
 	unsigned long long* grid_counters = nullptr;   // [0] open sources of the last pass, [1] candidates visited
+	bool    grid_pyramid = true;        // best-first descent of an occupancy pyramid (grid_tree.cuh); ICPB_GRID_PYRAMID=0: rings + brute-force fallback
+	unsigned char* grid_occ = nullptr;  // pyramid occupancy bytes, all levels
+	GridPyramid grid_py = {};           // level dimensions / offsets (host copy; `occ` points at grid_occ)
 
 	// source (this rank's shard)
 	int n = 0, n_cap = 0;        // n_cap: padded capacity

@@ -159,6 +159,7 @@ static int create_common(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
+	if (const char* e = getenv("ICPB_GRID_PYRAMID")) c->grid_pyramid = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_GSS")) { int a = 0, b = 0, d = 0; if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b >= a && d > 0) { c->kf_gss[0] = a; c->kf_gss[1] = b; c->kf_gss[2] = d; } }
 	if (const char* e = getenv("ICPB_KF_DIMS")) c->kf_dims_forced = atoi(e);
 	if (const char* e = getenv("ICPB_KF_S")) c->kf_s = (atoi(e) == 16) ? 16 : 8;
@@ -247,7 +248,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
+	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	if (c->st_host) cudaFreeHost(c->st_host);
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	for (int k = 0; k < 4; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);

@@ -15,9 +15,16 @@
 //  fallback: sources still open after ring GRID_RMAX (far from the cloud, e.g. the first ICP iterations)
 //      are appended to a compact list and finished by the brute-force K1 kernel through its `remap`
 //      path (device-side count, no host round trip). Both paths are exact, so their union is.
+//  pyramid (default; grid_tree.cuh): an occupancy pyramid over the same cells (an octree whose leaves are the grid's
+//      cells) descended best-first by one thread per source closes EVERY source whatever its distance — no ring limit,
+//      no brute-force fallback (1 650 points + 130 nodes per source at the initial pose of the 1M x 1M registration,
+//      55 + 41 near convergence, identical keys; the whole 45-iteration registration: 215 ms on a B200 against 1.27 s
+//      with rings + fallback). ICPB_GRID_PYRAMID=0 selects the ring search described above.
 #include "common.cuh"
 #include "k1_device.cuh"
+#include "grid_tree.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace icpb {
 
@@ -39,8 +46,6 @@ __global__ void grid_bbox_kernel(const float4* __restrict__ q4, int m, unsigned*
 		if ((threadIdx.x & 31) == 0) { atomicMin(mm + k, f2ord(lo[k])); atomicMax(mm + 3 + k, f2ord(hi[k])); }
 	}
 }
-
-struct GridGeom { float ox, oy, oz, inv_h, h; int nx, ny, nz; };
 
 __device__ __forceinline__ int cell_coord(float v, float o, float inv_h) { return (int)floorf((v - o) * inv_h); }
 
@@ -176,6 +181,58 @@ __global__ void __launch_bounds__(128) grid_query_kernel(const float* __restrict
 	if ((threadIdx.x & 31) == 0 && seen) atomicAdd(visited, seen);
 }
 
+// ---- occupancy pyramid -------------------------------------------------------------------------------------------
+__global__ void pyr_level0_kernel(const int* __restrict__ cell_start, long long ncell, unsigned char* __restrict__ occ)
+{
+	const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < ncell) occ[c] = cell_start[c + 1] > cell_start[c];
+}
+__global__ void pyr_up_kernel(const unsigned char* __restrict__ child, int nxc, int nyc, int nzc, unsigned char* __restrict__ parent, int nxp, int nyp, int nzp)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (long long)nxp * nyp * nzp) return;
+	const int x = (int)(i % nxp), y = (int)((i / nxp) % nyp), z = (int)(i / ((long long)nxp * nyp));
+	unsigned char o = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		const int cx = 2 * x + (k & 1), cy = 2 * y + ((k >> 1) & 1), cz = 2 * z + ((k >> 2) & 1);
+		if (cx < nxc && cy < nyc && cz < nzc) o |= child[(long long)cx + (long long)nxc * ((long long)cy + (long long)nyc * cz)];
+	}
+	parent[i] = o;
+}
+
+// One thread per source: best-first descent of the pyramid (grid_tree.cuh), warm-started from the previous
+// correspondence when one exists (any real candidate is a valid starting key).
+template <int MODE>
+__global__ void __launch_bounds__(128) grid_tree_query_kernel(const float* __restrict__ px, const float* __restrict__ py_, const float* __restrict__ pz, int n,
+                                                              const float4* __restrict__ sorted4, const int* __restrict__ cell_start, const float4* __restrict__ q4, int m,
+                                                              const int* __restrict__ seed, GridGeom g, const GridPyramid pyr, float thr0,
+                                                              u64* __restrict__ keys, unsigned long long* __restrict__ visited, const int* done)
+{
+	if (done != nullptr && *done) return;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long seen = 0;
+	if (i < n) {
+		const float x = px[i], y = py_[i], z = pz[i];
+		u64 best = KEY_UNMATCHED;
+		if (seed != nullptr) {
+			const int j0 = seed[i];
+			if (j0 >= 0 && j0 < m) {
+				const float4 q = __ldg(q4 + j0);
+				float d = dist_chain(x, y, z, q.x, q.y, q.z);
+				if (d < thr0) {
+					if (MODE == ICPB_DIST_SQRT) d = __fsqrt_rn(d);
+					best = ((u64)__float_as_uint(d) << 32) | (u64)(uint32_t)j0;
+				}
+			}
+		}
+		best = grid_tree_nn<MODE>(x, y, z, g, pyr, cell_start, sorted4, thr0, best, &seen);
+		if (best != KEY_UNMATCHED) keys[i] = best;
+	}
+	for (int o = 16; o > 0; o >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, o);
+	if ((threadIdx.x & 31) == 0 && seen) atomicAdd(visited, seen);
+}
+
 int launch_match_brute_remap(Ctx* c, int dist_mode, float sentinel, const int* remap, const int* count_dev);
 
 static int build_grid(Ctx* c)
@@ -192,20 +249,9 @@ static int build_grid(Ctx* c)
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	cudaFree(mm);
 	auto dec = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
-	float lo[3], hi[3], ext[3];
-	for (int k = 0; k < 3; k++) { lo[k] = dec(h_mm[k]); hi[k] = dec(h_mm[3 + k]); ext[k] = fmaxf(hi[k] - lo[k], 1e-6f); }
-	double cells_max = fmin(fmax(4.0 * m, 4096.0), 16.0 * 1024 * 1024);
-	double h = cbrt((double)ext[0] * ext[1] * ext[2] / cells_max);
-	// flat clouds: never let one axis explode the cell count
-	for (int it = 0; it < 8; it++) {
-		double cells = (floor(ext[0] / h) + 1) * (floor(ext[1] / h) + 1) * (floor(ext[2] / h) + 1);
-		if (cells <= cells_max) break;
-		h *= 1.26;
-	}
-	GridGeom g;
-	g.h = (float)h; g.inv_h = (float)(1.0 / h);
-	g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
-	g.nx = (int)floor(ext[0] / h) + 1; g.ny = (int)floor(ext[1] / h) + 1; g.nz = (int)floor(ext[2] / h) + 1;
+	float lo[3], hi[3];
+	for (int k = 0; k < 3; k++) { lo[k] = dec(h_mm[k]); hi[k] = dec(h_mm[3 + k]); }
+	const GridGeom g = compute_grid_geom(lo, hi, m);
 	const size_t ncell = (size_t)g.nx * g.ny * g.nz;
 	c->grid_dim[0] = g.nx; c->grid_dim[1] = g.ny; c->grid_dim[2] = g.nz;
 	c->grid_origin[0] = g.ox; c->grid_origin[1] = g.oy; c->grid_origin[2] = g.oz; c->grid_cell = g.h;
@@ -236,6 +282,23 @@ static int build_grid(Ctx* c)
 	}
 	if (!c->grid_counters) ICPB_CUDA(c, cudaMalloc((void**)&c->grid_counters, 4 * sizeof(unsigned long long)));
 	ICPB_CUDA(c, cudaMemsetAsync(c->grid_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+	if (c->grid_pyramid) {
+		GridPyramid& py = c->grid_py;
+		const long long total = pyramid_layout(g, py);
+		cudaFree(c->grid_occ); c->grid_occ = nullptr;
+		ICPB_CUDA(c, cudaMalloc((void**)&c->grid_occ, (size_t)total));
+		py.occ = c->grid_occ;
+		pyr_level0_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, c->stream>>>(c->grid_cell_start, (long long)ncell, c->grid_occ);
+		c->launches++;
+		for (int L = 1; L < py.levels; L++) {
+			const long long np = (long long)py.nx[L] * py.ny[L] * py.nz[L];
+			pyr_up_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(c->grid_occ + py.off[L - 1], py.nx[L - 1], py.ny[L - 1], py.nz[L - 1],
+			                                                                    c->grid_occ + py.off[L], py.nx[L], py.ny[L], py.nz[L]);
+			c->launches++;
+		}
+		ICPB_CUDA(c, cudaGetLastError());
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
 	c->grid_ready = true;
 	return ICPB_OK;
 }
@@ -258,6 +321,17 @@ int launch_match_grid(Ctx* c, int dist_mode, float sentinel)
 			while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
 		}
 		thr0 = y;
+	}
+	if (c->grid_pyramid) {
+		unsigned long long* visited_t = c->grid_counters + 1;
+		ICPB_CUDA(c, cudaMemsetAsync(c->grid_counters, 0, sizeof(unsigned long long), c->stream));      // no open sources in this mode
+		auto kt = (dist_mode == ICPB_DIST_SQRT) ? grid_tree_query_kernel<ICPB_DIST_SQRT> : grid_tree_query_kernel<ICPB_DIST_SQ>;
+		kt<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->px, c->py, c->pz, c->n, c->grid_sorted4, c->grid_cell_start, c->q4, c->m,
+		                                               c->kf_use_seed ? c->seed : nullptr, g, c->grid_py, thr0, c->keys, visited_t, &c->st->done);
+		c->launches++;
+		ICPB_CUDA(c, cudaGetLastError());
+		c->pairs_acc += (double)c->n * (double)c->m;
+		return ICPB_OK;
 	}
 	int* open_count = reinterpret_cast<int*>(c->grid_counters);                    // [0] low word: open sources of this pass
 	unsigned long long* visited = c->grid_counters + 1;                           // [1] candidates visited (cumulative)

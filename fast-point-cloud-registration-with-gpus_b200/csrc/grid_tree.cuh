@@ -1,0 +1,170 @@
+// grid_tree.cuh — K1g far field: exact nearest neighbour by best-first descent of an occupancy pyramid built over the
+// uniform grid (an octree whose leaves are the grid's cells). Host/device code: the same traversal is compiled for the
+// GPU kernel (grid_nn.cu) and for the CPU harness that checks it against brute force (tools/grid_tree_host_test.cu).
+//
+// Why: the ring search of grid_nn.cu closes a source only if its neighbour lies within 2 cells; sources farther away
+// (the first iterations of a registration) were handed to the brute-force kernel. The pyramid closes every source,
+// whatever its distance, in O(depth) node tests plus the points of the few leaves that survive pruning.
+//
+// Exactness (same contract as every matching kernel: argmin of the reference's float chain, lowest index on ties,
+// nothing at or above the sentinel): a node is skipped only if  lb * 0.998 > bound,  where lb is the squared distance
+// from the source to the node's box SHRUNK-proofed by `slack` per axis (covers the rounding of the cell assignment
+// floor((v - o) * inv_h) and of the box corners, both <= a few ulps of the largest coordinate), 0.998 covers the
+// rounding of the float chain (relative 3 * 2^-24) and of lb itself, and `bound` is the squared-domain value of the
+// best key so far widened to its whole sqrt class in sqrt mode. Equality never prunes, so an equally distant target
+// with a lower index is still found. Candidates are compared as (distance bits << 32 | index) keys, independent of the
+// visiting order. `nodes` (optional) counts node visits.
+#pragma once
+#include "common.cuh"
+#include <cmath>
+
+namespace icpb {
+
+constexpr int GP_STACK = 7 * GP_MAX_L + 2;      // GridGeom / GridPyramid / GP_MAX_L: common.cuh
+
+// Cell size: <= ~4 cells per point, <= 16M cells, never letting one axis of a flat cloud explode the count.
+inline GridGeom compute_grid_geom(const float lo[3], const float hi[3], int m)
+{
+	float ext[3];
+	for (int k = 0; k < 3; k++) ext[k] = fmaxf(hi[k] - lo[k], 1e-6f);
+	const double cells_max = fmin(fmax(4.0 * m, 4096.0), 16.0 * 1024 * 1024);
+	double h = cbrt((double)ext[0] * ext[1] * ext[2] / cells_max);
+	for (int it = 0; it < 8; it++) {
+		const double cells = (floor(ext[0] / h) + 1) * (floor(ext[1] / h) + 1) * (floor(ext[2] / h) + 1);
+		if (cells <= cells_max) break;
+		h *= 1.26;
+	}
+	GridGeom g;
+	g.h = (float)h; g.inv_h = (float)(1.0 / h);
+	g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+	g.nx = (int)floor(ext[0] / h) + 1; g.ny = (int)floor(ext[1] / h) + 1; g.nz = (int)floor(ext[2] / h) + 1;
+	return g;
+}
+
+// Level dimensions / offsets of the pyramid over a grid; returns the total number of occupancy bytes.
+inline long long pyramid_layout(const GridGeom& g, GridPyramid& py)
+{
+	int nx = g.nx, ny = g.ny, nz = g.nz, L = 0;
+	long long total = 0;
+	while (true) {
+		py.nx[L] = nx; py.ny[L] = ny; py.nz[L] = nz; py.off[L] = total;
+		total += (long long)nx * ny * nz;
+		if ((nx == 1 && ny == 1 && nz == 1) || L == GP_MAX_L - 1) break;
+		nx = (nx + 1) >> 1; ny = (ny + 1) >> 1; nz = (nz + 1) >> 1; L++;
+	}
+	py.levels = L + 1;
+	const float ex = fmaxf(fabsf(g.ox), fabsf(g.ox + g.nx * g.h)), ey = fmaxf(fabsf(g.oy), fabsf(g.oy + g.ny * g.h)), ez = fmaxf(fabsf(g.oz), fabsf(g.oz + g.nz * g.h));
+	py.slack = 4e-6f * (fmaxf(ex, fmaxf(ey, ez)) + g.h);
+	return total;
+}
+
+__host__ __device__ __forceinline__ int gt_cell_coord(float v, float o, float inv_h) { return (int)floorf((v - o) * inv_h); }
+
+__host__ __device__ __forceinline__ float gt_chain(float xp, float yp, float zp, float xq, float yq, float zq)
+{
+#ifdef __CUDA_ARCH__
+	const float dx = __fsub_rn(xp, xq), dy = __fsub_rn(yp, yq), dz = __fsub_rn(zp, zq);
+	return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+#else
+	const float dx = xp - xq, dy = yp - yq, dz = zp - zq;
+	return fmaf(dz, dz, fmaf(dx, dx, dy * dy));       // host harness: compile with -ffp-contract=off semantics (explicit fmaf)
+#endif
+}
+
+__host__ __device__ __forceinline__ float gt_sqrt(float v)
+{
+#ifdef __CUDA_ARCH__
+	return __fsqrt_rn(v);
+#else
+	return sqrtf(v);
+#endif
+}
+
+// squared-domain bound below which (inclusive) a node may still hold a candidate that beats or ties `best`
+template <int MODE> __host__ __device__ __forceinline__ float gt_bound(u64 best)
+{
+	if (best == KEY_UNMATCHED) return INFINITY;
+	unsigned hi32 = (unsigned)(best >> 32);
+	float f;
+#ifdef __CUDA_ARCH__
+	f = __uint_as_float(hi32);
+#else
+	memcpy(&f, &hi32, 4);
+#endif
+	if (MODE != ICPB_DIST_SQRT) return f;
+	const float t = f * f;
+	return t + t * 2e-6f + 1e-37f;                      // every square whose sqrt.rn equals f, and then some
+}
+
+__host__ __device__ __forceinline__ float gt_box_lb(float x, float y, float z, const GridGeom& g, float w, int cx, int cy, int cz, float slack)
+{
+	const float lx = g.ox + (float)cx * w, ly = g.oy + (float)cy * w, lz = g.oz + (float)cz * w;
+	float dx = fmaxf(fmaxf(lx - x, x - (lx + w)), 0.0f), dy = fmaxf(fmaxf(ly - y, y - (ly + w)), 0.0f), dz = fmaxf(fmaxf(lz - z, z - (lz + w)), 0.0f);
+	dx = fmaxf(dx - slack, 0.0f); dy = fmaxf(dy - slack, 0.0f); dz = fmaxf(dz - slack, 0.0f);
+	return (dz * dz + dx * dx + dy * dy) * 0.998f;
+}
+
+// Exact nearest neighbour of (x,y,z) among the grid's points. `best`: KEY_UNMATCHED or the key of any real candidate
+// (warm start). `seen` (optional) accumulates the number of points examined.
+template <int MODE>
+__host__ __device__ inline u64 grid_tree_nn(float x, float y, float z, const GridGeom& g, const GridPyramid& py, const int* __restrict__ cell_start,
+                                            const float4* __restrict__ sorted4, float thr0, u64 best, unsigned long long* seen,
+                                            unsigned long long* nodes = nullptr)
+{
+	if (!(x == x) || !(y == y) || !(z == z)) return best;           // NaN source: no distance compares below anything
+	u64 stack[GP_STACK];
+	int sp = 0;
+	stack[sp++] = (u64)(py.levels - 1) << 54;                       // root: level | cx << 36 | cy << 18 | cz
+	float bound = gt_bound<MODE>(best);
+	unsigned long long pts = 0, visited = 0;
+	while (sp > 0) {
+		const u64 node = stack[--sp];
+		visited++;
+		const int L = (int)(node >> 54), cx = (int)((node >> 36) & 0x3ffff), cy = (int)((node >> 18) & 0x3ffff), cz = (int)(node & 0x3ffff);
+		const float w = g.h * (float)(1 << L);
+		const float lb = gt_box_lb(x, y, z, g, w, cx, cy, cz, py.slack);
+		if (lb > bound || lb >= thr0) continue;
+		if (L == 0) {
+			const int c = cx + g.nx * (cy + g.ny * cz);
+			const int k0 = cell_start[c], k1 = cell_start[c + 1];
+			for (int k = k0; k < k1; k++) {
+				const float4 q = sorted4[k];
+				float d = gt_chain(x, y, z, q.x, q.y, q.z);
+				if (d < thr0) {
+					if (MODE == ICPB_DIST_SQRT) d = gt_sqrt(d);
+					unsigned db, ib;
+#ifdef __CUDA_ARCH__
+					db = __float_as_uint(d); ib = (unsigned)__float_as_int(q.w);
+#else
+					memcpy(&db, &d, 4); memcpy(&ib, &q.w, 4);
+#endif
+					const u64 key = ((u64)db << 32) | (u64)ib;
+					if (key < best) { best = key; bound = gt_bound<MODE>(best); }
+				}
+			}
+			pts += (unsigned long long)(k1 - k0);
+			continue;
+		}
+		// children at level L-1, the octant nearest to the source pushed last (popped first)
+		const int Lc = L - 1;
+		const float wc = g.h * (float)(1 << Lc);
+		const float mx = g.ox + (float)(2 * cx + 1) * wc, my = g.oy + (float)(2 * cy + 1) * wc, mz = g.oz + (float)(2 * cz + 1) * wc;
+		const int nearo = (x >= mx ? 1 : 0) | (y >= my ? 2 : 0) | (z >= mz ? 4 : 0);
+		const int nxc = py.nx[Lc], nyc = py.ny[Lc], nzc = py.nz[Lc];
+		const unsigned char* occ = py.occ + py.off[Lc];
+		for (int i = 7; i >= 0; i--) {
+			const int o = i ^ nearo;
+			const int ccx = 2 * cx + (o & 1), ccy = 2 * cy + ((o >> 1) & 1), ccz = 2 * cz + ((o >> 2) & 1);
+			if (ccx >= nxc || ccy >= nyc || ccz >= nzc) continue;
+			if (!occ[(long long)ccx + (long long)nxc * ((long long)ccy + (long long)nyc * ccz)]) continue;
+			const float clb = gt_box_lb(x, y, z, g, wc, ccx, ccy, ccz, py.slack);
+			if (clb > bound || clb >= thr0) continue;
+			stack[sp++] = ((u64)Lc << 54) | ((u64)ccx << 36) | ((u64)ccy << 18) | (u64)ccz;
+		}
+	}
+	if (seen) *seen += pts;
+	if (nodes) *nodes += visited;
+	return best;
+}
+
+} // namespace icpb

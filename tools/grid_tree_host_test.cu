@@ -1,0 +1,178 @@
+// CPU harness for csrc/grid_tree.cuh: builds the uniform grid and its occupancy pyramid on the host exactly as
+// grid_nn.cu builds them on the device, runs the SAME traversal code (host instantiation) for every source and
+// compares index and distance bits with a literal brute-force scan (reference chain via fmaf, strict `<` in ascending
+// order = lowest index on ties, sentinel). No GPU needed:
+//     nvcc -O2 -std=c++17 -Xcompiler -ffp-contract=off -I fast-point-cloud-registration-with-gpus_b200/csrc -I include \
+//          tools/grid_tree_host_test.cu -o /tmp/grid_tree_host_test && /tmp/grid_tree_host_test
+#include "grid_tree.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+using namespace icpb;
+
+struct HostGrid {
+	GridGeom g; GridPyramid py;
+	std::vector<int> cell_start; std::vector<float4> sorted4; std::vector<unsigned char> occ;
+};
+
+static HostGrid build(const std::vector<float>& Q)
+{
+	const int m = (int)Q.size() / 3;
+	float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+	for (int j = 0; j < m; j++) for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], Q[3 * j + k]); hi[k] = fmaxf(hi[k], Q[3 * j + k]); }
+	HostGrid G;
+	G.g = compute_grid_geom(lo, hi, m);
+	const GridGeom& g = G.g;
+	const size_t ncell = (size_t)g.nx * g.ny * g.nz;
+	std::vector<int> cell_of(m), cnt(ncell + 1, 0);
+	for (int j = 0; j < m; j++) {
+		int cx = std::min(std::max(gt_cell_coord(Q[3 * j], g.ox, g.inv_h), 0), g.nx - 1);
+		int cy = std::min(std::max(gt_cell_coord(Q[3 * j + 1], g.oy, g.inv_h), 0), g.ny - 1);
+		int cz = std::min(std::max(gt_cell_coord(Q[3 * j + 2], g.oz, g.inv_h), 0), g.nz - 1);
+		cell_of[j] = cx + g.nx * (cy + g.ny * cz);
+		cnt[cell_of[j]]++;
+	}
+	G.cell_start.assign(ncell + 1, 0);
+	for (size_t c = 0; c < ncell; c++) G.cell_start[c + 1] = G.cell_start[c] + cnt[c];
+	std::vector<int> fill(ncell, 0);
+	G.sorted4.resize(m);
+	for (int j = m - 1; j >= 0; j--) {            // reversed on purpose: the order inside a cell must not matter
+		const int c = cell_of[j];
+		float4 q = make_float4(Q[3 * j], Q[3 * j + 1], Q[3 * j + 2], 0.f);
+		memcpy(&q.w, &j, 4);
+		G.sorted4[G.cell_start[c] + fill[c]++] = q;
+	}
+	const long long total = pyramid_layout(g, G.py);
+	G.occ.assign((size_t)total, 0);
+	for (size_t c = 0; c < ncell; c++) G.occ[c] = G.cell_start[c + 1] > G.cell_start[c];
+	for (int L = 1; L < G.py.levels; L++) {
+		const int nxc = G.py.nx[L - 1], nyc = G.py.ny[L - 1], nzc = G.py.nz[L - 1];
+		for (int z = 0; z < G.py.nz[L]; z++) for (int y = 0; y < G.py.ny[L]; y++) for (int x = 0; x < G.py.nx[L]; x++) {
+			unsigned char o = 0;
+			for (int i = 0; i < 8; i++) {
+				const int cx = 2 * x + (i & 1), cy = 2 * y + ((i >> 1) & 1), cz = 2 * z + ((i >> 2) & 1);
+				if (cx < nxc && cy < nyc && cz < nzc) o |= G.occ[(size_t)G.py.off[L - 1] + cx + (size_t)nxc * (cy + (size_t)nyc * cz)];
+			}
+			G.occ[(size_t)G.py.off[L] + x + (size_t)G.py.nx[L] * (y + (size_t)G.py.ny[L] * z)] = o;
+		}
+	}
+	G.py.occ = G.occ.data();
+	return G;
+}
+
+template <int MODE> static u64 brute(const float* p, const std::vector<float>& Q, float sentinel)
+{
+	const int m = (int)Q.size() / 3;
+	float best = sentinel; int bj = -1;
+	for (int j = 0; j < m; j++) {
+		float d = gt_chain(p[0], p[1], p[2], Q[3 * j], Q[3 * j + 1], Q[3 * j + 2]);
+		if (MODE == ICPB_DIST_SQRT) d = sqrtf(d);
+		if (d < best) { best = d; bj = j; }
+	}
+	if (bj < 0) return KEY_UNMATCHED;
+	unsigned db; memcpy(&db, &best, 4);
+	return ((u64)db << 32) | (u64)(unsigned)bj;
+}
+
+static float sqrt_domain_threshold(float sentinel)
+{
+	float y = sentinel * sentinel;
+	if (std::isinf(y)) return y;
+	while (sqrtf(y) < sentinel) y = nextafterf(y, INFINITY);
+	while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
+	return y;
+}
+
+static int failures = 0;
+template <int MODE> static void check(const char* name, const std::vector<float>& P, const std::vector<float>& Q, float sentinel, bool warm)
+{
+	HostGrid G = build(Q);
+	const int n = (int)P.size() / 3;
+	const float thr0 = MODE == ICPB_DIST_SQRT ? sqrt_domain_threshold(sentinel) : sentinel;
+	unsigned long long seen = 0, nodes = 0; int bad = 0;
+	for (int i = 0; i < n; i++) {
+		const u64 want = brute<MODE>(&P[3 * i], Q, sentinel);
+		u64 start = KEY_UNMATCHED;
+		if (warm) {                                   // warm start from an arbitrary real candidate (index i mod m)
+			const int j = i % (int)(Q.size() / 3);
+			float d = gt_chain(P[3 * i], P[3 * i + 1], P[3 * i + 2], Q[3 * j], Q[3 * j + 1], Q[3 * j + 2]);
+			if (d < thr0) { if (MODE == ICPB_DIST_SQRT) d = sqrtf(d); unsigned db; memcpy(&db, &d, 4); start = ((u64)db << 32) | (u64)(unsigned)j; }
+		}
+		const u64 got = grid_tree_nn<MODE>(P[3 * i], P[3 * i + 1], P[3 * i + 2], G.g, G.py, G.cell_start.data(), G.sorted4.data(), thr0, start, &seen, &nodes);
+		if (got != want) { if (bad < 3) printf("  MISMATCH %s source %d: got %016llx want %016llx\n", name, i, (unsigned long long)got, (unsigned long long)want); bad++; }
+	}
+	printf("%-44s mode %d %s  grid %dx%dx%d levels %d  %6.1f points + %6.1f nodes per source (of %zu points)  %s\n", name, MODE, warm ? "warm" : "cold",
+	       G.g.nx, G.g.ny, G.g.nz, G.py.levels, (double)seen / n, (double)nodes / n, Q.size() / 3, bad ? "FAIL" : "ok");
+	failures += bad;
+}
+
+static void saddle(int W, std::vector<float>& D, std::vector<float>& M)
+{
+	D.resize(3 * (size_t)W * W); M.resize(D.size());
+	const float r[9] = { 0.9788f, 0.0089f, 0.2045f, -0.0490f, 0.9800f, 0.1922f, -0.1987f, -0.1980f, 0.9599f };   // ~ the reference pose
+	for (int i = 0; i < W * W; i++) {
+		const float x = -2.0f + 4.0f * (float)(i / W) / (float)(W - 1), y = -2.0f + 4.0f * (float)(i % W) / (float)(W - 1), z = x * x - y * y;
+		D[3 * i] = x; D[3 * i + 1] = y; D[3 * i + 2] = z;
+		for (int k = 0; k < 3; k++) M[3 * i + k] = r[k] * x + r[k + 3] * y + r[k + 6] * z + (k == 0 ? 0.8f : k == 1 ? -0.3f : 0.2f);
+	}
+}
+
+int main(int argc, char** argv)
+{
+	std::mt19937 rng(5);
+	std::vector<float> D, M;
+	if (argc > 1 && !strcmp(argv[1], "big")) {       // the bench size: 1M targets, a sample of sources at the initial pose and near convergence
+		saddle(1000, D, M);
+		std::vector<float> far, nearp;
+		for (int i = 0; i < 1000000; i += 997) { for (int k = 0; k < 3; k++) { far.push_back(D[3 * i + k]); nearp.push_back(M[3 * i + k] + (k == 2 ? 2e-3f : 0.0f)); } }
+		check<0>("1M saddle, initial pose (far field)", far, M, 100000.0f, false);
+		check<0>("1M saddle, 2e-3 off the surface", nearp, M, 100000.0f, false);
+		return failures ? 1 : 0;
+	}
+	saddle(120, D, M);
+	std::vector<float> Dsub(D.begin(), D.begin() + 3 * 3000);
+	for (int warm = 0; warm < 2; warm++) {
+		check<0>("saddle, initial pose (far field)", Dsub, M, 100000.0f, warm);
+		check<1>("saddle, initial pose (far field)", Dsub, M, 100000.0f, warm);
+	}
+	// near field: the source is the target itself, perturbed by a few ulps and by 1e-3
+	std::vector<float> Pn(M.begin(), M.begin() + 3 * 3000);
+	for (size_t k = 0; k < Pn.size(); k++) Pn[k] = (k % 3 == 0) ? nextafterf(Pn[k], INFINITY) : Pn[k] + ((k % 7 == 0) ? 1e-3f : 0.0f);
+	check<0>("saddle, converged (near field)", Pn, M, 100000.0f, false);
+	check<1>("saddle, converged (near field)", Pn, M, 100000.0f, true);
+	// lattice: massive ties and duplicates, outliers far outside the box
+	std::uniform_int_distribution<int> li(-10, 10), lp(-20, 20);
+	std::vector<float> Q(3 * 6000), P(3 * 2000);
+	for (auto& v : Q) v = 0.25f * (float)li(rng);
+	for (auto& v : P) v = 0.125f * (float)lp(rng);
+	for (int i = 0; i < 40; i++) for (int k = 0; k < 3; k++) P[3 * i + k] += 40.0f;
+	for (int i = 40; i < 50; i++) for (int k = 0; k < 3; k++) P[3 * i + k] -= 1e3f;
+	for (int warm = 0; warm < 2; warm++) { check<0>("lattice with ties, duplicates, outliers", P, Q, 100000.0f, warm); check<1>("lattice with ties, duplicates, outliers", P, Q, 100000.0f, warm); }
+	// sentinel rule
+	std::normal_distribution<float> nd(0.f, 1.f);
+	std::vector<float> Qn(3 * 2000), Pw(3 * 600);
+	for (auto& v : Qn) v = nd(rng);
+	for (auto& v : Pw) v = 3.0f * nd(rng);
+	check<0>("random cloud, sentinel 0.05", Pw, Qn, 0.05f, false);
+	check<1>("random cloud, sentinel 0.05", Pw, Qn, 0.05f, true);
+	check<0>("random cloud", Pw, Qn, 100000.0f, true);
+	// degenerate boxes
+	std::vector<float> line(3 * 300, 0.f), pl;
+	for (int j = 0; j < 300; j++) line[3 * j] = (float)j / 299.0f;
+	for (int j = 0; j < 300; j += 7) { pl.push_back(line[3 * j] + 0.001f); pl.push_back(0.001f); pl.push_back(0.001f); }
+	check<0>("collinear target", pl, line, 100000.0f, false);
+	std::vector<float> one = { 1.f, 2.f, 3.f }, two = { 0.f, 0.f, 0.f, 5.f, 5.f, 5.f };
+	check<0>("single target point", two, one, 100000.0f, false);
+	// large offsets and scales
+	std::vector<float> Qo(Qn), Po(Pw);
+	for (auto& v : Qo) v = v * 30.0f - 5e4f;
+	for (auto& v : Po) v = v * 30.0f - 5e4f;
+	check<0>("offset -5e4, scale 30", Po, Qo, 3e38f, false);
+	check<1>("offset -5e4, scale 30", Po, Qo, 3e38f, true);
+	// non-finite sources
+	std::vector<float> Pbad(Pw.begin(), Pw.begin() + 30); Pbad[0] = NAN; Pbad[4] = INFINITY; Pbad[8] = -INFINITY;
+	check<0>("NaN / inf sources", Pbad, Qn, 100000.0f, false);
+	printf(failures ? "FAILED: %d mismatches\n" : "all exact\n", failures);
+	return failures ? 1 : 0;
+}
