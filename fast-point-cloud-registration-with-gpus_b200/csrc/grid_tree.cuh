@@ -8,8 +8,10 @@
 //
 // Exactness (same contract as every matching kernel: argmin of the reference's float chain, lowest index on ties,
 // nothing at or above the sentinel): a node is skipped only if  lb * 0.998 > bound,  where lb is the squared distance
-// from the source to the node's box SHRUNK-proofed by `slack` per axis (covers the rounding of the cell assignment
-// floor((v - o) * inv_h) and of the box corners, both <= a few ulps of the largest coordinate), 0.998 covers the
+// from the source to the node's box reduced by `slack` per axis (covers the rounding of the cell assignment
+// floor((v - o) * inv_h) and of the box corners; both are evaluated in the grid's own frame, coordinates minus the grid
+// origin, so they are relative to the grid's extent and a cloud far from the origin prunes as well as a centred one),
+// 0.998 covers the
 // rounding of the float chain (relative 3 * 2^-24) and of lb itself, and `bound` is the squared-domain value of the
 // best key so far widened to its whole sqrt class in sqrt mode. Equality never prunes, so an equally distant target
 // with a lower index is still found. Candidates are compared as (distance bits << 32 | index) keys, independent of the
@@ -53,8 +55,10 @@ inline long long pyramid_layout(const GridGeom& g, GridPyramid& py)
 		nx = (nx + 1) >> 1; ny = (ny + 1) >> 1; nz = (nz + 1) >> 1; L++;
 	}
 	py.levels = L + 1;
-	const float ex = fmaxf(fabsf(g.ox), fabsf(g.ox + g.nx * g.h)), ey = fmaxf(fabsf(g.oy), fabsf(g.oy + g.ny * g.h)), ez = fmaxf(fabsf(g.oz), fabsf(g.oz + g.nz * g.h));
-	py.slack = 4e-6f * (fmaxf(ex, fmaxf(ey, ez)) + g.h);
+	// box distances are evaluated in the grid's own frame (coordinates minus the grid origin, as the cell assignment
+	// is), so every rounding involved is relative to the grid's EXTENT, not to how far the cloud is from the origin
+	const float ext = fmaxf((float)g.nx, fmaxf((float)g.ny, (float)g.nz)) * g.h;
+	py.slack = 4e-6f * (ext + g.h);
 	return total;
 }
 
@@ -96,9 +100,10 @@ template <int MODE> __host__ __device__ __forceinline__ float gt_bound(u64 best)
 	return t + t * 2e-6f + 1e-37f;                      // every square whose sqrt.rn equals f, and then some
 }
 
-__host__ __device__ __forceinline__ float gt_box_lb(float x, float y, float z, const GridGeom& g, float w, int cx, int cy, int cz, float slack)
+// (x, y, z): the source in the grid's frame, i.e. minus the grid origin
+__host__ __device__ __forceinline__ float gt_box_lb(float x, float y, float z, float w, int cx, int cy, int cz, float slack)
 {
-	const float lx = g.ox + (float)cx * w, ly = g.oy + (float)cy * w, lz = g.oz + (float)cz * w;
+	const float lx = (float)cx * w, ly = (float)cy * w, lz = (float)cz * w;
 	float dx = fmaxf(fmaxf(lx - x, x - (lx + w)), 0.0f), dy = fmaxf(fmaxf(ly - y, y - (ly + w)), 0.0f), dz = fmaxf(fmaxf(lz - z, z - (lz + w)), 0.0f);
 	dx = fmaxf(dx - slack, 0.0f); dy = fmaxf(dy - slack, 0.0f); dz = fmaxf(dz - slack, 0.0f);
 	return (dz * dz + dx * dx + dy * dy) * 0.998f;
@@ -112,6 +117,7 @@ __host__ __device__ inline u64 grid_tree_nn(float x, float y, float z, const Gri
                                             unsigned long long* nodes = nullptr)
 {
 	if (!(x == x) || !(y == y) || !(z == z)) return best;           // NaN source: no distance compares below anything
+	const float xr = x - g.ox, yr = y - g.oy, zr = z - g.oz;        // the grid's frame (exact, or rounded relative to the distance)
 	u64 stack[GP_STACK];
 	int sp = 0;
 	stack[sp++] = (u64)(py.levels - 1) << 54;                       // root: level | cx << 36 | cy << 18 | cz
@@ -122,7 +128,7 @@ __host__ __device__ inline u64 grid_tree_nn(float x, float y, float z, const Gri
 		visited++;
 		const int L = (int)(node >> 54), cx = (int)((node >> 36) & 0x3ffff), cy = (int)((node >> 18) & 0x3ffff), cz = (int)(node & 0x3ffff);
 		const float w = g.h * (float)(1 << L);
-		const float lb = gt_box_lb(x, y, z, g, w, cx, cy, cz, py.slack);
+		const float lb = gt_box_lb(xr, yr, zr, w, cx, cy, cz, py.slack);
 		if (lb > bound || lb >= thr0) continue;
 		if (L == 0) {
 			const int c = cx + g.nx * (cy + g.ny * cz);
@@ -148,8 +154,8 @@ __host__ __device__ inline u64 grid_tree_nn(float x, float y, float z, const Gri
 		// children at level L-1, the octant nearest to the source pushed last (popped first)
 		const int Lc = L - 1;
 		const float wc = g.h * (float)(1 << Lc);
-		const float mx = g.ox + (float)(2 * cx + 1) * wc, my = g.oy + (float)(2 * cy + 1) * wc, mz = g.oz + (float)(2 * cz + 1) * wc;
-		const int nearo = (x >= mx ? 1 : 0) | (y >= my ? 2 : 0) | (z >= mz ? 4 : 0);
+		const float mx = (float)(2 * cx + 1) * wc, my = (float)(2 * cy + 1) * wc, mz = (float)(2 * cz + 1) * wc;
+		const int nearo = (xr >= mx ? 1 : 0) | (yr >= my ? 2 : 0) | (zr >= mz ? 4 : 0);
 		const int nxc = py.nx[Lc], nyc = py.ny[Lc], nzc = py.nz[Lc];
 		const unsigned char* occ = py.occ + py.off[Lc];
 		for (int i = 7; i >= 0; i--) {
@@ -157,7 +163,7 @@ __host__ __device__ inline u64 grid_tree_nn(float x, float y, float z, const Gri
 			const int ccx = 2 * cx + (o & 1), ccy = 2 * cy + ((o >> 1) & 1), ccz = 2 * cz + ((o >> 2) & 1);
 			if (ccx >= nxc || ccy >= nyc || ccz >= nzc) continue;
 			if (!occ[(long long)ccx + (long long)nxc * ((long long)ccy + (long long)nyc * ccz)]) continue;
-			const float clb = gt_box_lb(x, y, z, g, wc, ccx, ccy, ccz, py.slack);
+			const float clb = gt_box_lb(xr, yr, zr, wc, ccx, ccy, ccz, py.slack);
 			if (clb > bound || clb >= thr0) continue;
 			stack[sp++] = ((u64)Lc << 54) | ((u64)ccx << 36) | ((u64)ccy << 18) | (u64)ccz;
 		}

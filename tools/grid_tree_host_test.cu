@@ -170,6 +170,20 @@ int main(int argc, char** argv)
 	for (auto& v : Po) v = v * 30.0f - 5e4f;
 	check<0>("offset -5e4, scale 30", Po, Qo, 3e38f, false);
 	check<1>("offset -5e4, scale 30", Po, Qo, 3e38f, true);
+	// a cloud a million units from the origin with unit spread (world / UTM coordinates): ulp(1e6) = 0.06 > the cell size
+	std::vector<float> Qu(Qn), Pu(Pw);
+	for (size_t k = 0; k < Qu.size(); k++) Qu[k] = Qu[k] + (k % 3 == 0 ? 1e6f : k % 3 == 1 ? -2.5e5f : 3e3f);
+	for (size_t k = 0; k < Pu.size(); k++) Pu[k] = Pu[k] + (k % 3 == 0 ? 1e6f : k % 3 == 1 ? -2.5e5f : 3e3f);
+	check<0>("unit cloud at (1e6,-2.5e5,3e3)", Pu, Qu, 3e38f, false);
+	check<1>("unit cloud at (1e6,-2.5e5,3e3)", Pu, Qu, 3e38f, true);
+	// sources exactly on cell faces and corners of the grid's frame
+	{
+		HostGrid G = build(Qn);
+		std::vector<float> Pf;
+		for (int i = 0; i < 400; i++) { Pf.push_back(G.g.ox + (float)(i % 17) * G.g.h); Pf.push_back(G.g.oy + (float)((i / 3) % 15) * G.g.h); Pf.push_back(G.g.oz + (float)((i / 7) % 18) * G.g.h); }
+		check<0>("sources on cell faces / corners", Pf, Qn, 100000.0f, false);
+		check<1>("sources on cell faces / corners", Pf, Qn, 100000.0f, true);
+	}
 	// non-finite sources
 	std::vector<float> Pbad(Pw.begin(), Pw.begin() + 30); Pbad[0] = NAN; Pbad[4] = INFINITY; Pbad[8] = -INFINITY;
 	check<0>("NaN / inf sources", Pbad, Qn, 100000.0f, false);
