@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-ref-binary", action="store_true")
+    ap.add_argument("--skip-grid", action="store_true", help="do not run the extra whole-registration measurement with the exact grid variant (N=1)")
     ap.add_argument("--balance", type=int, default=0, help="N > 1: 1 = deal source blocks in proportion to each GPU's measured matching rate (two extra untimed steps); 0 = even deal (B200s of one box measured within +-1.2 %, so this is off by default)")
     ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
                     help="how the source is dealt to the ranks (N > 1): blocks of 2048 points round-robin, or contiguous ranges")
@@ -329,6 +330,22 @@ def main():
     achieved = allmax(-achieved) * -1.0 if world > 1 else achieved      # the slowest rank's figure
 
     fcfg = ctx.filter_config()
+    # Extra, outside every timed region and never allowed to disturb the contract line: the same registration from its
+    # initial pose to convergence with the exact uniform-grid variant (ICPB_NN_GRID: occupancy pyramid over the cells,
+    # identical correspondences), device time from the engine's events. One GPU only.
+    grid_extra = None
+    if world == 1 and not args.skip_grid:
+        try:
+            ctx.set_source(shard)
+            ctx.run(ib.default_params(max_iter=64, nn_method=ib.NN_GRID))        # builds the grid, warms up
+            ctx.set_source(shard)
+            g_err, g_res = ctx.run(ib.default_params(max_iter=64, nn_method=ib.NN_GRID))
+            grid_extra = {"what": "whole registration of the same clouds with the exact uniform-grid variant (ICPB_NN_GRID), initial pose to convergence",
+                          "iterations_run": int(g_res.iterations_run), "elapsed_ms": float(g_res.elapsed_ms),
+                          "icp_iters_per_sec": float(g_res.iterations_run) / (float(g_res.elapsed_ms) * 1e-3),
+                          "final_rms": float(g_err[g_res.iterations + 1])}
+        except Exception as exc:      # noqa: BLE001
+            grid_extra = {"error": str(exc)[:200]}
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
@@ -347,6 +364,7 @@ def main():
                            else ("combined with ncclAllReduce" if world > 1 else "(single GPU: no exchange)")),
                        "l2": "256 MiB device write between timed steps (untimed); timing = CUDA events per step on the engine stream"},
             "icp_iters_per_sec": args.steps / (total_ms * 1e-3),
+            "exact_grid_registration": grid_extra,
             "match_ms_per_step": match_total_ms / args.steps,
             "match_ms_per_step_fastest_rank": match_fastest_rank_ms / args.steps,
             "rank_balance": ({"weights": [w / (sum(balance_weights) / world) for w in balance_weights],
