@@ -109,6 +109,7 @@ int  launch_key_reset(Ctx* c);
 int  launch_resolve(Ctx* c, float sentinel);
 int  launch_match(Ctx* c, int dist_mode, int nn_method, float sentinel);
 int  launch_match_grid(Ctx* c, int dist_mode, float sentinel);
+int  launch_knn_tree(Ctx* c, int k1, int knn_dist_mode, int* nbr);   // K5 through the grid's occupancy pyramid (grid_nn.cu)
 int  launch_match_filter(Ctx* c, int dist_mode, float sentinel);
 int  kf_policy_update(Ctx* c);
 int  prepare_match_filter(Ctx* c);
@@ -166,6 +167,8 @@ struct Ctx {
 	unsigned long long* grid_counters = nullptr;   // [0] open sources of the last pass, [1] candidates visited
 	bool    grid_pyramid = true;        // best-first descent of an occupancy pyramid (grid_tree.cuh); ICPB_GRID_PYRAMID=0: rings + brute-force fallback
 	unsigned char* grid_occ = nullptr;  // pyramid occupancy bytes, all levels
+	bool    knn_pyramid = false;        // ICPB_KNN_PYRAMID=1: neighbour lists through the pyramid instead of the tiled scan (host-verified
+	                                    // traversal, tools/grid_tree_host_test.cu; off until it has been timed and checked on a GPU)
 	GridPyramid grid_py = {};           // level dimensions / offsets (host copy; `occ` points at grid_occ)
 
 	// source (this rank's shard)

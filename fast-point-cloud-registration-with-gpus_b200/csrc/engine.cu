@@ -160,6 +160,7 @@ static int create_common(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
 	if (const char* e = getenv("ICPB_GRID_PYRAMID")) c->grid_pyramid = atoi(e) != 0;
+	if (const char* e = getenv("ICPB_KNN_PYRAMID")) c->knn_pyramid = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_GSS")) { int a = 0, b = 0, d = 0; if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b >= a && d > 0) { c->kf_gss[0] = a; c->kf_gss[1] = b; c->kf_gss[2] = d; } }
 	if (const char* e = getenv("ICPB_KF_DIMS")) c->kf_dims_forced = atoi(e);
 	if (const char* e = getenv("ICPB_KF_S")) c->kf_s = (atoi(e) == 16) ? 16 : 8;

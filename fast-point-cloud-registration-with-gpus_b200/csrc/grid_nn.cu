@@ -303,6 +303,35 @@ static int build_grid(Ctx* c)
 	return ICPB_OK;
 }
 
+// K5 through the pyramid (ICPB_KNN_PYRAMID=1): one thread per target point, k+1 nearest targets by best-first descent.
+template <int MODE>
+__global__ void __launch_bounds__(128) knn_tree_kernel(const float4* __restrict__ q4, int m, int k1, const float4* __restrict__ sorted4,
+                                                       const int* __restrict__ cell_start, GridGeom g, const GridPyramid pyr, int* __restrict__ nbr)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	const float4 me = q4[i];
+	float kd[GT_KMAX]; int ki[GT_KMAX];
+	grid_tree_knn<MODE>(me.x, me.y, me.z, k1, g, pyr, cell_start, sorted4, kd, ki);
+	for (int p = 0; p < k1; p++) nbr[(size_t)i * k1 + p] = ki[p] >= 0 ? ki[p] : 0;      // `minimum` returns 0 when nothing is below 10000
+}
+
+int launch_knn_tree(Ctx* c, int k1, int knn_dist_mode, int* nbr)
+{
+	if (k1 < 1 || k1 > GT_KMAX || !c->grid_pyramid) return ICPB_ERR_BADARG;
+	int rc;
+	if (!c->grid_ready) { if ((rc = build_grid(c)) != ICPB_OK) return rc; }
+	GridGeom g;
+	g.h = c->grid_cell; g.inv_h = (float)(1.0 / (double)c->grid_cell);
+	g.ox = c->grid_origin[0]; g.oy = c->grid_origin[1]; g.oz = c->grid_origin[2];
+	g.nx = c->grid_dim[0]; g.ny = c->grid_dim[1]; g.nz = c->grid_dim[2];
+	auto kern = (knn_dist_mode == ICPB_DIST_SQRT) ? knn_tree_kernel<ICPB_DIST_SQRT> : knn_tree_kernel<ICPB_DIST_SQ>;
+	kern<<<(c->m + 127) / 128, 128, 0, c->stream>>>(c->q4, c->m, k1, c->grid_sorted4, c->grid_cell_start, g, c->grid_py, nbr);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+
 int launch_match_grid(Ctx* c, int dist_mode, float sentinel)
 {
 	if (dist_mode == ICPB_DIST_STD) { snprintf(c->err, sizeof c->err, "ICPB_NN_GRID supports ICPB_DIST_SQ and ICPB_DIST_SQRT"); return ICPB_ERR_BADARG; }

@@ -173,4 +173,78 @@ __host__ __device__ inline u64 grid_tree_nn(float x, float y, float z, const Gri
 	return best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// k nearest neighbours by the same descent (K5: the neighbour lists PCA normals are estimated from).
+// Contract of the reference's knn + minimum (src/ICP_point_to_plane.cu:30-70): the K1 smallest entries under the
+// order (distance, index) — distance = sqrt.rn of the chain in SQRT mode, the chain itself in SQ mode — among the
+// entries below 10000.0; the query point itself (distance 0) is an ordinary entry. `kd/ki` come back sorted; slots that
+// found nothing hold ki = -1. The pruning bound is the K1-th best key so far (its whole sqrt class in SQRT mode);
+// equality never prunes, so equally distant targets with lower indices are still found.
+// ------------------------------------------------------------------------------------------------
+constexpr int GT_KMAX = 8;
+
+template <int MODE>
+__host__ __device__ inline void grid_tree_knn(float x, float y, float z, int k1, const GridGeom& g, const GridPyramid& py, const int* __restrict__ cell_start,
+                                              const float4* __restrict__ sorted4, float kd[GT_KMAX], int ki[GT_KMAX])
+{
+	for (int p = 0; p < GT_KMAX; p++) { kd[p] = INFINITY; ki[p] = -1; }
+	if (!(x == x) || !(y == y) || !(z == z)) return;
+	const float limit = 10000.0f;                                    // `minimum` starts from 10000.0 and uses strict `<`
+	const float thr0 = (MODE == ICPB_DIST_SQRT) ? 1.0e8f : limit;    // squared-domain cut: sqrt(d) < 1e4  <=>  d < 1e8 (1e8 is a perfect square of a float)
+	const float xr = x - g.ox, yr = y - g.oy, zr = z - g.oz;
+	u64 stack[GP_STACK];
+	int sp = 0;
+	stack[sp++] = (u64)(py.levels - 1) << 54;
+	float bound = INFINITY;                                          // squared-domain bound of the K1-th best so far
+	while (sp > 0) {
+		const u64 node = stack[--sp];
+		const int L = (int)(node >> 54), cx = (int)((node >> 36) & 0x3ffff), cy = (int)((node >> 18) & 0x3ffff), cz = (int)(node & 0x3ffff);
+		const float w = g.h * (float)(1 << L);
+		const float lb = gt_box_lb(xr, yr, zr, w, cx, cy, cz, py.slack);
+		if (lb > bound || lb >= thr0) continue;
+		if (L == 0) {
+			const int c = cx + g.nx * (cy + g.ny * cz);
+			const int k0 = cell_start[c], k1e = cell_start[c + 1];
+			for (int k = k0; k < k1e; k++) {
+				const float4 q = sorted4[k];
+				float d = gt_chain(x, y, z, q.x, q.y, q.z);
+				if (MODE == ICPB_DIST_SQRT) d = gt_sqrt(d);
+				if (!(d < limit)) continue;
+				int idx;
+#ifdef __CUDA_ARCH__
+				idx = __float_as_int(q.w);
+#else
+				memcpy(&idx, &q.w, 4);
+#endif
+				// insert (d, idx) if it beats the current K1-th entry
+				const int last = k1 - 1;
+				if (ki[last] >= 0 && !(d < kd[last] || (d == kd[last] && idx < ki[last]))) continue;
+				int pos = last;
+				while (pos > 0 && (ki[pos - 1] < 0 || d < kd[pos - 1] || (d == kd[pos - 1] && idx < ki[pos - 1]))) { kd[pos] = kd[pos - 1]; ki[pos] = ki[pos - 1]; pos--; }
+				kd[pos] = d; ki[pos] = idx;
+				if (ki[last] >= 0) {
+					const float f = kd[last];
+					if (MODE == ICPB_DIST_SQRT) { const float t = f * f; bound = t + t * 2e-6f + 1e-37f; } else bound = f;
+				}
+			}
+			continue;
+		}
+		const int Lc = L - 1;
+		const float wc = g.h * (float)(1 << Lc);
+		const float mx = (float)(2 * cx + 1) * wc, my = (float)(2 * cy + 1) * wc, mz = (float)(2 * cz + 1) * wc;
+		const int nearo = (xr >= mx ? 1 : 0) | (yr >= my ? 2 : 0) | (zr >= mz ? 4 : 0);
+		const int nxc = py.nx[Lc], nyc = py.ny[Lc], nzc = py.nz[Lc];
+		const unsigned char* occ = py.occ + py.off[Lc];
+		for (int i = 7; i >= 0; i--) {
+			const int o = i ^ nearo;
+			const int ccx = 2 * cx + (o & 1), ccy = 2 * cy + ((o >> 1) & 1), ccz = 2 * cz + ((o >> 2) & 1);
+			if (ccx >= nxc || ccy >= nyc || ccz >= nzc) continue;
+			if (!occ[(long long)ccx + (long long)nxc * ((long long)ccy + (long long)nyc * ccz)]) continue;
+			const float clb = gt_box_lb(xr, yr, zr, wc, ccx, ccy, ccz, py.slack);
+			if (clb > bound || clb >= thr0) continue;
+			stack[sp++] = ((u64)Lc << 54) | ((u64)ccx << 36) | ((u64)ccy << 18) | (u64)ccz;
+		}
+	}
+}
+
 } // namespace icpb

@@ -282,7 +282,10 @@ int icpb_estimate_normals_ex(icpb_ctx* ctx, int k, int knn_dist_mode, float* ela
 	if ((rc = kn_stage(c, sizeof(int) * (size_t)c->m)) != ICPB_OK) return rc;
 	int* flags = reinterpret_cast<int*>(c->stage_xyz);
 	ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-	if (knn_dist_mode == ICPB_DIST_SQRT) {
+	if (c->knn_pyramid && c->grid_pyramid) {
+		if ((rc = launch_knn_tree(c, k1, knn_dist_mode, c->nbr)) != ICPB_OK) return rc;
+		c->launches--;                      // counted by the launcher; the common increment below stays
+	} else if (knn_dist_mode == ICPB_DIST_SQRT) {
 		knn_kernel<true><<<(c->m + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, c->stream>>>(c->qtiles, c->q4, c->m, c->nt, k1, c->nbr, flags);
 		c->launches++;
 		ICPB_CUDA(c, cudaGetLastError());

@@ -149,3 +149,36 @@ def test_100k_point_to_plane_properties(ctx, ib, orc):
     assert np.array_equal(ctx.correspondences(), np.arange(100000))
     assert np.abs(np.array(res.R[:]) - orc.euler_matrix([0.2, -0.2, 0.05])).max() < 2e-5
     assert np.abs(np.array(res.t[:]) - [0.8, -0.3, 0.2]).max() < 2e-5
+
+
+def test_knn_through_the_pyramid_equals_the_tiled_scan(ib, orc, golden_dir):
+    """ICPB_KNN_PYRAMID=1: K5's neighbour lists by best-first descent of the grid's occupancy pyramid — same lists as the
+    default kernels, the reference knn kernel's golden output and the oracle, in both ranking modes, on ties / ragged
+    sizes / the sqrt-merge case / clouds spread beyond the 10000 cut-off."""
+    os.environ["ICPB_KNN_PYRAMID"] = "1"
+    try:
+        c = ib.Context(0)
+    finally:
+        del os.environ["ICPB_KNN_PYRAMID"]
+    try:
+        g = np.load(os.path.join(golden_dir, "ref_knn_normals.npz"))
+        for W in (32, 64):
+            c.set_target(g["Q_W%d" % W]); c.estimate_normals(4)
+            assert np.array_equal(c.neighbors(4), g["nbr_W%d" % W])
+        rng = np.random.default_rng(2)
+        for m in (5, 9, 257, 4097):
+            Q = (rng.integers(-6, 7, size=(m, 3)) * 0.5).astype(np.float32)
+            for mode, omode in ((ib.DIST_SQRT, orc.MODE_SQRT), (ib.DIST_SQ, orc.MODE_SQ)):
+                c.set_target(Q); c.estimate_normals(4, mode)
+                assert np.array_equal(c.neighbors(4), orc.knn(Q, 5, omode)), (m, mode)
+        Q = (rng.normal(size=(700, 3)) * 6000.0).astype(np.float32)
+        c.set_target(Q); c.estimate_normals(4)
+        assert np.array_equal(c.neighbors(4), orc.knn(Q, 5))
+        D, M = orc.synth_p2p(317, 100000)
+        c.set_target(M); ms = c.estimate_normals(4)
+        with ib.Context(0) as ref:
+            ref.set_target(M); ms_ref = ref.estimate_normals(4)
+            assert np.array_equal(c.neighbors(4), ref.neighbors(4))
+        print("normals at 100k points: pyramid %.3f ms, tiled scan %.3f ms" % (ms, ms_ref))
+    finally:
+        c.close()

@@ -107,6 +107,33 @@ template <int MODE> static void check(const char* name, const std::vector<float>
 	failures += bad;
 }
 
+// knn + minimum of the reference (src/ICP_point_to_plane.cu:30-70), literally: all distances, then k1 argmin passes with
+// strict `<` from 10000.0, each winner invalidated with 10000.0; "nothing found" returns index 0.
+template <int MODE> static void check_knn(const char* name, const std::vector<float>& Q, int k1)
+{
+	HostGrid G = build(Q);
+	const int m = (int)Q.size() / 3;
+	int bad = 0;
+	std::vector<float> d(m);
+	for (int i = 0; i < m; i++) {
+		for (int j = 0; j < m; j++) { float v = gt_chain(Q[3 * i], Q[3 * i + 1], Q[3 * i + 2], Q[3 * j], Q[3 * j + 1], Q[3 * j + 2]); d[j] = MODE == ICPB_DIST_SQRT ? sqrtf(v) : v; }
+		int want[GT_KMAX];
+		for (int r = 0; r < k1; r++) {
+			float mn = 10000.0f; int b = 0;
+			for (int j = 0; j < m; j++) if (d[j] < mn) { mn = d[j]; b = j; }
+			want[r] = b; d[b] = 10000.0f;
+		}
+		float kd[GT_KMAX]; int ki[GT_KMAX];
+		grid_tree_knn<MODE>(Q[3 * i], Q[3 * i + 1], Q[3 * i + 2], k1, G.g, G.py, G.cell_start.data(), G.sorted4.data(), kd, ki);
+		for (int r = 0; r < k1; r++) {
+			const int got = ki[r] >= 0 ? ki[r] : 0;
+			if (got != want[r]) { if (bad < 3) printf("  KNN MISMATCH %s query %d rank %d: got %d want %d\n", name, i, r, got, want[r]); bad++; break; }
+		}
+	}
+	printf("%-44s mode %d k+1=%d  grid %dx%dx%d  %d queries  %s\n", name, MODE, k1, G.g.nx, G.g.ny, G.g.nz, m, bad ? "FAIL" : "ok");
+	failures += bad;
+}
+
 static void saddle(int W, std::vector<float>& D, std::vector<float>& M)
 {
 	D.resize(3 * (size_t)W * W); M.resize(D.size());
@@ -187,6 +214,29 @@ int main(int argc, char** argv)
 	// non-finite sources
 	std::vector<float> Pbad(Pw.begin(), Pw.begin() + 30); Pbad[0] = NAN; Pbad[4] = INFINITY; Pbad[8] = -INFINITY;
 	check<0>("NaN / inf sources", Pbad, Qn, 100000.0f, false);
+	// ---- k nearest neighbours (K5) ----
+	{
+		std::vector<float> Dk, Mk;
+		saddle(48, Dk, Mk);
+		check_knn<1>("knn: saddle target", Mk, 5);
+		check_knn<0>("knn: saddle target", Mk, 5);
+		check_knn<1>("knn: lattice with duplicates", std::vector<float>(Q.begin(), Q.begin() + 3 * 2500), 5);
+		check_knn<0>("knn: lattice with duplicates", std::vector<float>(Q.begin(), Q.begin() + 3 * 2500), 7);
+		check_knn<1>("knn: random cloud", Qn, 5);
+		check_knn<1>("knn: collinear", line, 5);
+		std::vector<float> tiny(Qn.begin(), Qn.begin() + 9);
+		check_knn<1>("knn: 3 points, k+1 = 5", tiny, 5);
+		std::vector<float> wide(Qn.begin(), Qn.begin() + 3 * 400);
+		for (auto& v : wide) v *= 6000.0f;                                    // most pairs farther than 10000: the cut-off matters
+		check_knn<1>("knn: spread beyond the 10000 cut-off", wide, 5);
+		check_knn<0>("knn: spread beyond the 10000 cut-off", wide, 5);
+		check_knn<1>("knn: unit cloud at 1e6", std::vector<float>(Qu.begin(), Qu.begin() + 3 * 1200), 5);
+		// sqrt merging: a ring of points whose squared distances to the centre differ by ulps
+		std::vector<float> ring = { 0.f, 0.f, 0.f };
+		const float e = sqrtf(nextafterf(1.0f, 2.0f) - 1.0f);
+		for (int k = 0; k < 12; k++) { const float a = 6.2831853f * (float)k / 12.0f; ring.push_back(cosf(a)); ring.push_back(sinf(a)); ring.push_back((k % 2) ? e : 0.0f); }
+		check_knn<1>("knn: sqrt-merged ring", ring, 5);
+	}
 	printf(failures ? "FAILED: %d mismatches\n" : "all exact\n", failures);
 	return failures ? 1 : 0;
 }
