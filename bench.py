@@ -122,6 +122,9 @@ def run_reference_arm(args, rank, emit):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     import icp_synth
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm would then be timed on ONE thread (r1: SCALE ratios at
+    # N > 1 were against a single-threaded baseline). Use every processor OpenMP sees, and record the count in effect.
+    cores = orc.set_num_threads(0)
     D, M = icp_synth.p2p_clouds(args.width)
     n = D.shape[0]
     # each step = one bounded sample: S sources x all targets, S sized for ~3 s of CPU work
@@ -141,6 +144,8 @@ def run_reference_arm(args, rank, emit):
     pairs = float(S) * M.shape[0] * args.steps
     value = pairs / dt
     cores = orc.num_threads()
+    if cores == 1 and (os.cpu_count() or 1) > 1:
+        sys.stderr.write("bench.py: WARNING: the CPU arm ran on 1 thread of %d processors\n" % os.cpu_count())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -247,9 +252,11 @@ def main():
     n_total, m = D.shape[0], M.shape[0]
     if args.shard == "contiguous":
         lo, hi = icp_dist.shard_bounds(n_total, rank, world)
+        shard_index = np.arange(lo, hi, dtype=np.int64)
         shard = np.ascontiguousarray(D[lo:hi])
     else:                                   # blocks of 2048 sources dealt round-robin: balances the ranks' matching cost
-        shard = np.ascontiguousarray(D[icp_dist.shard_indices(n_total, rank, world)])
+        shard_index = icp_dist.shard_indices(n_total, rank, world)
+        shard = np.ascontiguousarray(D[shard_index])
     n_rank = shard.shape[0]
 
     fp32_peak = ctx.fp32_peak_tflops()
@@ -260,10 +267,13 @@ def main():
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
+    step_errs_all = []                      # RMS after every step since the last source upload (warm-up included)
+
     def one_step():
         flush_buf.fill_(1)
         torch.cuda.synchronize()
         err, res = ctx.run(ib.default_params(max_iter=1, stop_early=0))
+        step_errs_all.append(float(err[1]))
         return res
 
     # N > 1: the step ends when the slowest rank ends, and B200s of one box differ by a few per cent in sustained speed.
@@ -276,9 +286,11 @@ def main():
         speed[rank] = float(n_rank) / max(1e-6, r1.match_ms + r2.match_ms)
         dist.all_reduce(speed)
         balance_weights = [float(v) for v in speed.cpu().tolist()]
-        shard = np.ascontiguousarray(D[icp_dist.shard_indices_weighted(n_total, rank, balance_weights)])
+        shard_index = icp_dist.shard_indices_weighted(n_total, rank, balance_weights)
+        shard = np.ascontiguousarray(D[shard_index])
         n_rank = shard.shape[0]
         ctx.set_source(shard)
+        step_errs_all.clear()
     for _ in range(args.warmup):
         one_step()
     barrier()
@@ -289,10 +301,46 @@ def main():
     for _ in range(args.steps):
         res = one_step()
         step_ms.append(res.elapsed_ms); match_ms.append(res.match_ms)
+    last_res = res
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
     clocks = clocks_stop(clk_p, clk_f, t_epoch0, time.time()) if rank == 0 else None
+
+    # ---- parity carried by the bench line: the state after the W + K steps — every source point's
+    # correspondence, the last transform, the error trajectory — is checksummed, and at N > 1 rank 0 replays the same
+    # steps on ONE GPU (its own, full source) and the run FAILS unless the sharded run gave the same correspondences bit
+    # for bit and the same errors / transform to FP64 summation-order noise.
+    import zlib
+    idx_rank = ctx.correspondences()
+    step_errs = np.array(step_errs_all, dtype=np.float32)
+    parity = {"steps_checked": len(step_errs_all)}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (shard_index.astype(np.int64), idx_rank))
+        if rank == 0:
+            idx_all = np.full(n_total, -1, np.int32)
+            for sidx, sval in gathered:
+                idx_all[sidx] = sval
+            with ib.Context(local_rank) as one:
+                one.set_target(M); one.set_source(D)
+                errs1 = []
+                for _ in range(len(step_errs_all)):
+                    e1, r1 = one.run(ib.default_params(max_iter=1, stop_early=0))
+                    errs1.append(float(e1[1]))
+                idx1 = one.correspondences()
+                last_R1 = np.array(r1.last_R[:], np.float64)
+            errs1 = np.array(errs1, np.float32)
+            parity.update({"one_gpu_replay": True, "idx_equal": bool(np.array_equal(idx_all, idx1)),
+                           "max_rel_err_diff": float(np.max(np.abs(step_errs - errs1) / np.maximum(np.abs(errs1), 1e-12))),
+                           "max_R_diff": float(np.max(np.abs(np.array(last_res.last_R[:], np.float64) - last_R1))),
+                           "idx_crc32": int(zlib.crc32(idx_all.tobytes())), "idx_crc32_one_gpu": int(zlib.crc32(idx1.tobytes()))})
+            if not (parity["idx_equal"] and parity["max_rel_err_diff"] <= 1e-5 and parity["max_R_diff"] <= 1e-6):
+                raise SystemExit("bench.py: the %d-GPU run does not reproduce the 1-GPU run: %s" % (world, json.dumps(parity)))
+    else:
+        parity.update({"one_gpu_replay": False, "idx_crc32": int(zlib.crc32(idx_rank.tobytes()))})
+    parity["errors_crc32"] = int(zlib.crc32(step_errs.tobytes()))
+    parity["final_rms"] = float(step_errs[-1])
 
     total_ms = allmax(sum(step_ms))
     match_total_ms = allmax(sum(match_ms))
@@ -374,6 +422,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": "icpb_iterate_host (pinned host clouds -> idx, R, T, rms) + icpb_get_source; host-driven loop, each step uploads the previous step's transformed source", "steps": args.e2e_steps},
             "gpu_launches": launches_all,
+            "parity": parity,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
@@ -395,6 +444,7 @@ def main():
         if world == 1 and not args.skip_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle as orc
+            orc.set_num_threads(0)             # all host cores, whatever OMP_NUM_THREADS says
             rate, S, dt = cpu_match_rate(orc, D, M, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                                     "sample": "%d of %d sources x all %d targets, %.1f s, oracle orc_match_f32 (OpenMP)" % (S, n_total, m, dt)}

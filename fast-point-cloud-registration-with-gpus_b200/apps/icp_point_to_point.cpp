@@ -8,6 +8,7 @@
 // configurations of BASELINE.json; they do not exist in the reference.
 #include "synth.h"
 #include "icp_b200.h"
+#include "runner.h"
 
 int main(int argc, char** argv)
 {
@@ -19,11 +20,11 @@ int main(int argc, char** argv)
 
 	synth::Clouds c = synth::point_to_point_clouds(W, npts);
 
-	icpb_ctx* ctx = nullptr;
-	int rc = icpb_create(&ctx, 0);
+	Runner run;                                        // --gpus N (N > 1): source sharded over N GPUs of this box, one process
+	int rc = run.create(opt.gpus);
 	if (rc != ICPB_OK) { printf("Error creating the ICP context: %s\n", icpb_status_string(rc)); return -1; }
-	if ((rc = icpb_set_target(ctx, c.M.data(), npts, 0)) != ICPB_OK || (rc = icpb_set_source(ctx, c.D.data(), npts, 0)) != ICPB_OK) {
-		printf("Error uploading the clouds: %s\n", icpb_last_error(ctx));
+	if ((rc = run.set_clouds(c.M.data(), npts, c.D.data(), npts)) != ICPB_OK) {
+		printf("Error uploading the clouds: %s\n", run.last_error());
 		return -1;
 	}
 
@@ -39,8 +40,8 @@ int main(int argc, char** argv)
 	if (opt.report) p.flags |= ICPB_FLAG_PROFILE;     // per-iteration matching times for the report
 	std::vector<float> err((size_t)max_iter + 1, 0.f);
 	icpb_result res;
-	rc = icpb_run(ctx, &p, err.data(), &res);
-	if (rc != ICPB_OK) { printf("Error in the ICP loop: %s\n", icpb_last_error(ctx)); return -1; }
+	rc = run.run(&p, err.data(), &res);
+	if (rc != ICPB_OK) { printf("Error in the ICP loop: %s\n", run.last_error()); return -1; }
 
 	printf("Error:\n");
 	for (int i = 0; i < res.iterations + 1; i++) printf("%d: %.4f\n", i + 1, err[(size_t)i]);
@@ -54,7 +55,8 @@ int main(int argc, char** argv)
 		       npts, npts, res.iterations_run, res.match_ms, pairs / (res.match_ms * 1e-3), res.iterations_run / (res.elapsed_ms * 1e-3));
 		printf("[report] R (column-major): "); for (int k = 0; k < 9; k++) printf("%.7f ", res.R[k]);
 		printf("\n[report] t: %.7f %.7f %.7f\n", res.t[0], res.t[1], res.t[2]);
+		printf("[report] gpus %d (%s), %.3f ms per ICP iteration\n", run.gpus, run.exchange(), res.elapsed_ms / res.iterations_run);
 	}
-	icpb_destroy(ctx);
+	run.destroy();
 	return 0;
 }

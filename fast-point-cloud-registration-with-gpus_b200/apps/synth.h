@@ -111,7 +111,7 @@ inline bool parse(int argc, char** argv, Options& o)
 		else if ((v = val("--nn"))) o.grid_nn = (strcmp(v, "grid") == 0);
 		else if (a == "--report") o.report = 1;
 		else {
-			fprintf(stderr, "usage: %s [--width W] [--n N] [--max-iter K] [--tol T] [--nn brute|grid] [--sync-every K] [--report]\n", argv[0]);
+			fprintf(stderr, "usage: %s [--width W] [--n N] [--max-iter K] [--tol T] [--nn brute|grid] [--sync-every K] [--gpus G] [--report]\n", argv[0]);
 			return false;
 		}
 	}

@@ -11,6 +11,7 @@
 // memory traffic inside the loop except the final results. Two CTAs (16 warps) share an SM; registrations are drawn
 // from an atomic counter because their iteration counts differ (static round-robin left CTAs idle at the end).
 #include "common.cuh"
+#include <algorithm>
 #include "k1_device.cuh"
 #include "solve_device.cuh"
 #include <cstdlib>
@@ -35,7 +36,30 @@ struct BatchParams {
 	double* t;              // [batch][3]
 	int* idx;               // [batch][n] or nullptr
 	int* next;              // zeroed before the launch: CTAs draw registrations from it (their iteration counts differ)
+	// streaming upload (config 5 end to end): the clouds arrive in chunks of `chunk` registrations WHILE the kernel runs;
+	// the copy engine sets ready[c] = 1 after chunk c has landed (a 4-byte H2D copy queued behind the chunk's data on
+	// the same stream). nullptr: everything is resident before the launch.
+	const int* ready;
+	int chunk;
+	int* fail;              // set when a chunk never arrived (bounded wait instead of a hang)
 };
+
+// The drawing thread waits until registration b's chunk has landed. DMA writes by the copy engine need no SM, so a
+// kernel that occupies every SM cannot starve them (unlike a kernel waiting for another kernel).
+__device__ __forceinline__ int k9_draw(const BatchParams& p)
+{
+	const int b = atomicAdd(p.next, 1);
+	if (p.ready == nullptr || b >= p.batch) return b;
+	const int* flag = p.ready + b / p.chunk;
+	const long long t0 = clock64();
+	for (;;) {
+		int v;
+		asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		if (v != 0) return b;
+		if (clock64() - t0 > 20000000000ll) { *p.fail = 1; return p.batch; }      // ~10 s: the upload died
+		__nanosleep(200);
+	}
+}
 
 __device__ __forceinline__ double block_sum(double v, double* red /* [THREADS/32] */)
 {
@@ -68,7 +92,7 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_kernel(const BatchP
 	__shared__ int s_b;
 	while (true) {
 		__syncthreads();
-		if (tid == 0) s_b = atomicAdd(p.next, 1);
+		if (tid == 0) s_b = k9_draw(p);
 		__syncthreads();
 		const int b = s_b;
 		if (b >= p.batch) break;
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(K9_THREADS, 2) icp_batched_filter_kernel(const
 
 	while (true) {
 		__syncthreads();
-		if (tid == 0) s_b = atomicAdd(p.next, 1);
+		if (tid == 0) s_b = k9_draw(p);
 		__syncthreads();
 		const int b = s_b;
 		if (b >= p.batch) break;
@@ -538,6 +562,7 @@ static float sqrt_threshold_host(float sentinel)
 extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int batch, const float* sources, int n, const float* targets, int m,
                                 float* errors, int* iterations, double* R, double* t, float* elapsed_ms)
 {
+	ICPB_NVTX("icpb_run_batched");
 	if (!ctx) return ICPB_ERR_BADARG;
 	Ctx* c = reinterpret_cast<Ctx*>(ctx);
 	ICPB_CUDA(c, cudaSetDevice(c->device));
@@ -551,17 +576,42 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 
 	const size_t sb = sizeof(float) * 3 * (size_t)batch * n, tb = sizeof(float) * 3 * (size_t)batch * m;
 	const size_t eb = sizeof(float) * (size_t)batch * (params->max_iter + 1);
-	float *d_s = nullptr, *d_t = nullptr, *d_e = nullptr; int *d_it = nullptr, *d_run = nullptr, *d_next = nullptr; double *d_R = nullptr, *d_tt = nullptr;
-	auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_t); cudaFree(d_e); cudaFree(d_it); cudaFree(d_run); cudaFree(d_next); cudaFree(d_R); cudaFree(d_tt); };
-#define K9_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(c, e__, #call, __FILE__, __LINE__); } } while (0)
-	K9_TRY(cudaMalloc((void**)&d_s, sb)); K9_TRY(cudaMalloc((void**)&d_t, tb)); K9_TRY(cudaMalloc((void**)&d_e, eb));
-	K9_TRY(cudaMalloc((void**)&d_it, sizeof(int) * batch)); K9_TRY(cudaMalloc((void**)&d_run, sizeof(int) * batch));
-	K9_TRY(cudaMalloc((void**)&d_R, sizeof(double) * 9 * batch)); K9_TRY(cudaMalloc((void**)&d_tt, sizeof(double) * 3 * batch));
-	K9_TRY(cudaMemcpyAsync(d_s, sources, sb, cudaMemcpyHostToDevice, c->stream));
-	K9_TRY(cudaMemcpyAsync(d_t, targets, tb, cudaMemcpyHostToDevice, c->stream));
+	// Device buffers are kept in the context and only ever grow: a serving loop calls this with the same shapes over and
+	// over, and cudaMalloc/cudaFree pairs cost more than the 25 MB upload of a 512-pair batch.
+	K9Buffers& kb = c->k9;
+	auto grow = [&](void** ptr, size_t& cap, size_t need) -> cudaError_t {
+		if (need <= cap) return cudaSuccess;
+		cudaFree(*ptr); *ptr = nullptr; cap = 0;
+		const cudaError_t e = cudaMalloc(ptr, need);
+		if (e == cudaSuccess) cap = need;
+		return e;
+	};
+#define K9_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(c, e__, #call, __FILE__, __LINE__); } while (0)
+	constexpr int CHUNK = 32;                            // registrations per upload chunk (1.5 MB at 2048 points: ~60 us of PCIe)
+	const int nchunks = (batch + CHUNK - 1) / CHUNK;
+	// where do the clouds live? device pointers are used in place (the device-resident measurement), pinned host memory is
+	// streamed in chunks behind the running kernel, pageable host memory is uploaded first (its copies are staged by the CPU)
+	auto mem_type = [](const void* ptr) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return cudaMemoryTypeUnregistered; } return a.type; };
+	const cudaMemoryType ts = mem_type(sources), tt_ = mem_type(targets);
+	const bool resident = (ts == cudaMemoryTypeDevice || ts == cudaMemoryTypeManaged) && (tt_ == cudaMemoryTypeDevice || tt_ == cudaMemoryTypeManaged);
+	bool streaming = !resident && ts == cudaMemoryTypeHost && tt_ == cudaMemoryTypeHost && batch > CHUNK;
+	if (const char* e = getenv("ICPB_K9_STREAM")) if (atoi(e) == 0) streaming = false;
+	if (!resident) { K9_TRY(grow((void**)&kb.s, kb.s_cap, sb)); K9_TRY(grow((void**)&kb.t, kb.t_cap, tb)); }
+	K9_TRY(grow((void**)&kb.e, kb.e_cap, eb));
+	K9_TRY(grow((void**)&kb.ints, kb.ints_cap, sizeof(int) * ((size_t)2 * batch + 8 + (size_t)nchunks)));
+	K9_TRY(grow((void**)&kb.dbl, kb.dbl_cap, sizeof(double) * 12 * (size_t)batch));
+	if (!kb.copy_stream) { K9_TRY(cudaStreamCreateWithFlags(&kb.copy_stream, cudaStreamNonBlocking)); K9_TRY(cudaEventCreateWithFlags(&kb.ev, cudaEventDisableTiming)); }
+	if (!kb.one) { K9_TRY(cudaMallocHost((void**)&kb.one, 2 * sizeof(int))); kb.one[0] = 1; kb.one[1] = 0; }
+	const float* d_s = resident ? sources : kb.s; const float* d_t = resident ? targets : kb.t;
+	float* d_e = kb.e;
+	int* d_it = kb.ints; int* d_run = kb.ints + batch; int* d_next = kb.ints + 2 * (size_t)batch; int* d_fail = d_next + 1; int* d_ready = d_next + 8;
+	double* d_R = kb.dbl; double* d_tt = kb.dbl + 9 * (size_t)batch;
 	K9_TRY(cudaMemsetAsync(d_e, 0, eb, c->stream));
-	K9_TRY(cudaMalloc((void**)&d_next, sizeof(int)));
-	K9_TRY(cudaMemsetAsync(d_next, 0, sizeof(int), c->stream));
+	K9_TRY(cudaMemsetAsync(d_next, 0, sizeof(int) * (8 + (size_t)nchunks), c->stream));
+	if (!resident && !streaming) {
+		K9_TRY(cudaMemcpyAsync(kb.s, sources, sb, cudaMemcpyHostToDevice, c->stream));
+		K9_TRY(cudaMemcpyAsync(kb.t, targets, tb, cudaMemcpyHostToDevice, c->stream));
+	}
 
 	BatchParams p;
 	p.sources = d_s; p.targets = d_t; p.batch = batch; p.n = n; p.m = m;
@@ -569,6 +619,7 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 	p.sentinel = params->sentinel; p.tol = params->tol;
 	p.thr0 = (params->dist_mode == ICPB_DIST_SQRT) ? sqrt_threshold_host(params->sentinel) : params->sentinel;
 	p.errors = d_e; p.iterations = d_it; p.iterations_run = d_run; p.R = d_R; p.t = d_tt; p.idx = nullptr; p.next = d_next;
+	p.ready = streaming ? d_ready : nullptr; p.chunk = CHUNK; p.fail = d_fail;
 	const int mpad = ((m + K9_TRK - 1) / K9_TRK) * K9_TRK;
 	// default: the filter kernel (K9F); ICPB_K9_FILTER=0 selects the direct kernel (every pair through the exact chain)
 	bool use_filter = true;
@@ -592,18 +643,33 @@ extern "C" int icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int ba
 	if (per_sm < 1) per_sm = 1;
 	int grid = c->sm_count * per_sm;
 	if (grid > batch) grid = batch;
+	if (streaming) K9_TRY(cudaEventRecord(kb.ev, c->stream));        // the flags are zeroed before any chunk may set one
 	K9_TRY(cudaEventRecord(c->ev[2], c->stream));
 	kern<<<grid, K9_THREADS, smem, c->stream>>>(p);
 	c->launches++;
 	K9_TRY(cudaGetLastError());
 	K9_TRY(cudaEventRecord(c->ev[3], c->stream));
+	if (streaming) {
+		// the kernel is already running (or queued) on the compute stream; the chunks follow on the copy stream, each one
+		// trailed by its 4-byte "landed" flag. CTAs that draw a registration whose chunk is still in flight wait for it.
+		K9_TRY(cudaStreamWaitEvent(kb.copy_stream, kb.ev, 0));
+		for (int ch = 0; ch < nchunks; ch++) {
+			const size_t b0 = (size_t)ch * CHUNK, cnt = (size_t)std::min(CHUNK, batch - ch * CHUNK);
+			K9_TRY(cudaMemcpyAsync(kb.s + b0 * n * 3, sources + b0 * n * 3, sizeof(float) * 3 * cnt * n, cudaMemcpyHostToDevice, kb.copy_stream));
+			K9_TRY(cudaMemcpyAsync(kb.t + b0 * m * 3, targets + b0 * m * 3, sizeof(float) * 3 * cnt * m, cudaMemcpyHostToDevice, kb.copy_stream));
+			K9_TRY(cudaMemcpyAsync(d_ready + ch, kb.one, sizeof(int), cudaMemcpyHostToDevice, kb.copy_stream));
+		}
+	}
+	int h_fail = 0;
 	K9_TRY(cudaMemcpyAsync(errors, d_e, eb, cudaMemcpyDeviceToHost, c->stream));
 	K9_TRY(cudaMemcpyAsync(iterations, d_it, sizeof(int) * batch, cudaMemcpyDeviceToHost, c->stream));
 	K9_TRY(cudaMemcpyAsync(R, d_R, sizeof(double) * 9 * batch, cudaMemcpyDeviceToHost, c->stream));
 	K9_TRY(cudaMemcpyAsync(t, d_tt, sizeof(double) * 3 * batch, cudaMemcpyDeviceToHost, c->stream));
+	K9_TRY(cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	if (streaming) K9_TRY(cudaStreamSynchronize(kb.copy_stream));
 	K9_TRY(cudaStreamSynchronize(c->stream));
+	if (h_fail) { snprintf(c->err, sizeof c->err, "icpb_run_batched: a chunk of the streamed upload never arrived"); return ICPB_ERR_CUDA; }
 	if (elapsed_ms) K9_TRY(cudaEventElapsedTime(elapsed_ms, c->ev[2], c->ev[3]));
 #undef K9_TRY
-	cleanup();
 	return ICPB_OK;
 }

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cuda_runtime.h>
 #include "icp_b200.h"
+#include <nvtx3/nvToolsExt.h>
 
 namespace icpb {
 
@@ -97,6 +98,16 @@ struct GridPyramid {
 	float slack;                   // absolute per-axis slack of the box distance (grid_tree.cuh)
 };
 
+// ---- tracing: NVTX ranges per API call and per phase of an iteration; header-only NVTX v3 costs a
+// null-pointer test when no tool is attached. nsys / ncu --nvtx show them as icpb:<name>.
+struct NvtxRange {
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+	NvtxRange(const NvtxRange&) = delete;
+	NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define ICPB_NVTX(name) ::icpb::NvtxRange nvtx_range__(name)
+
 // ---- error handling -----------------------------------------------------------------------------
 struct Ctx;
 int  fail_cuda(Ctx* c, cudaError_t e, const char* what, const char* file, int line);
@@ -131,6 +142,18 @@ int  dist_allreduce_f64(Dist* d, double* dev_buf, int count, cudaStream_t s, cha
 // (ncclAllReduce min) on whether the fused exchange can be used. out->world stays 0 when it cannot.
 int  dist_peer_init(Dist* d, int device, cudaStream_t s, PeerXchg* out, char* err, size_t errlen);
 void dist_destroy(Dist* d);
+int  dist_check_async(Dist* d, char* err, size_t errlen);       // ncclCommGetAsyncError (NCCL path only)
+bool dist_has_comm(const Dist* d);
+int  dist_init_local(Dist** outs, PeerXchg* peers, const int* devices, int world, char* err, size_t errlen);   // in-process group
+int  create_context(Ctx** out, int device);                     // engine.cu
+
+// device / pinned buffers of icpb_run_batched, kept across calls (grow-only)
+struct K9Buffers {
+	float *s = nullptr, *t = nullptr, *e = nullptr; int* ints = nullptr; double* dbl = nullptr;
+	size_t s_cap = 0, t_cap = 0, e_cap = 0, ints_cap = 0, dbl_cap = 0;
+	cudaStream_t copy_stream = nullptr; cudaEvent_t ev = nullptr;
+	int* one = nullptr;              // pinned {1, 0}: source of the "chunk landed" flag copies
+};
 
 // ---- the context ---------------------------------------------------------------------------------
 struct Ctx {
@@ -173,6 +196,7 @@ struct Ctx {
 
 	// source (this rank's shard)
 	int n = 0, n_cap = 0;        // n_cap: padded capacity
+	int n_cap_at_graph = 0;      // capacity when graph_gen was last checked (a reallocation invalidates captured graphs)
 	float *px = nullptr, *py = nullptr, *pz = nullptr;
 	u64*  keys = nullptr;
 	int*  idx = nullptr;
@@ -233,6 +257,8 @@ struct Ctx {
 	float graph_sentinel = 0.f;
 	bool graphs_enabled = false;                     // ICPB_GRAPHS=1 (or ICPB_FLAG_GRAPH) enables: capture + instantiate cost
 	                                                 // milliseconds, which only repeated registrations of one size amortise
+
+	K9Buffers k9;
 
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t* ev_match = nullptr; int ev_match_cap = 0;

@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <chrono>
+#include <thread>
 
 namespace icpb {
 
@@ -46,6 +48,7 @@ static int ensure_errors(Ctx* c, int count)
 	if (count <= c->err_cap) return ICPB_OK;
 	int rc = dev_alloc(c, &c->errors, (size_t)count);
 	if (rc != ICPB_OK) return rc;
+	c->graph_gen++;                     // captured kernels hold the old c->errors pointer
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	ICPB_CUDA(c, cudaMallocHost((void**)&c->errors_host, sizeof(float) * (size_t)count));
 	c->err_cap = count;
@@ -102,8 +105,12 @@ static int enqueue_iteration(Ctx* c, const icpb_params* p, cudaEvent_t* ev, bool
 {
 	int rc;
 	if (ev) ICPB_CUDA(c, cudaEventRecord(ev[0], c->stream));
-	if ((rc = launch_match(c, p->dist_mode, p->nn_method, p->sentinel)) != ICPB_OK) return rc;
+	nvtxRangePushA("icpb:match");
+	rc = launch_match(c, p->dist_mode, p->nn_method, p->sentinel);
+	nvtxRangePop();
+	if (rc != ICPB_OK) return rc;
 	if (ev) ICPB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+	ICPB_NVTX("icpb:minimize+transform");
 	if ((rc = launch_moments(c, p->metric)) != ICPB_OK) return rc;
 	const bool nccl_exchange = c->world > 1 && c->peer.world < 2;   // otherwise the exchange happens inside K2/K7/K4
 	if (nccl_exchange) {
@@ -124,11 +131,24 @@ static int enqueue_iteration(Ctx* c, const icpb_params* p, cudaEvent_t* ev, bool
 static int read_state(Ctx* c)
 {
 	ICPB_CUDA(c, cudaMemcpyAsync(c->st_host, c->st, sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
+	if (c->world > 1 && dist_has_comm(c->dist) && c->peer.world < 2) {
+		// NCCL path: a collective whose peer died never completes. Poll the stream and the communicator's asynchronous
+		// error state (ncclCommGetAsyncError) instead of blocking in cudaStreamSynchronize; on error the communicator is
+		// aborted, which lets the pending work drain.
+		for (;;) {
+			const cudaError_t q = cudaStreamQuery(c->stream);
+			if (q == cudaSuccess) break;
+			if (q != cudaErrorNotReady) return fail_cuda(c, q, "cudaStreamQuery", __FILE__, __LINE__);
+			const int rc = dist_check_async(c->dist, c->err, sizeof c->err);
+			if (rc != ICPB_OK) { cudaStreamSynchronize(c->stream); return rc; }
+			std::this_thread::sleep_for(std::chrono::microseconds(20));
+		}
+	}
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return kf_policy_update(c);      // the stream is idle: a good moment to look at the filter's exact-pass rate
 }
 
-static int create_common(Ctx** out, int device)
+int create_context(Ctx** out, int device)
 {
 	int count = 0;
 	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ICPB_ERR_NODEVICE;
@@ -213,7 +233,7 @@ int icpb_create(icpb_ctx** out, int device)
 {
 	if (!out) return ICPB_ERR_BADARG;
 	Ctx* c = nullptr;
-	int rc = create_common(&c, device);
+	int rc = create_context(&c, device);
 	if (rc != ICPB_OK) return rc;
 	*out = reinterpret_cast<icpb_ctx*>(c);
 	return ICPB_OK;
@@ -225,7 +245,7 @@ int icpb_create_dist(icpb_ctx** out, int device, int rank, int world, const void
 {
 	if (!out || world < 1 || rank < 0 || rank >= world) return ICPB_ERR_BADARG;
 	Ctx* c = nullptr;
-	int rc = create_common(&c, device);
+	int rc = create_context(&c, device);
 	if (rc != ICPB_OK) return rc;
 	c->rank = rank; c->world = world;
 	if (world > 1) {
@@ -250,6 +270,10 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
+	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);
+	if (c->k9.one) cudaFreeHost(c->k9.one);
+	if (c->k9.ev) cudaEventDestroy(c->k9.ev);
+	if (c->k9.copy_stream) cudaStreamDestroy(c->k9.copy_stream);
 	if (c->st_host) cudaFreeHost(c->st_host);
 	if (c->errors_host) cudaFreeHost(c->errors_host);
 	for (int k = 0; k < 4; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -285,6 +309,7 @@ int icpb_dist_info(const icpb_ctx* ctx, int* rank, int* world, int* peer_exchang
 // ---- clouds ---------------------------------------------------------------------------------------
 int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 {
+	ICPB_NVTX("icpb_set_target");
 	ICPB_ENTER(ctx);
 	Ctx* c = C(ctx);
 	if (!xyz || m <= 0) return fail(c, ICPB_ERR_BADARG, "icpb_set_target: empty target");
@@ -311,6 +336,7 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 
 int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 {
+	ICPB_NVTX("icpb_set_source");
 	ICPB_ENTER(ctx);
 	Ctx* c = C(ctx);
 	if (n < 0 || (n > 0 && !xyz)) return fail(c, ICPB_ERR_BADARG, "icpb_set_source: bad arguments");
@@ -329,9 +355,12 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 		if ((rc = dev_alloc(c, &c->dmin, (size_t)cap)) != ICPB_OK) return rc;
 		c->n_cap = cap;
 	}
+	// a captured iteration graph bakes in the buffers and the point count: it stays valid across uploads that change
+	// neither (the repeated same-size registrations ICPB_FLAG_GRAPH is meant for)
+	if (cap > c->n_cap_at_graph || n != c->n) c->graph_gen++;
+	c->n_cap_at_graph = c->n_cap;
 	c->n = n; c->step_state_ready = false;   // the control block caches the global point count
 	c->n_total_valid = false;
-	c->graph_gen++;
 	const float* src = xyz;
 	if (!on_device && n > 0) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)n)) != ICPB_OK) return rc;
@@ -400,6 +429,7 @@ static int ensure_step_state(Ctx* c)
 
 int icpb_match(icpb_ctx* ctx, int dist_mode, int nn_method, float sentinel)
 {
+	ICPB_NVTX("icpb_match");
 	ICPB_ENTER(ctx);
 	Ctx* c = C(ctx);
 	if (c->m <= 0 || c->n <= 0) return fail(c, ICPB_ERR_STATE, "icpb_match: set the target and the source first");
@@ -451,6 +481,19 @@ int icpb_transform(icpb_ctx* ctx, float* rms)
 	return ICPB_OK;
 }
 
+int icpb_set_transform(icpb_ctx* ctx, const float R[9], const float T[3])
+{
+	ICPB_ENTER(ctx);
+	Ctx* c = C(ctx);
+	if (!R || !T) return fail(c, ICPB_ERR_BADARG, "icpb_set_transform: NULL argument");
+	int rc;
+	if ((rc = ensure_step_state(c)) != ICPB_OK) return rc;
+	ICPB_CUDA(c, cudaMemcpyAsync(c->st->R, R, sizeof(float) * 9, cudaMemcpyHostToDevice, c->stream));
+	ICPB_CUDA(c, cudaMemcpyAsync(c->st->T, T, sizeof(float) * 3, cudaMemcpyHostToDevice, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return ICPB_OK;
+}
+
 int icpb_get_moments(icpb_ctx* ctx, double* mom, int count)
 {
 	ICPB_ENTER(ctx);
@@ -465,6 +508,7 @@ int icpb_get_moments(icpb_ctx* ctx, double* mom, int count)
 // ---- whole loop ------------------------------------------------------------------------------------------
 int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_result* result)
 {
+	ICPB_NVTX("icpb_run");
 	ICPB_ENTER(ctx);
 	Ctx* c = C(ctx);
 	int rc;

@@ -24,22 +24,30 @@ namespace icpb {
 
 constexpr int GP_STACK = 7 * GP_MAX_L + 2;      // GridGeom / GridPyramid / GP_MAX_L: common.cuh
 
-// Cell size: <= ~4 cells per point, <= 16M cells, never letting one axis of a flat cloud explode the count.
+// Cell size: <= ~4 cells per point, <= 16M cells and <= GP_MAX_DIM cells along any axis (the pyramid has GP_MAX_L
+// levels and packs node coordinates in 18 bits: a collinear or very thin cloud must not exceed that on its long axis).
+// h grows until both limits hold — a flat cloud of large extent needs many more than a handful of steps because its
+// flat axis is clamped to an absolute 1e-6 and the cube-root estimate is then far too small.
+constexpr int GP_MAX_DIM = 1 << (GP_MAX_L - 1);
 inline GridGeom compute_grid_geom(const float lo[3], const float hi[3], int m)
 {
 	float ext[3];
-	for (int k = 0; k < 3; k++) ext[k] = fmaxf(hi[k] - lo[k], 1e-6f);
+	for (int k = 0; k < 3; k++) { ext[k] = fmaxf(hi[k] - lo[k], 1e-6f); if (!(ext[k] < 3e38f)) ext[k] = 3e38f; }
 	const double cells_max = fmin(fmax(4.0 * m, 4096.0), 16.0 * 1024 * 1024);
 	double h = cbrt((double)ext[0] * ext[1] * ext[2] / cells_max);
-	for (int it = 0; it < 8; it++) {
-		const double cells = (floor(ext[0] / h) + 1) * (floor(ext[1] / h) + 1) * (floor(ext[2] / h) + 1);
-		if (cells <= cells_max) break;
+	const double emax = fmax((double)ext[0], fmax((double)ext[1], (double)ext[2]));
+	h = fmax(h, emax / (double)(GP_MAX_DIM - 1));          // the long axis alone
+	if (!(h > 0.0)) h = 1e-6;
+	for (int it = 0; it < 4096; it++) {
+		const double dx = floor(ext[0] / h) + 1, dy = floor(ext[1] / h) + 1, dz = floor(ext[2] / h) + 1;
+		if (dx * dy * dz <= cells_max && fmax(dx, fmax(dy, dz)) <= (double)GP_MAX_DIM) break;
 		h *= 1.26;
 	}
 	GridGeom g;
 	g.h = (float)h; g.inv_h = (float)(1.0 / h);
 	g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
 	g.nx = (int)floor(ext[0] / h) + 1; g.ny = (int)floor(ext[1] / h) + 1; g.nz = (int)floor(ext[2] / h) + 1;
+	// h >= emax / (GP_MAX_DIM - 1) from the start, so every axis has at most GP_MAX_DIM cells: the pyramid reaches a single root
 	return g;
 }
 

@@ -269,6 +269,7 @@ int icpb_estimate_normals(icpb_ctx* ctx, int k, float* elapsed_ms) { return icpb
 
 int icpb_estimate_normals_ex(icpb_ctx* ctx, int k, int knn_dist_mode, float* elapsed_ms)
 {
+	ICPB_NVTX("icpb_estimate_normals");
 	if (!ctx) return ICPB_ERR_BADARG;
 	Ctx* c = C(ctx);
 	if (knn_dist_mode != ICPB_DIST_SQ && knn_dist_mode != ICPB_DIST_SQRT) { snprintf(c->err, sizeof c->err, "icpb_estimate_normals_ex: knn_dist_mode must be ICPB_DIST_SQ or ICPB_DIST_SQRT"); return ICPB_ERR_BADARG; }

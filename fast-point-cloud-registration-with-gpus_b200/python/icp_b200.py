@@ -54,6 +54,7 @@ def _load():
         "icpb_match": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]),
         "icpb_minimize": (C.c_int, [vp, C.c_int, fp, fp]),
         "icpb_transform": (C.c_int, [vp, fp]),
+        "icpb_set_transform": (C.c_int, [vp, fp, fp]),
         "icpb_get_moments": (C.c_int, [vp, dp, C.c_int]),
         "icpb_estimate_normals": (C.c_int, [vp, C.c_int, fp]),
         "icpb_estimate_normals_ex": (C.c_int, [vp, C.c_int, C.c_int, fp]),
@@ -72,6 +73,18 @@ def _load():
         "icpb_get_filter_stats": (C.c_int, [vp, dp, dp]),
         "icpb_get_filter_config": (C.c_int, [vp, ip, ip, ip, dp]),
         "icpb_launch_count": (C.c_longlong, [vp]),
+        "icpb_group_create": (C.c_int, [C.POINTER(vp), ip, C.c_int]),
+        "icpb_group_destroy": (C.c_int, [vp]),
+        "icpb_group_size": (C.c_int, [vp]),
+        "icpb_group_ctx": (vp, [vp, C.c_int]),
+        "icpb_group_last_error": (C.c_char_p, [vp]),
+        "icpb_group_info": (C.c_int, [vp, ip, ip, ip]),
+        "icpb_group_set_target": (C.c_int, [vp, vp, C.c_int]),
+        "icpb_group_set_source": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "icpb_group_estimate_normals": (C.c_int, [vp, C.c_int, C.c_int, fp]),
+        "icpb_group_run": (C.c_int, [vp, C.POINTER(Params), fp, C.POINTER(Result)]),
+        "icpb_group_get_source": (C.c_int, [vp, vp]),
+        "icpb_group_get_correspondences": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)     # AttributeError here = the library does not export what the header declares
@@ -175,6 +188,12 @@ class Context:
         rms = C.c_float()
         self._ck(lib.icpb_transform(self.h, C.byref(rms)), "transform")
         return rms.value
+
+    def set_transform(self, R, T):
+        R = np.ascontiguousarray(R, dtype=np.float32).reshape(9)
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(3)
+        fpp = C.POINTER(C.c_float)
+        self._ck(lib.icpb_set_transform(self.h, R.ctypes.data_as(fpp), T.ctypes.data_as(fpp)), "set_transform")
 
     def moments(self, count=16):
         out = np.zeros(count, dtype=np.float64)
@@ -292,6 +311,72 @@ class Context:
 
     def launch_count(self):
         return int(lib.icpb_launch_count(self.h))
+
+
+class Group:
+    """Several GPUs driven from this one process through icpb_group_* (the C/C++ multi-GPU host path)."""
+
+    def __init__(self, ndev, devices=None):
+        self.h = C.c_void_p()
+        dev = (C.c_int * ndev)(*devices) if devices is not None else None
+        rc = lib.icpb_group_create(C.byref(self.h), dev, ndev)
+        if rc != 0:
+            raise IcpError("icpb_group_create: %s" % lib.icpb_status_string(rc).decode())
+        self.ndev, self.n, self.m = ndev, 0, 0
+
+    def close(self):
+        if self.h:
+            lib.icpb_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise IcpError("%s: %s (%s)" % (what, lib.icpb_status_string(rc).decode(), lib.icpb_group_last_error(self.h).decode()))
+
+    def info(self):
+        n, p, d = C.c_int(), C.c_int(), (C.c_int * self.ndev)()
+        self._ck(lib.icpb_group_info(self.h, C.byref(n), C.byref(p), d), "group_info")
+        return {"ndev": n.value, "peer_exchange": bool(p.value), "devices": list(d)}
+
+    def set_target(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, 3)
+        self.m = q.shape[0]
+        self._ck(lib.icpb_group_set_target(self.h, _ptr(q), self.m), "group_set_target")
+
+    def set_source(self, p, block=2048):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        self.n = p.shape[0]
+        self._ck(lib.icpb_group_set_source(self.h, _ptr(p), self.n, block), "group_set_source")
+
+    def estimate_normals(self, k=4, knn_dist_mode=DIST_SQRT):
+        ms = C.c_float()
+        self._ck(lib.icpb_group_estimate_normals(self.h, k, knn_dist_mode, C.byref(ms)), "group_estimate_normals")
+        return ms.value
+
+    def run(self, params):
+        errors = np.zeros(params.max_iter + 1, dtype=np.float32)
+        res = Result()
+        self._ck(lib.icpb_group_run(self.h, C.byref(params), errors.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)), "group_run")
+        return errors, res
+
+    def get_source(self):
+        out = np.empty((self.n, 3), dtype=np.float32)
+        self._ck(lib.icpb_group_get_source(self.h, _ptr(out)), "group_get_source")
+        return out
+
+    def correspondences(self):
+        out = np.empty(self.n, dtype=np.int32)
+        self._ck(lib.icpb_group_get_correspondences(self.h, _ptr(out)), "group_get_correspondences")
+        return out
+
+    def launch_count(self, rank=0):
+        return int(lib.icpb_launch_count(lib.icpb_group_ctx(self.h, rank)))
 
 
 def nccl_unique_id():

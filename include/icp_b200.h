@@ -117,6 +117,34 @@ int  icpb_destroy(icpb_ctx* ctx);
 const char* icpb_last_error(const icpb_ctx* ctx);
 int  icpb_device_info(const icpb_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name64);
 
+/* ---- several GPUs, one process, plain C/C++ (north star: "host code stays C/C++ ... source points sharded across the
+ * 8 GPUs of one box with the target replicated") ------------------------------------------------------------------
+ * A group is `ndev` contexts (rank r on devices[r]; devices == NULL means 0..ndev-1) created and driven from ONE
+ * process: no launcher, no MPI, no unique id. The per-iteration moment sums are exchanged inside the reduction kernels
+ * over NVLink peer memory (cudaDeviceEnablePeerAccess), or with ncclAllReduce launches on communicators made by
+ * ncclCommInitAll when peer access is missing, ndev > 8 or ICPB_PEER=0. Every call below drives all devices at once
+ * (one host thread per device inside the call) and returns when all of them are done. Results — correspondences,
+ * trajectories, transforms — are those of one GPU: indices bit for bit, sums to FP64 summation-order noise.
+ * Replaces nothing in the reference (it is single-GPU, src/ICP_point_to_point.cu:90-460); it is that main()'s shape. */
+typedef struct icpb_group icpb_group;
+int  icpb_group_create(icpb_group** out, const int* devices, int ndev);
+int  icpb_group_destroy(icpb_group* g);
+int  icpb_group_size(const icpb_group* g);
+icpb_ctx* icpb_group_ctx(icpb_group* g, int rank);        /* rank's context, e.g. for icpb_get_filter_stats; owned by the group */
+const char* icpb_group_last_error(const icpb_group* g);
+int  icpb_group_info(const icpb_group* g, int* ndev, int* peer_exchange, int* devices /* [ndev] or NULL */);
+int  icpb_group_set_target(icpb_group* g, const float* xyz_host, int m);                  /* replicated on every device */
+/* Shards the source: block > 0 deals blocks of `block` consecutive points round-robin (2048 = the matching kernels'
+ * source block: every rank sees the same mix of regions of the cloud, which balances the matching step); block == 0
+ * gives contiguous shards. */
+int  icpb_group_set_source(icpb_group* g, const float* xyz_host, int n, int block);
+int  icpb_group_estimate_normals(icpb_group* g, int k, int knn_dist_mode, float* elapsed_ms);
+/* icpb_run on every rank; `result` is rank 0's (all ranks hold identical bits; the call checks it) with the times taken
+ * as the maximum over the ranks and nn_pairs summed. */
+int  icpb_group_run(icpb_group* g, const icpb_params* params, float* errors, icpb_result* result);
+int  icpb_group_get_source(icpb_group* g, float* xyz_host);           /* in the original point order */
+int  icpb_group_get_correspondences(icpb_group* g, int* idx_host);    /* in the original point order */
+
 /* ---- clouds ------------------------------------------------------------------------------- */
 /* `xyz` is AoS float[3*count]; `on_device` != 0 means it already is a device pointer on the
  * context's GPU. Replaces the cudaMemcpy H2D of src/ICP_point_to_point.cu:207-208. The target is
@@ -138,6 +166,9 @@ int  icpb_minimize(icpb_ctx* ctx, int metric, float R[9], float T[3]);
 /* Transformation + error — RyT + cublasScopy + Scopy/Saxpy/Snrm2 (src/ICP_point_to_point.cu:403-416).
  * Applies the R,T of the last icpb_minimize; returns the RMS  ||P' - Q_idx|| / sqrt(N). */
 int  icpb_transform(icpb_ctx* ctx, float* rms);
+/* Overrides the R (column-major), T that the next icpb_transform applies — the reference's d_temp_r / d_temp_T
+ * (src/ICP_point_to_point.cu:379-397), for callers that minimise elsewhere and for testing K4 against `RyT` alone. */
+int  icpb_set_transform(icpb_ctx* ctx, const float R[9], const float T[3]);
 /* Moments of the last icpb_minimize (after the allreduce when distributed): 16 doubles for
  * point-to-point {sum p (3), sum q (3), sum q p^T (9, column-major, rows = q), N},
  * 28 for point-to-plane {upper triangle of C row by row (21), b (6), N}. */

@@ -44,6 +44,21 @@ ORC_API int orc_num_threads(void)
 #endif
 }
 
+/* The CPU arm must use every host core whatever the launcher put in the environment (torchrun exports
+ * OMP_NUM_THREADS=1): n <= 0 selects the number of processors OpenMP sees. Returns the count now in effect. */
+ORC_API int orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if (n <= 0) n = omp_get_num_procs();
+	omp_set_dynamic(0);
+	omp_set_num_threads(n);
+	return omp_get_max_threads();
+#else
+	(void)n;
+	return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------
  * Synthetic data
  * ---------------------------------------------------------------------------------- */
@@ -190,6 +205,13 @@ ORC_API void orc_match_f32(const float* P, int n, const float* Q, int m, int mod
 		}
 		if (best >= 0) idx[i] = best;
 	}
+}
+
+/* The distance of pair (P_i, Q_i), i = 0..n-1, with the kernel's arithmetic (tests: the winning distance a matching pass reports). */
+ORC_API void orc_pair_dist_f32(const float* P, const float* Q, int n, int mode, float* d)
+{
+	for (int i = 0; i < n; i++)
+		d[i] = orc_dist(mode, P[3 * (size_t)i], P[3 * (size_t)i + 1], P[3 * (size_t)i + 2], Q[3 * (size_t)i], Q[3 * (size_t)i + 1], Q[3 * (size_t)i + 2]);
 }
 
 /* Same, restricted to sources [i0,i1): the bounded sample bench.py times. */

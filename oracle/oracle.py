@@ -37,6 +37,7 @@ def _ip(a): return a.ctypes.data_as(_i)
 
 
 _lib.orc_num_threads.restype = C.c_int
+_lib.orc_set_num_threads.restype = C.c_int
 _lib.orc_icp_p2p_f32.restype = C.c_int
 _lib.orc_icp_p2plane_f32.restype = C.c_int
 _lib.orc_icp_p2plane_mode_f32.restype = C.c_int
@@ -51,6 +52,11 @@ _lib.orc_solve6_spd.restype = C.c_int
 
 def num_threads():
     return _lib.orc_num_threads()
+
+
+def set_num_threads(n=0):
+    """n <= 0: every processor OpenMP sees (not OMP_NUM_THREADS, which torchrun sets to 1). Returns the count in effect."""
+    return _lib.orc_set_num_threads(C.c_int(int(n)))
 
 
 def synth_p2p(width, npts=None):
@@ -99,6 +105,14 @@ def match(P, Q, mode=MODE_SQ, sentinel=100000.0, idx0=None):
     idx = np.zeros(P.shape[0], np.int32) if idx0 is None else np.ascontiguousarray(idx0, np.int32).copy()
     _lib.orc_match_f32(_fp(P), C.c_int(P.shape[0]), _fp(Q), C.c_int(Q.shape[0]), C.c_int(mode), C.c_float(sentinel), _ip(idx))
     return idx
+
+
+def pair_distances(P, Q, mode=MODE_SQ):
+    """d[i] = the reference kernel's distance between P[i] and Q[i] (same arithmetic as `match`)."""
+    P = np.ascontiguousarray(P, np.float32).reshape(-1, 3); Q = np.ascontiguousarray(Q, np.float32).reshape(-1, 3)
+    d = np.zeros(P.shape[0], np.float32)
+    _lib.orc_pair_dist_f32(_fp(P), _fp(Q), C.c_int(P.shape[0]), C.c_int(mode), _fp(d))
+    return d
 
 
 def moments(P, Q, idx):

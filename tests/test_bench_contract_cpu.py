@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                        "--width", "64", "--skip-ref-binary"], capture_output=True, text=True, timeout=300)
+                        "--width", "64", "--skip-ref-binary"], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))       # what torchrun exports to every rank
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -20,6 +21,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1), "the CPU arm must use every host core whatever OMP_NUM_THREADS says"
 
 
 def test_gpu_arm_fails_loudly_without_a_device():

@@ -78,3 +78,32 @@ def test_batched_filter_is_bitwise_the_direct_kernel(ib):
     for a, b in zip(out["1"], out["0"]):
         for x, y in zip(a, b):
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+
+
+def test_batched_full_config5_4096_pairs(ctx, ib, orc):
+    """BASELINE.json config 5 at full size: 4096 independent pairs of 2048-point clouds, poses from the counter-based
+    generator of SURVEY.md 8(d) (splitmix64, seed 20240, stream b). Every pair must recover its generating pose; a
+    sample is compared with the oracle's whole trajectory; and the batch is split-invariant (the 8-GPU run is 8
+    replicas of 512 pairs each: a pair's result must not depend on which batch it sits in)."""
+    import icp_synth
+    B = 4096
+    S, T, r, t = icp_synth.batched_pairs(B)
+    assert S.shape == (B, 2048, 3) and T.shape == (B, 2048, 3)
+    p = ib.default_params(max_iter=40)
+    errors, iters, R, tt, ms = ctx.run_batched(p, S, T)
+    Rtrue = np.stack([icp_synth.euler_matrix(r[b]).astype(np.float64) for b in range(B)])
+    assert np.abs(R - Rtrue).max() < 2e-5
+    assert np.abs(tt - t.astype(np.float64)).max() < 2e-5
+    final = errors[np.arange(B), iters + 1]
+    assert final.max() < 1e-5 and iters.min() >= 3 and iters.max() < 40
+    for b in (0, 511, 512, 1777, 2048, 3000, 4095):
+        o = orc.icp_p2p(S[b], T[b], max_iter=40)
+        assert iters[b] == o["iterations"], b
+        k = o["iterations"] + 2
+        assert np.all(np.abs(errors[b, :k] - o["errors"][:k]) <= 1e-5 * np.abs(o["errors"][:k]) + 1e-7), b
+        assert np.abs(R[b] - o["R"]).max() <= 1e-5 and np.abs(tt[b] - o["t"]).max() <= 1e-5, b
+    # rank 3 of 8 holds pairs [1536, 2048): identical bits to the same pairs inside the full batch
+    lo, hi = 3 * 512, 4 * 512
+    e2, i2, R2, t2, _ = ctx.run_batched(p, S[lo:hi], T[lo:hi])
+    assert np.array_equal(i2, iters[lo:hi]) and np.array_equal(e2.view(np.uint32), errors[lo:hi].view(np.uint32))
+    assert np.array_equal(R2.view(np.uint64), R[lo:hi].view(np.uint64)) and np.array_equal(t2.view(np.uint64), tt[lo:hi].view(np.uint64))

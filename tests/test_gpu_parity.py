@@ -163,8 +163,17 @@ def test_step_by_step_vs_oracle(ctx, orc, golden_dir):
         got = ctx.get_source()
         assert np.array_equal(got.view(np.uint32), P.view(np.uint32))
         assert abs(rms - orc.rms(P, M, ref_idx)) <= 1e-6 * max(rms, 1e-3)
-    r = np.load(os.path.join(golden_dir, "ref_ryt.npz"))   # and against the reference's RyT kernel itself
+    # and against the reference's RyT kernel itself (tests/golden/ref_ryt.npz = its output on a B200): K4 in the loop
+    # (transform_kernel, with R,T injected) and the stand-alone entry point must both reproduce it bit for bit
+    r = np.load(os.path.join(golden_dir, "ref_ryt.npz"))
     ctx.set_target(r["P"]); ctx.set_source(r["P"])
+    assert np.array_equal(ctx.match(0), np.arange(r["P"].shape[0]))
+    ctx.set_transform(r["R"], r["T"])
+    rms = ctx.transform()
+    got = ctx.get_source()
+    assert np.array_equal(got.view(np.uint32), r["out"].view(np.uint32))
+    assert abs(rms - orc.rms(r["out"], r["P"], np.arange(r["P"].shape[0], dtype=np.int32))) <= 1e-6 * max(rms, 1e-3)
+    assert np.array_equal(ctx.apply_transform(r["R"], r["T"], r["P"]).view(np.uint32), r["out"].view(np.uint32))
 
 
 @pytest.mark.parametrize("W,expect_run", [(32, 15), (128, 27)])

@@ -191,6 +191,26 @@ int main(int argc, char** argv)
 	check<0>("collinear target", pl, line, 100000.0f, false);
 	std::vector<float> one = { 1.f, 2.f, 3.f }, two = { 0.f, 0.f, 0.f, 5.f, 5.f, 5.f };
 	check<0>("single target point", two, one, 100000.0f, false);
+	// long collinear / thin / flat targets: one axis would need > 2^17 cells (368334x1x1 grid, 18 levels, cold MISMATCH);
+	// a sample of sources along and beside the line, cold and warm; brute force over 100k targets for each
+	{
+		std::vector<float> L(3 * 100000, 0.f), PL;
+		for (int j = 0; j < 100000; j++) { L[3 * j] = (float)j * 1e-3f; }
+		for (int j = 0; j < 100000; j += 331) { PL.push_back(L[3 * j] + 4e-4f); PL.push_back((j % 2) ? 0.0f : 0.01f); PL.push_back((j % 3) ? 0.0f : -0.02f); }
+		for (int warm = 0; warm < 2; warm++) { check<0>("100k collinear target", PL, L, 100000.0f, warm); check<1>("100k collinear target", PL, L, 100000.0f, warm); }
+		std::uniform_real_distribution<float> u(0.f, 1.f);
+		std::vector<float> T(3 * 100000), PT;
+		for (int j = 0; j < 100000; j++) { T[3 * j] = 200.0f * u(rng); T[3 * j + 1] = 0.01f * u(rng); T[3 * j + 2] = 0.01f * u(rng); }      // thin rod
+		for (int j = 0; j < 100000; j += 407) { PT.push_back(T[3 * j] + 1e-3f); PT.push_back(T[3 * j + 1] - 2e-3f); PT.push_back(0.02f * u(rng)); }
+		check<0>("100k thin rod 200 x 0.01 x 0.01", PT, T, 100000.0f, false);
+		check<1>("100k thin rod 200 x 0.01 x 0.01", PT, T, 100000.0f, true);
+		std::vector<float> F(3 * 60000), PF;
+		for (int j = 0; j < 60000; j++) { F[3 * j] = 3000.0f * u(rng); F[3 * j + 1] = 3000.0f * u(rng); F[3 * j + 2] = 7.0f; }                // flat, large extent
+		for (int j = 0; j < 60000; j += 263) { PF.push_back(F[3 * j] + 0.5f); PF.push_back(F[3 * j + 1] - 0.25f); PF.push_back(7.0f + 3.0f * u(rng)); }
+		check<0>("60k flat sheet 3000 x 3000 x 0", PF, F, 100000.0f, false);
+		HostGrid G = build(L);
+		if (G.g.nx > GP_MAX_DIM || G.py.nx[G.py.levels - 1] != 1 || G.py.ny[G.py.levels - 1] != 1 || G.py.nz[G.py.levels - 1] != 1) { printf("FAIL: pyramid of the collinear target has no single root (%d levels, top %dx%dx%d)\n", G.py.levels, G.py.nx[G.py.levels - 1], G.py.ny[G.py.levels - 1], G.py.nz[G.py.levels - 1]); failures++; }
+	}
 	// large offsets and scales
 	std::vector<float> Qo(Qn), Po(Pw);
 	for (auto& v : Qo) v = v * 30.0f - 5e4f;
