@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native ICP engine (see DESIGN.md "Measurement").
+"""bench.py — benchmarks of the B200-native ICP engine (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--width 1000]
+    python bench.py [--config 2|3|4|5] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[3], the configuration its metric and target are quoted on; it fits one
-GPU): synthetic z = x^2 - y^2 saddle, 1 000 000 source x 1 000 000 target points, point-to-point ICP with
-exact brute-force nearest neighbours. A step = one ICP iteration (matching -> moments -> 3x3 SVD ->
-transform -> error). With N GPUs the SOURCE is sharded over the ranks, the target replicated, and the 16
-moment sums are exchanged inside the library (in the reduction kernels over NVLink peer memory; ICPB_PEER=0
-selects ncclAllReduce launches instead): total work is fixed => "scaling": "strong".
+--config selects the BASELINE.json configuration (default 4, the one its metric and target are quoted on):
+  2  configs[1]: synthetic saddle, 100 000 x 100 000 points, point-to-point ICP, exact brute-force NN
+  3  configs[2]: same clouds, point-to-plane ICP (k-NN PCA normals of the target, 6x6 solve)
+  4  configs[3]: 1 000 000 x 1 000 000 points, point-to-point, source sharded over the N GPUs, target replicated
+  5  configs[4]: batched registration, 4096 independent pairs of 2048-point clouds dealt to the N GPUs (replicas)
+A step = one ICP iteration (2-4: matching -> moments -> 3x3 SVD / 6x6 solve -> transform -> error) or one pass over the
+rank's pairs (5: every pair registered to convergence inside one persistent kernel).
 
 One JSON line on stdout (rank 0):
-  value      NN pairs/s, whole job, inputs resident in HBM, device time (CUDA events on the engine's
-             stream around each step, max over ranks, summed over the K steps)
-  e2e        same metric through the C-ABI call icpb_iterate_host with HOST buffers (pinned): H2D of both
-             clouds, one iteration, D2H of the correspondences + transform, wall-clock
-  roofline   the matching kernel: 8 FLOP per (source,target) pair / its CUDA-event duration, against the
-             FP32 FFMA peak measured in the same process (icpb_measure_fp32_peak); nominal peak beside it
-  cpu_baseline  the oracle's brute-force matching (OpenMP, all host cores) on a bounded sample (N=1 only)
---impl reference: the reference's CPU algorithm (oracle port of src/ICP_CPU.c / CPU_ICP_point_to_point.cpp
-matching, all host threads) on bounded samples of the same workload; rank 0 only.
+  value      NN pairs/s, whole job, inputs resident in HBM, device time (CUDA events on the engine's stream around each
+             step, max over ranks per step, summed over the K steps)
+  e2e        same metric through the C-ABI call with HOST buffers (pinned): icpb_iterate_host (+ icpb_get_source) or
+             icpb_run_batched; H2D of the clouds, the step, D2H of the results, wall clock
+  roofline   the dominant kernel (brute-force matching): 8 FLOP per (source,target) pair / its CUDA-event duration,
+             against the FP32 FFMA peak measured in the same process; `frac` counts the algorithmic 8 FLOP per pair,
+             `frac_executed` the FP32 work the kernel actually issues
+  cpu_baseline  the oracle's CPU restatement (OpenMP, ALL host cores) on a bounded sample (N=1 only)
+  parity     checksums of what the timed steps computed; at N > 1 rank 0 replays on ONE GPU and the run fails on a mismatch
+--impl reference: the reference's CPU algorithm (oracle port, all host threads) on bounded samples of the same workload;
+rank 0 only.
 """
 import argparse
 import json
@@ -102,6 +105,29 @@ def clocks_stop(p, f, t_begin=None, t_end=None):
             "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+P2P, P2PLANE = 0, 1
+CONFIGS = {
+    2: {"name": "configs[1]", "width": 317, "npts": 100000, "metric": P2P},
+    3: {"name": "configs[2]", "width": 317, "npts": 100000, "metric": P2PLANE},
+    4: {"name": "configs[3]", "width": 1000, "npts": None, "metric": P2P},
+    5: {"name": "configs[4]", "batch": 4096, "n": 2048, "width": 46},
+}
+
+
+def clouds_for(args):
+    import icp_synth
+    cfg = CONFIGS[args.config]
+    if args.width:                               # tests / experiments: another grid width, whole grid
+        return icp_synth.p2p_clouds(args.width)
+    return icp_synth.p2p_clouds(cfg["width"], cfg["npts"])
+
+
+def workload_text(args, n, m):
+    cfg = CONFIGS[args.config]
+    kind = "point-to-plane ICP (k-NN PCA normals, 6x6 solve)" if cfg.get("metric") == P2PLANE else "point-to-point ICP"
+    return "synthetic z=x^2-y^2, %dx%d points, %s, exact brute-force NN (BASELINE %s)" % (n, m, kind, cfg["name"])
+
+
 def cpu_match_rate(orc, D, M, seconds_target, mode=0):
     """Oracle brute-force matching on a bounded slice of the sources against the FULL target."""
     n = D.shape[0]
@@ -115,6 +141,19 @@ def cpu_match_rate(orc, D, M, seconds_target, mode=0):
     return sel.shape[0] * M.shape[0] / dt, sel.shape[0], dt
 
 
+def cpu_batched_rate(orc, S, T, seconds_target, max_iter=40):
+    """Oracle whole registrations (orc.icp_p2p: OpenMP matching inside) on a bounded number of pairs."""
+    n, m = S.shape[1], T.shape[1]
+    t0 = time.perf_counter(); o = orc.icp_p2p(S[0], T[0], max_iter=max_iter); dt = time.perf_counter() - t0
+    k = int(max(1, min(S.shape[0] - 1, seconds_target / max(dt, 1e-6))))
+    pairs, t0 = 0.0, time.perf_counter()
+    for b in range(1, 1 + k):
+        o = orc.icp_p2p(S[b], T[b], max_iter=max_iter)
+        pairs += float(o["iterations_run"]) * n * m
+    dt = time.perf_counter() - t0
+    return pairs / dt, k, dt
+
+
 def run_reference_arm(args, rank, emit):
     """The reference's CPU implementation of the path, on the box's host cores (rank 0 only)."""
     if rank != 0:
@@ -124,25 +163,53 @@ def run_reference_arm(args, rank, emit):
     import icp_synth
     # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm would then be timed on ONE thread (r1: SCALE ratios at
     # N > 1 were against a single-threaded baseline). Use every processor OpenMP sees, and record the count in effect.
-    cores = orc.set_num_threads(0)
-    D, M = icp_synth.p2p_clouds(args.width)
-    n = D.shape[0]
-    # each step = one bounded sample: S sources x all targets, S sized for ~3 s of CPU work
-    rate0, _, _ = cpu_match_rate(orc, D, M, 1.0)
-    S = int(max(256, min(n, (rate0 * 3.0 / M.shape[0]) // 256 * 256)))
-    sel = np.ascontiguousarray(D[:: max(1, n // S)][:S])
-    idx_prev = None
-    for _ in range(args.warmup):
-        orc.match(sel, M, 0)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        idx = orc.match(sel, M, 0)
-        mom = orc.moments(sel, M, idx)
-        R, T = orc.rt_from_moments(mom)
-        idx_prev = idx
-    dt = time.perf_counter() - t0
-    pairs = float(S) * M.shape[0] * args.steps
-    value = pairs / dt
+    orc.set_num_threads(0)
+    cfg = CONFIGS[args.config]
+    if args.config == 5:
+        B = args.batch or cfg["batch"]
+        k_step = 8                                     # pairs per step: ~0.1-0.3 s of CPU work each
+        S, T, _, _ = icp_synth.batched_pairs(min(B, (args.steps + args.warmup) * k_step), n=cfg["n"], width=cfg["width"])
+        n, m = S.shape[1], T.shape[1]
+        cur = 0
+        for _ in range(args.warmup):
+            for b in range(k_step):
+                orc.icp_p2p(S[(cur + b) % S.shape[0]], T[(cur + b) % S.shape[0]], max_iter=40)
+            cur += k_step
+        pairs, regs, t0 = 0.0, 0, time.perf_counter()
+        for _ in range(args.steps):
+            for b in range(k_step):
+                o = orc.icp_p2p(S[(cur + b) % S.shape[0]], T[(cur + b) % S.shape[0]], max_iter=40)
+                pairs += float(o["iterations_run"]) * n * m
+                regs += 1
+            cur += k_step
+        dt = time.perf_counter() - t0
+        value = pairs / dt
+        workload = "batched registration: %d independent pairs of %d-point synthetic clouds (BASELINE %s)" % (B, n, cfg["name"])
+        sample = "%d of %d pairs per step, whole registrations to convergence, oracle orc_icp_p2p_f32 (restates src/ICP_point_to_point.cu:295-423)" % (k_step, B)
+        extra = {"registrations_per_sec": regs / dt}
+        step_text = "one pass over the pairs (CPU: a bounded sample of %d pairs per step)" % k_step
+    else:
+        D, M = clouds_for(args)
+        n = D.shape[0]
+        mode = 1 if cfg["metric"] == P2PLANE else 0
+        # each step = one bounded sample: S sources x all targets, S sized for ~3 s of CPU work
+        rate0, _, _ = cpu_match_rate(orc, D, M, 1.0, mode)
+        S = int(max(256, min(n, (rate0 * 3.0 / M.shape[0]) // 256 * 256)))
+        sel = np.ascontiguousarray(D[:: max(1, n // S)][:S])
+        for _ in range(args.warmup):
+            orc.match(sel, M, mode)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            idx = orc.match(sel, M, mode)
+            mom = orc.moments(sel, M, idx)
+            orc.rt_from_moments(mom)
+        dt = time.perf_counter() - t0
+        value = float(S) * M.shape[0] * args.steps / dt
+        workload = workload_text(args, n, M.shape[0])
+        sample = ("%d of %d sources x all %d targets per step, oracle/icp_oracle.c orc_match_f32 (restates src/ICP_point_to_point.cu:31-57 "
+                  "= the float twin of src/ICP_CPU.c:220-234)" % (S, n, M.shape[0]))
+        extra = {"icp_iters_per_sec_extrapolated": value / (float(n) * M.shape[0])}
+        step_text = "one ICP iteration (CPU: matching on a bounded source sample + moments + SVD)"
     cores = orc.num_threads()
     if cores == 1 and (os.cpu_count() or 1) > 1:
         sys.stderr.write("bench.py: WARNING: the CPU arm ran on 1 thread of %d processors\n" % os.cpu_count())
@@ -150,15 +217,11 @@ def run_reference_arm(args, rank, emit):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic z=x^2-y^2, %dx%d points, point-to-point ICP, exact brute-force NN" % (n, M.shape[0]),
-                   "width": args.width, "step": "one ICP iteration (CPU: matching on a bounded source sample + moments + SVD)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of %d sources x all %d targets per step, oracle/icp_oracle.c orc_match_f32 "
-                                   "(restates src/ICP_point_to_point.cu:31-57 = the float twin of src/ICP_CPU.c:220-234), OpenMP %d threads"
-                                   % (S, n, M.shape[0], cores)},
+        "config": {"workload": workload, "config_id": args.config, "step": step_text},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + ", OpenMP %d threads" % cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "icp_iters_per_sec_extrapolated": value / (float(n) * M.shape[0]),
     }
+    line.update(extra)
     # the unmodified reference program (config 0: 100x100 points, double, 1 thread) for context
     exe = os.path.join(ROOT, "oracle", "_ref", "icp_cpu")
     if os.path.exists(exe) and not args.skip_ref_binary:
@@ -167,9 +230,9 @@ def run_reference_arm(args, rank, emit):
             out = subprocess.run([exe], capture_output=True, text=True, timeout=300).stdout
             wall = time.perf_counter() - t0
             import re
-            m = re.search(r"computed in ([\d.]+) ms with (\d+) iterations", out)
-            if m:
-                ms, its = float(m.group(1)), int(m.group(2))
+            mt = re.search(r"computed in ([\d.]+) ms with (\d+) iterations", out)
+            if mt:
+                ms, its = float(mt.group(1)), int(mt.group(2))
                 line["reference_binary"] = {"program": "src/ICP_CPU.c (unmodified, MKL shim, 1 thread, double)", "points": 10000,
                                             "iterations": its, "ms": ms, "nn_pairs_per_sec": (its + 1) * 1e8 / (ms * 1e-3), "wall_s": wall}
         except Exception as e:      # noqa: BLE001
@@ -177,102 +240,95 @@ def run_reference_arm(args, rank, emit):
     emit(line)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=1000, help="grid width W (W*W points per cloud); 1000 = BASELINE config 4")
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-ref-binary", action="store_true")
-    ap.add_argument("--skip-grid", action="store_true", help="do not run the extra whole-registration measurement with the exact grid variant (N=1)")
-    ap.add_argument("--balance", type=int, default=0, help="N > 1: 1 = deal source blocks in proportion to each GPU's measured matching rate (two extra untimed steps); 0 = even deal (B200s of one box measured within +-1.2 %, so this is off by default)")
-    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
-                    help="how the source is dealt to the ranks (N > 1): blocks of 2048 points round-robin, or contiguous ranges")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+class Env:
+    """Rank plumbing shared by the configurations: torch only for the device, the rendezvous and the clock sampling."""
 
-    # Libraries (NCCL's "NCCL version ..." banner, torchrun chatter) write to fd 1; the contract is ONE JSON line on
-    # stdout, so everything else is sent to stderr and the line is written to the saved descriptor at the end.
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
-    def emit(obj):
-        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+    def flush_l2(self):
+        self.flush_buf.fill_(1)
+        self.torch.cuda.synchronize()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    if args.impl == "reference":
-        run_reference_arm(args, rank, emit)
-        return
+    def _red(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
 
-    import torch
+    def allmax(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX if self.dist else None)
+
+    def allsum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM if self.dist else None)
+
+    def allmax_vec(self, v):
+        """element-wise max over ranks of a list of floats (per-step times: the step ends when the slowest rank ends)"""
+        if self.world == 1:
+            return list(v)
+        t = self.torch.tensor(list(v), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu().tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def run_stream_config(args, env, emit):
+    """Configurations 2, 3, 4: the streaming engine, one ICP iteration per step."""
+    import zlib
     import icp_b200 as ib
     import icp_dist
-    import icp_synth
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-        nccl_id = icp_dist.broadcast_bytes(ib.nccl_unique_id() if rank == 0 else None, 128)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    cfg = CONFIGS[args.config]
+    metric = cfg["metric"]
+    dmode = ib.DIST_SQRT if metric == P2PLANE else ib.DIST_SQ
+    rank, world, local_rank, dist = env.rank, env.world, env.local_rank, env.dist
+    nccl_id = icp_dist.broadcast_bytes(ib.nccl_unique_id() if rank == 0 else None, 128) if world > 1 else None
     ctx = ib.Context(local_rank, rank, world, nccl_id)
     clk_p, clk_f = clocks_start(local_rank) if rank == 0 else (None, None)     # seconds before the timed region, see clocks_stop
-    D, M = icp_synth.p2p_clouds(args.width)
+    D, M = clouds_for(args)
     n_total, m = D.shape[0], M.shape[0]
     if args.shard == "contiguous":
         lo, hi = icp_dist.shard_bounds(n_total, rank, world)
         shard_index = np.arange(lo, hi, dtype=np.int64)
-        shard = np.ascontiguousarray(D[lo:hi])
     else:                                   # blocks of 2048 sources dealt round-robin: balances the ranks' matching cost
         shard_index = icp_dist.shard_indices(n_total, rank, world)
-        shard = np.ascontiguousarray(D[shard_index])
+    shard = np.ascontiguousarray(D[shard_index])
     n_rank = shard.shape[0]
 
     fp32_peak = ctx.fp32_peak_tflops()
     ctx.set_target(M)
+    normals_ms = ctx.estimate_normals(4) if metric == P2PLANE else None
     ctx.set_source(shard)
     # the direct kernel (reference chain on every pair, no pruning) for comparison, outside the timed region
-    _, direct_ms = ctx.time_match(ib.DIST_SQ, ib.NN_BRUTE_DIRECT, reps=2)
-
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-
+    _, direct_ms = ctx.time_match(dmode, ib.NN_BRUTE_DIRECT, reps=2)
+    step_params = lambda: ib.default_params(metric=metric, dist_mode=dmode, max_iter=1, stop_early=0)
     step_errs_all = []                      # RMS after every step since the last source upload (warm-up included)
 
     def one_step():
-        flush_buf.fill_(1)
-        torch.cuda.synchronize()
-        err, res = ctx.run(ib.default_params(max_iter=1, stop_early=0))
+        env.flush_l2()
+        err, res = ctx.run(step_params())
         step_errs_all.append(float(err[1]))
         return res
 
@@ -282,7 +338,7 @@ def main():
     balance_weights = None
     if world > 1 and args.balance and args.shard != "contiguous":
         one_step(); r1 = one_step(); r2 = one_step()
-        speed = torch.zeros(world, dtype=torch.float64, device="cuda")
+        speed = env.torch.zeros(world, dtype=env.torch.float64, device="cuda")
         speed[rank] = float(n_rank) / max(1e-6, r1.match_ms + r2.match_ms)
         dist.all_reduce(speed)
         balance_weights = [float(v) for v in speed.cpu().tolist()]
@@ -293,7 +349,7 @@ def main():
         step_errs_all.clear()
     for _ in range(args.warmup):
         one_step()
-    barrier()
+    env.barrier()
     launches0 = ctx.launch_count()
     step_ms, match_ms = [], []
     t_epoch0 = time.time()
@@ -302,7 +358,7 @@ def main():
         res = one_step()
         step_ms.append(res.elapsed_ms); match_ms.append(res.match_ms)
     last_res = res
-    barrier()
+    env.barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
     clocks = clocks_stop(clk_p, clk_f, t_epoch0, time.time()) if rank == 0 else None
@@ -311,7 +367,6 @@ def main():
     # correspondence, the last transform, the error trajectory — is checksummed, and at N > 1 rank 0 replays the same
     # steps on ONE GPU (its own, full source) and the run FAILS unless the sharded run gave the same correspondences bit
     # for bit and the same errors / transform to FP64 summation-order noise.
-    import zlib
     idx_rank = ctx.correspondences()
     step_errs = np.array(step_errs_all, dtype=np.float32)
     parity = {"steps_checked": len(step_errs_all)}
@@ -323,10 +378,13 @@ def main():
             for sidx, sval in gathered:
                 idx_all[sidx] = sval
             with ib.Context(local_rank) as one:
-                one.set_target(M); one.set_source(D)
+                one.set_target(M)
+                if metric == P2PLANE:
+                    one.estimate_normals(4)
+                one.set_source(D)
                 errs1 = []
                 for _ in range(len(step_errs_all)):
-                    e1, r1 = one.run(ib.default_params(max_iter=1, stop_early=0))
+                    e1, r1 = one.run(step_params())
                     errs1.append(float(e1[1]))
                 idx1 = one.correspondences()
                 last_R1 = np.array(r1.last_R[:], np.float64)
@@ -342,47 +400,54 @@ def main():
     parity["errors_crc32"] = int(zlib.crc32(step_errs.tobytes()))
     parity["final_rms"] = float(step_errs[-1])
 
-    total_ms = allmax(sum(step_ms))
-    match_total_ms = allmax(sum(match_ms))
-    match_fastest_rank_ms = -allmax(-sum(match_ms))
-    launches_all = int(allsum(launches))
+    # a step ends when its slowest rank ends: per-step maximum over the ranks, then the sum over the K steps
+    total_ms = sum(env.allmax_vec(step_ms))
+    match_total_ms = sum(env.allmax_vec(match_ms))
+    match_fastest_rank_ms = -env.allmax(-sum(match_ms))
+    launches_all = int(env.allsum(launches))
     pairs_total = float(n_total) * m * args.steps
     value = pairs_total / (total_ms * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI entry point ------------------------------------------
+    torch = env.torch
     hD = torch.from_numpy(shard).pin_memory()
     hM = torch.from_numpy(M).pin_memory()
     hD_np, hM_np = hD.numpy(), hM.numpy()
     # every host buffer of the loop is pinned: the clouds that go up and the results that come down
     h_cur = [torch.empty_like(hD).pin_memory(), torch.empty_like(hD).pin_memory()]
     h_idx = torch.empty(shard.shape[0], dtype=torch.int32).pin_memory()
-    p = ib.default_params()
+    p = ib.default_params(metric=metric, dist_mode=dmode)
     # a genuine host-driven loop: every step uploads the CURRENT source and the target from pinned host memory, runs one
-    # iteration, and downloads the correspondences, the transform and the transformed source (which feeds the next step)
+    # iteration (point-to-plane: the target's normals are re-estimated, it is a new upload), and downloads the
+    # correspondences, the transform and the transformed source (which feeds the next step)
     idx, R, T, rms = ctx.iterate_host(p, hD_np, hM_np, idx_out=h_idx.numpy())            # warm
     cur = ctx.get_source(out=h_cur[0].numpy())
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for k in range(args.e2e_steps):
         idx, R, T, rms = ctx.iterate_host(p, cur, hM_np, idx_out=h_idx.numpy())
         cur = ctx.get_source(out=h_cur[(k + 1) & 1].numpy())
-    barrier()
-    e2e_s = allmax(time.perf_counter() - t0)
+    env.barrier()
+    e2e_s = env.allmax(time.perf_counter() - t0)
     e2e_value = float(n_total) * m * args.e2e_steps / e2e_s
-    h2d = allsum(float(shard.nbytes + M.nbytes))
-    d2h = allsum(float(idx.nbytes + R.nbytes + T.nbytes + 4 + cur.nbytes))
+    h2d = env.allsum(float(shard.nbytes + M.nbytes))
+    d2h = env.allsum(float(idx.nbytes + R.nbytes + T.nbytes + 4 + cur.nbytes))
 
     # per-GPU roofline of the dominant kernel (brute-force matching)
     pairs_rank = float(n_rank) * m * args.steps
     achieved = 8.0 * pairs_rank / (sum(match_ms) * 1e-3) * 1e-12
-    achieved = allmax(-achieved) * -1.0 if world > 1 else achieved      # the slowest rank's figure
+    achieved = env.allmax(-achieved) * -1.0 if world > 1 else achieved      # the slowest rank's figure
 
     fcfg = ctx.filter_config()
-    # Extra, outside every timed region and never allowed to disturb the contract line: the same registration from its
-    # initial pose to convergence with the exact uniform-grid variant (ICPB_NN_GRID: occupancy pyramid over the cells,
-    # identical correspondences), device time from the engine's events. One GPU only.
-    grid_extra = None
-    if world == 1 and not args.skip_grid:
+    used_filter = fcfg["dims_last"] in (2, 3)
+    # Extras, outside every timed region and never allowed to disturb the contract line (config 4, one GPU only):
+    #  (1) the same registration from its initial pose to convergence with the exact uniform-grid variant (ICPB_NN_GRID:
+    #      occupancy pyramid over the cells, identical correspondences), device time from the engine's events;
+    #  (2) the FLOOR of the headline rate: the filter's bound is as tight as the cloud lets it be — the saddle is a height
+    #      field and consecutive iterations give tight warm starts. Two clouds that are neither: uniform random points in
+    #      a cube, and a closed surface (noisy sphere), each matched against a slightly moved copy of itself.
+    grid_extra, floor_extra = None, None
+    if world == 1 and args.config == 4 and not args.skip_grid:
         try:
             ctx.set_source(shard)
             ctx.run(ib.default_params(max_iter=64, nn_method=ib.NN_GRID))        # builds the grid, warms up
@@ -394,25 +459,54 @@ def main():
                           "final_rms": float(g_err[g_res.iterations + 1])}
         except Exception as exc:      # noqa: BLE001
             grid_extra = {"error": str(exc)[:200]}
+    if world == 1 and args.config == 4 and not args.skip_floor:
+        try:
+            import icp_synth
+            floor_extra = {}
+            rng = np.random.default_rng(2024)
+            nf = n_total
+            vol = (rng.random((nf, 3)) * 4.0 - 2.0).astype(np.float32)
+            u = rng.normal(size=(nf, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+            sph = (u * (2.0 + 0.01 * rng.normal(size=(nf, 1)))).astype(np.float32)
+            Rm = icp_synth.euler_matrix([0.02, -0.02, 0.005])
+            for name, Q in (("random_volumetric", vol), ("noisy_sphere_surface", sph)):
+                P = icp_synth.rigid_move(Q, Rm, [0.02, -0.01, 0.015])
+                ctx.set_target(Q); ctx.set_source(P)
+                ctx.run(ib.default_params(max_iter=2, stop_early=0, sync_every=1))          # cold pass + one warm pass
+                e_f, r_f = ctx.run(ib.default_params(max_iter=3, stop_early=0, sync_every=1))
+                fc = ctx.filter_config()
+                floor_extra[name] = {"points": "%dx%d" % (nf, nf), "nn_pairs_per_sec": float(nf) * nf * r_f.iterations_run / (r_f.match_ms * 1e-3),
+                                     "match_ms_per_iteration": float(r_f.match_ms) / r_f.iterations_run, "bound_dims": fc["dims_last"],
+                                     "exact_fraction": fc["last_exact_fraction"]}
+            floor_extra["what"] = ("k1_filter on clouds that are not height fields (3 warm iterations each, device time of the matching kernel); "
+                                   "non-finite or denormal-range inputs fall to the direct kernel: roofline_direct_kernel below")
+            ctx.set_target(M); ctx.set_source(shard)
+        except Exception as exc:      # noqa: BLE001
+            floor_extra = {"error": str(exc)[:200]}
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
-        traffic = tj.get("k1_filter", {}).get(str(args.width))
+        traffic = tj.get("k1_filter", {}).get(str(args.width or cfg["width"]))
     except Exception:      # noqa: BLE001
         pass
     if rank == 0:
+        fma_per_pair = fcfg["dims_last"] if used_filter else 3
+        executed_frac = (achieved / 8.0) * (fma_per_pair * 2.0 if used_filter else 12.0) / fp32_peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic z=x^2-y^2, %dx%d points, point-to-point ICP, exact brute-force NN (BASELINE configs[3])" % (n_total, m),
-                       "width": args.width, "step": "one ICP iteration: matching + moments + 3x3 SVD + transform + error",
-                       "parallelism": "source sharded x%d (%s), target replicated, 16 FP64 moment sums %s" % (
-                           world, "contiguous shards" if args.shard == "contiguous" else "blocks of 2048 points dealt round-robin", "exchanged inside the reduction kernels over NVLink peer memory (no collective launch)" if ctx.dist_info()["peer_exchange"]
+            "config": {"workload": workload_text(args, n_total, m), "config_id": args.config,
+                       "step": "one ICP iteration: matching + moments + %s + transform + error" % ("6x6 Cholesky solve" if metric == P2PLANE else "3x3 SVD"),
+                       "parallelism": "source sharded x%d (%s), target replicated, %d FP64 moment sums %s" % (
+                           world, "contiguous shards" if args.shard == "contiguous" else "blocks of 2048 points dealt round-robin", 28 if metric == P2PLANE else 16,
+                           "exchanged inside the reduction kernels over NVLink peer memory (no collective launch)" if ctx.dist_info()["peer_exchange"]
                            else ("combined with ncclAllReduce" if world > 1 else "(single GPU: no exchange)")),
-                       "l2": "256 MiB device write between timed steps (untimed); timing = CUDA events per step on the engine stream"},
+                       "l2": "256 MiB device write between timed steps (untimed); timing = CUDA events per step on the engine stream, per-step max over ranks"},
             "icp_iters_per_sec": args.steps / (total_ms * 1e-3),
+            "normals_ms": normals_ms,
             "exact_grid_registration": grid_extra,
+            "non_height_field_floor": floor_extra,
             "match_ms_per_step": match_total_ms / args.steps,
             "match_ms_per_step_fastest_rank": match_fastest_rank_ms / args.steps,
             "rank_balance": ({"weights": [w / (sum(balance_weights) / world) for w in balance_weights],
@@ -425,18 +519,17 @@ def main():
             "parity": parity,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "frac_executed": executed_frac,
+                         "frac_meaning": "frac = brute-force-equivalent (the ALGORITHMIC 8 FLOP per pair of SURVEY.md 8(d) / time / peak; can exceed 1 because the filter "
+                                         "kernel issues 2-3 FMAs per pair, not the direct form's 6 FP32 ops); frac_executed = FP32 lane-operations actually issued per pair "
+                                         "(filter: dims FMAs = 2*dims FLOP; direct kernel: 6 ops = 12 FLOP-slots) / time / peak = FMA-pipe utilisation",
                          "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
-                         "kernel": "k1_filter (brute-force NN: a %d-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)" % fcfg["dims_last"],
+                         "kernel": ("k1_filter (brute-force NN: a %d-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)" % fcfg["dims_last"])
+                                   if used_filter else "k1_match (the reference's chain on every pair)",
                          "flop_per_pair": 8, "filter": fcfg,
-                         "executed": {"fma_per_pair": fcfg["dims_last"], "min3_per_pair": 0.5,
-                                      "fma_pipe_frac": (achieved / 8.0) * fcfg["dims_last"] * 2.0 / fp32_peak,
-                                      "note": "FP32 work the filter actually executes per pair (exact re-evaluations of the few unexcluded sub-tiles not counted): "
-                                              "FMAs on the FMA pipe, half a 3-input min on the 16-lane ALU pipe; ncu shows the two pipes never overlapping in this loop"},
                          "traffic": traffic,
-                         "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "note": "compute-bound (FP32 issue slots); `achieved` counts the ALGORITHMIC 8 FLOP per pair SURVEY.md 8(d) defines, so frac can exceed 1: "
-                                 "the direct form executes 6 FP32 ops per pair (ceiling 66.7% of FFMA peak), the filter 3 (full bound) or 2 (planar bound) FMAs per pair"},
+                         "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"},
             "roofline_direct_kernel": {"kernel": "k1_match (reference chain on every pair)", "ms_per_launch": direct_ms,
                                        "achieved": 8.0 * float(n_rank) * m / (direct_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
                                        "frac": 8.0 * float(n_rank) * m / (direct_ms * 1e-3) * 1e-12 / fp32_peak},
@@ -445,13 +538,166 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle as orc
             orc.set_num_threads(0)             # all host cores, whatever OMP_NUM_THREADS says
-            rate, S, dt = cpu_match_rate(orc, D, M, args.cpu_seconds)
+            rate, S, dt = cpu_match_rate(orc, D, M, args.cpu_seconds, 1 if metric == P2PLANE else 0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                                     "sample": "%d of %d sources x all %d targets, %.1f s, oracle orc_match_f32 (OpenMP)" % (S, n_total, m, dt)}
         emit(line)
     ctx.close()
+
+
+def run_batched_config(args, env, emit):
+    """Configuration 5: 4096 independent pairs of 2048-point clouds dealt to the N GPUs (replicas, no communication);
+    a step = one pass over the rank's pairs, every pair registered to convergence inside one persistent kernel."""
+    import zlib
+    import icp_b200 as ib
+    import icp_dist
+    import icp_synth
+    cfg = CONFIGS[5]
+    torch = env.torch
+    rank, world, local_rank, dist = env.rank, env.world, env.local_rank, env.dist
+    B = args.batch or cfg["batch"]
+    ctx = ib.Context(local_rank)                       # replicas: every rank is a plain single-GPU context
+    clk_p, clk_f = clocks_start(local_rank) if rank == 0 else (None, None)
+    lo, hi = icp_dist.shard_bounds(B, rank, world)
+    S_all, T_all, r_all, t_all = icp_synth.batched_pairs(B, n=cfg["n"], width=cfg["width"])
+    S, T = np.ascontiguousarray(S_all[lo:hi]), np.ascontiguousarray(T_all[lo:hi])
+    b_rank, n, m = S.shape[0], S.shape[1], T.shape[1]
+    fp32_peak = ctx.fp32_peak_tflops()
+    prm = ib.default_params(max_iter=40)
+    dS, dT = torch.from_numpy(S).cuda(), torch.from_numpy(T).cuda()
+
+    def one_step():
+        env.flush_l2()
+        return ctx.run_batched_ptr(prm, b_rank, n, m, dS.data_ptr(), dT.data_ptr())
+
+    for _ in range(args.warmup):
+        one_step()
+    env.barrier()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    t_epoch0 = time.time()
+    for _ in range(args.steps):
+        errors, iters, R, tt, ms = one_step()
+        step_ms.append(ms)
+    env.barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = clocks_stop(clk_p, clk_f, t_epoch0, time.time()) if rank == 0 else None
+    total_ms = sum(env.allmax_vec(step_ms))
+    iters_run_rank = float(np.sum(iters.astype(np.int64) + 1))              # loop bodies executed (the converging one included)
+    pairs_step = env.allsum(iters_run_rank * n * m)
+    iters_step = env.allsum(iters_run_rank)
+    value = pairs_step * args.steps / (total_ms * 1e-3)
+    achieved = 8.0 * iters_run_rank * n * m * args.steps / (sum(step_ms) * 1e-3) * 1e-12
+    achieved = env.allmax(-achieved) * -1.0 if world > 1 else achieved
+
+    # parity: every pair recovers its generating pose; the batch is split-invariant (rank 0 re-registers the LAST rank's
+    # pairs on its own GPU and compares bits)
+    Rtrue = np.stack([icp_synth.euler_matrix(r_all[b]).astype(np.float64) for b in range(lo, hi)])
+    pose_err = float(max(np.abs(R - Rtrue).max(), np.abs(tt - t_all[lo:hi].astype(np.float64)).max()))
+    pose_err = env.allmax(pose_err)
+    parity = {"max_pose_error_vs_generator": pose_err, "iterations_min_max": [int(iters.min()), int(iters.max())],
+              "errors_crc32_rank0": int(zlib.crc32(errors.tobytes())), "iters_crc32_rank0": int(zlib.crc32(iters.tobytes()))}
+    if pose_err > 2e-5:
+        raise SystemExit("bench.py: batched registration did not recover the generating poses (max error %g)" % pose_err)
     if world > 1:
-        dist.destroy_process_group()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (lo, hi, errors, iters))
+        if rank == 0:
+            glo, ghi, gerr, git = gathered[-1]
+            e2, i2, _, _, _ = ctx.run_batched(prm, np.ascontiguousarray(S_all[glo:ghi]), np.ascontiguousarray(T_all[glo:ghi]))
+            same = bool(np.array_equal(i2, git) and np.array_equal(e2.view(np.uint32), gerr.view(np.uint32)))
+            parity["split_invariant_vs_rank0_replay"] = same
+            if not same:
+                raise SystemExit("bench.py: rank %d's pairs give different bits when registered on rank 0" % (world - 1))
+
+    # ---- e2e: pinned host clouds through icpb_run_batched (chunked upload streamed behind the running kernel) ----
+    hS, hT = torch.from_numpy(S).pin_memory(), torch.from_numpy(T).pin_memory()
+    ctx.run_batched(prm, hS.numpy(), hT.numpy())                              # warm (buffers, streams)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e_h, i_h, R_h, t_h, ms_h = ctx.run_batched(prm, hS.numpy(), hT.numpy())
+    env.barrier()
+    e2e_s = env.allmax(time.perf_counter() - t0)
+    e2e_value = pairs_step * args.e2e_steps / e2e_s
+    h2d = env.allsum(float(S.nbytes + T.nbytes))
+    d2h = env.allsum(float(e_h.nbytes + i_h.nbytes + R_h.nbytes + t_h.nbytes))
+    launches_all = int(env.allsum(launches))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batched registration: %d independent pairs of %d-point synthetic clouds, one ICP per CTA (BASELINE %s)" % (B, n, cfg["name"]),
+                       "config_id": 5, "step": "one pass over all pairs: every pair registered to convergence (max 40 iterations, tol 1e-6)",
+                       "parallelism": "replicas only: %d pairs per GPU x%d, no communication" % (b_rank, world),
+                       "poses": "splitmix64 seed 20240 stream b (SURVEY.md 8d)",
+                       "l2": "256 MiB device write between timed steps (untimed); timing = CUDA events around the kernel, per-step max over ranks"},
+            "registrations_per_sec": B * args.steps / (total_ms * 1e-3),
+            "icp_iters_per_sec": iters_step * args.steps / (total_ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "icpb_run_batched (pinned host clouds in; errors, iteration counts, R, t out); upload in chunks of 32 pairs streamed behind the running kernel",
+                    "steps": args.e2e_steps, "registrations_per_sec": B * args.e2e_steps / e2e_s, "wall_ms_per_step": 1e3 * e2e_s / args.e2e_steps},
+            "gpu_launches": launches_all,
+            "parity": parity,
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "frac_executed": (achieved / 8.0) * 6.0 / fp32_peak,
+                         "frac_meaning": "frac = brute-force-equivalent 8 FLOP per (source,target) pair per executed ICP iteration; frac_executed = the 3-FMA bound the filter issues per pair",
+                         "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak)",
+                         "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
+                         "kernel": "icp_batched_filter_kernel (K9F: whole ICP loop per CTA, 3-FMA lower-bound filter + exact chain)", "flop_per_pair": 8, "traffic": None},
+        }
+        if world == 1 and not args.skip_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as orc
+            orc.set_num_threads(0)
+            rate, k, dt = cpu_batched_rate(orc, S_all, T_all, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                                    "sample": "%d of %d pairs registered to convergence, %.1f s, oracle orc_icp_p2p_f32 (OpenMP matching)" % (k, B, dt)}
+        emit(line)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5], help="BASELINE.json configuration (1-based): 4 = 1M x 1M point-to-point (default)")
+    ap.add_argument("--width", type=int, default=0, help="override the grid width W (W*W points per cloud) of configs 2-4")
+    ap.add_argument("--batch", type=int, default=0, help="override the number of pairs of config 5")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-ref-binary", action="store_true")
+    ap.add_argument("--skip-grid", action="store_true", help="do not run the extra whole-registration measurement with the exact grid variant (config 4, N=1)")
+    ap.add_argument("--skip-floor", action="store_true", help="do not run the extra k1_filter measurements on non-height-field clouds (config 4, N=1)")
+    ap.add_argument("--balance", type=int, default=0, help="N > 1: 1 = deal source blocks in proportion to each GPU's measured matching rate (two extra untimed steps); 0 = even deal (B200s of one box measured within +-1.2 %, so this is off by default)")
+    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
+                    help="how the source is dealt to the ranks (N > 1): blocks of 2048 points round-robin, or contiguous ranges")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    # Libraries (NCCL's "NCCL version ..." banner, torchrun chatter) write to fd 1; the contract is ONE JSON line on
+    # stdout, so everything else is sent to stderr and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
+    if args.impl == "reference":
+        run_reference_arm(args, int(os.environ.get("RANK", "0")), emit)
+        return
+    env = Env(args)
+    if args.config == 5:
+        run_batched_config(args, env, emit)
+    else:
+        run_stream_config(args, env, emit)
+    env.close()
 
 
 if __name__ == "__main__":

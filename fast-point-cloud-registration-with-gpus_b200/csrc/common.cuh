@@ -33,7 +33,7 @@ struct IterState {
 	int    max_iter;
 	int    stop_early;
 	int    flags;         // ICPB_FLAG_*
-	int    pad0;
+	int    count_slot;    // moments[count_slot] = number of points that entered the sums (15 point-to-point, 27 point-to-plane)
 	double tol;
 	double n_total;       // global number of source points (all ranks)
 	double moments[32];   // reduced moment sums (16 point-to-point, 28 point-to-plane)
@@ -84,6 +84,7 @@ struct ReduceParams {
 	int          fuse_tail;                               // the last block also runs the solve / bookkeeping (single GPU, or
 	                                                      // several GPUs with the peer-memory exchange fused in)
 	int          metric;
+	int          flags;                                   // ICPB_FLAG_* of the run
 	PeerXchg     peer;                                    // peer.world > 1: exchange the sums inside the last block
 };
 
@@ -242,6 +243,7 @@ struct Ctx {
 	int err_cap = 0;
 	float* errors_host = nullptr;// pinned
 	bool   step_state_ready = false;
+	int    run_flags = 0;        // ICPB_FLAG_* of the current run (step-wise API: 0)
 
 	// K1 configuration
 	int k1_cfg = 6;              // index into the K1 tuning table (nn_bruteforce.cu); 6 = best measured on B200

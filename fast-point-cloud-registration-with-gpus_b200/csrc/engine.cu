@@ -60,6 +60,8 @@ static int reset_state(Ctx* c, const icpb_params* p)
 	IterState* h = c->st_host;
 	memset(h, 0, sizeof *h);
 	h->max_iter = p->max_iter; h->stop_early = p->stop_early; h->tol = p->tol; h->flags = p->flags;
+	h->count_slot = (p->metric == ICPB_POINT_TO_PLANE) ? 27 : 15;
+	c->run_flags = p->flags;
 	h->n_total = (double)c->n;
 	for (int k = 0; k < 9; k++) h->Rtot[k] = (k % 4 == 0) ? 1.0 : 0.0;
 	for (int k = 0; k < 9; k++) h->R[k] = (k % 4 == 0) ? 1.0f : 0.0f;
@@ -164,7 +166,7 @@ int create_context(Ctx** out, int device)
 	snprintf(c->name, sizeof c->name, "%s", prop.name);
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICPB_ERR_CUDA; }
 	for (int k = 0; k < 4; k++) cudaEventCreate(&c->ev[k]);
-	c->reduce_grid = c->sm_count * 4;
+	c->reduce_grid = c->sm_count * 8;
 	if (cudaMalloc((void**)&c->st, sizeof(IterState)) != cudaSuccess ||
 	    cudaMallocHost((void**)&c->st_host, sizeof(IterState)) != cudaSuccess ||
 	    cudaMalloc((void**)&c->partials, sizeof(double) * 32 * (size_t)c->reduce_grid) != cudaSuccess) {

@@ -192,11 +192,11 @@ __global__ void pyr_up_kernel(const unsigned char* __restrict__ child, int nxc, 
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= (long long)nxp * nyp * nzp) return;
 	const int x = (int)(i % nxp), y = (int)((i / nxp) % nyp), z = (int)(i / ((long long)nxp * nyp));
-	unsigned char o = 0;
+	unsigned char o = 0;               // bit k = child k (x + 2y + 4z) is occupied: one load tells the descent which children to test
 #pragma unroll
 	for (int k = 0; k < 8; k++) {
 		const int cx = 2 * x + (k & 1), cy = 2 * y + ((k >> 1) & 1), cz = 2 * z + ((k >> 2) & 1);
-		if (cx < nxc && cy < nyc && cz < nzc) o |= child[(long long)cx + (long long)nxc * ((long long)cy + (long long)nyc * cz)];
+		if (cx < nxc && cy < nyc && cz < nzc && child[(long long)cx + (long long)nxc * ((long long)cy + (long long)nyc * cz)]) o |= (unsigned char)(1u << k);
 	}
 	parent[i] = o;
 }

@@ -21,6 +21,7 @@
 namespace icpb {
 
 constexpr int RB = 256;   // threads per block of the reduction kernels
+constexpr int RP = 4;     // consecutive points per thread and pass: 16-byte loads of the SoA arrays, 4 gathers in flight
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -47,10 +48,19 @@ template <int NV> __device__ __forceinline__ void block_reduce(double (&v)[NV], 
 	}
 }
 
-// The last block to finish sums the per-block rows in block order (deterministic).
+// The last block to finish sums the per-block rows in a FIXED order (deterministic: bitwise reproducible results for a
+// given point count). ncu on the r1 kernels showed where their time went: a 100k-point launch took 33 us and a 1M-point
+// one 55 us — a ~30 us floor that was this sum done by NV threads over up to 592 rows, one dependent L2 round trip
+// after the other. Here all RB threads take part: the rows are dealt to RB / NVP groups (NVP = NV rounded up to a power
+// of two, lane = value index), every group adds its rows in ascending order with 8 independent loads in flight, and the
+// group sums are then added in group order.
 template <int NV> __device__ __forceinline__ bool last_block_sum(double* partials, int* ticket, double* dst)
 {
+	constexpr int NVP = NV <= 1 ? 1 : (NV <= 16 ? 16 : 32);
+	constexpr int GROUPS = RB / NVP;
+	static_assert(NV <= 32, "one lane per value");
 	__shared__ int is_last;
+	__shared__ double gsum[GROUPS * NVP];
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -60,10 +70,27 @@ template <int NV> __device__ __forceinline__ bool last_block_sum(double* partial
 	__syncthreads();
 	if (!is_last) return false;
 	__threadfence();
+	const int grp = threadIdx.x / NVP, v = threadIdx.x % NVP;
+	double s = 0.0;
+	if (v < NV) {
+		const unsigned nrows = gridDim.x;
+		unsigned b = grp;
+		for (; b + 7 * GROUPS < nrows; b += 8 * GROUPS) {
+			double t[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) t[k] = __ldcg(partials + (size_t)(b + k * GROUPS) * 32 + v);
+#pragma unroll
+			for (int k = 0; k < 8; k++) s += t[k];
+		}
+		for (; b < nrows; b += GROUPS) s += __ldcg(partials + (size_t)b * 32 + v);
+	}
+	gsum[grp * NVP + v] = s;
+	__syncthreads();
 	if (threadIdx.x < NV) {
-		double s = 0.0;
-		for (unsigned b = 0; b < gridDim.x; b++) s += partials[(size_t)b * 32 + threadIdx.x];
-		dst[threadIdx.x] = s;
+		double t = 0.0;
+#pragma unroll 8
+		for (int g = 0; g < GROUPS; g++) t += gsum[g * NVP + threadIdx.x];
+		dst[threadIdx.x] = t;
 	}
 	if (threadIdx.x == 0) *ticket = 0;
 	__syncthreads();
@@ -79,38 +106,71 @@ __global__ void solve_kernel(IterState* st, int metric)
 // ------------------------------------------------------------------------------------------------
 // K2 / K7: moment accumulation
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int resolve_idx(const ReduceParams& p, int i)
+// Correspondences of RP consecutive points: keys -> idx (+ seed), then the gathers. A source whose every distance was
+// >= sentinel keeps its previous correspondence (src/ICP_point_to_point.cu:51-55 leaves idx[i] unwritten) — or, with
+// ICPB_FLAG_REJECT_UNMATCHED, is marked -1 and dropped from the sums.
+struct Corr4 { int j[RP]; bool use[RP]; };
+
+__device__ __forceinline__ Corr4 resolve4(const ReduceParams& p, int i0, bool reject)
 {
-	// A source whose every distance was >= sentinel keeps its previous correspondence
-	// (src/ICP_point_to_point.cu:51-55 leaves idx[i] unwritten).
-	const u64 key = p.keys[i];
-	int j = p.idx[i];
-	if (key != KEY_UNMATCHED) { j = (int)(uint32_t)(key & 0xffffffffull); p.idx[i] = j; p.seed[i] = j; }
-	return j;
+	Corr4 c;
+	const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(p.keys + i0), k23 = *reinterpret_cast<const ulonglong2*>(p.keys + i0 + 2);
+	const u64 key[RP] = { k01.x, k01.y, k23.x, k23.y };
+	const int4 old = *reinterpret_cast<const int4*>(p.idx + i0);
+	const int prev[RP] = { old.x, old.y, old.z, old.w };
+	int out[RP];
+	bool any_new = false;
+#pragma unroll
+	for (int r = 0; r < RP; r++) {
+		const bool in = i0 + r < p.n;
+		const bool hit = key[r] != KEY_UNMATCHED;
+		int j = hit ? (int)(uint32_t)(key[r] & 0xffffffffull) : (reject ? -1 : prev[r]);
+		out[r] = in ? j : prev[r];
+		c.j[r] = j; c.use[r] = in && j >= 0;
+		any_new |= in && hit;
+	}
+	if (any_new || reject) {
+		*reinterpret_cast<int4*>(p.idx + i0) = make_int4(out[0], out[1], out[2], out[3]);
+		const int4 sd = *reinterpret_cast<const int4*>(p.seed + i0);
+		int so[RP] = { sd.x, sd.y, sd.z, sd.w };
+#pragma unroll
+		for (int r = 0; r < RP; r++) if (i0 + r < p.n && key[r] != KEY_UNMATCHED) so[r] = out[r];
+		*reinterpret_cast<int4*>(p.seed + i0) = make_int4(so[0], so[1], so[2], so[3]);
+	}
+	return c;
 }
 
 __global__ void __launch_bounds__(RB) moments_p2p_kernel(const ReduceParams p)
 {
 	if (p.st->done) return;
-	__shared__ double red[(RB / 32) * 15];
-	double acc[15];
+	__shared__ double red[(RB / 32) * 16];
+	double acc[16];
 #pragma unroll
-	for (int k = 0; k < 15; k++) acc[k] = 0.0;
-	for (int i = blockIdx.x * RB + threadIdx.x; i < p.n; i += gridDim.x * RB) {
-		const int j = resolve_idx(p, i);
-		const float4 q = __ldg(p.q4 + j);
-		const double x = p.px[i], y = p.py[i], z = p.pz[i];
-		const double qx = q.x, qy = q.y, qz = q.z;
-		acc[0] += x; acc[1] += y; acc[2] += z;
-		acc[3] += qx; acc[4] += qy; acc[5] += qz;
-		acc[6] += qx * x; acc[7] += qy * x; acc[8] += qz * x;      // column 0 of sum q p^T (rows = q)
-		acc[9] += qx * y; acc[10] += qy * y; acc[11] += qz * y;
-		acc[12] += qx * z; acc[13] += qy * z; acc[14] += qz * z;
+	for (int k = 0; k < 16; k++) acc[k] = 0.0;
+	const bool reject = (p.flags & ICPB_FLAG_REJECT_UNMATCHED) != 0;
+	for (int i0 = RP * (blockIdx.x * RB + threadIdx.x); i0 < p.n; i0 += RP * gridDim.x * RB) {
+		const Corr4 c = resolve4(p, i0, reject);
+		float4 q[RP];
+#pragma unroll
+		for (int r = 0; r < RP; r++) q[r] = c.use[r] ? __ldg(p.q4 + c.j[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+		const float4 X = *reinterpret_cast<const float4*>(p.px + i0), Y = *reinterpret_cast<const float4*>(p.py + i0), Z = *reinterpret_cast<const float4*>(p.pz + i0);
+		const float xs[RP] = { X.x, X.y, X.z, X.w }, ys[RP] = { Y.x, Y.y, Y.z, Y.w }, zs[RP] = { Z.x, Z.y, Z.z, Z.w };
+#pragma unroll
+		for (int r = 0; r < RP; r++) {
+			if (!c.use[r]) continue;
+			const double x = xs[r], y = ys[r], z = zs[r];
+			const double qx = q[r].x, qy = q[r].y, qz = q[r].z;
+			acc[0] += x; acc[1] += y; acc[2] += z;
+			acc[3] += qx; acc[4] += qy; acc[5] += qz;
+			acc[6] += qx * x; acc[7] += qy * x; acc[8] += qz * x;      // column 0 of sum q p^T (rows = q)
+			acc[9] += qx * y; acc[10] += qy * y; acc[11] += qz * y;
+			acc[12] += qx * z; acc[13] += qy * z; acc[14] += qz * z;
+			acc[15] += 1.0;                                             // N: the points that entered the sums
+		}
 	}
 	double* row = p.partials + (size_t)blockIdx.x * 32;
-	block_reduce<15>(acc, red, row);
-	if (last_block_sum<15>(p.partials, &p.st->ticket_a, p.st->moments)) {
-		if (threadIdx.x == 0) p.st->moments[15] = (double)p.n;
+	block_reduce<16>(acc, red, row);
+	if (last_block_sum<16>(p.partials, &p.st->ticket_a, p.st->moments)) {
 		bool ok = true;
 		if (p.peer.world > 1) { __syncthreads(); ok = peer_allreduce_block(p.peer, p.st->moments, 16); }
 		if (threadIdx.x == 0) {
@@ -125,33 +185,46 @@ __global__ void __launch_bounds__(RB) moments_p2p_kernel(const ReduceParams p)
 __global__ void __launch_bounds__(RB) moments_p2plane_kernel(const ReduceParams p)
 {
 	if (p.st->done) return;
-	__shared__ double red[(RB / 32) * 27];
-	double acc[27];
+	__shared__ double red[(RB / 32) * 28];
+	double acc[28];
 #pragma unroll
-	for (int k = 0; k < 27; k++) acc[k] = 0.0;
-	for (int i = blockIdx.x * RB + threadIdx.x; i < p.n; i += gridDim.x * RB) {
-		const int j = resolve_idx(p, i);
-		const float4 q = __ldg(p.q4 + j), nn = __ldg(p.nrm4 + j);
-		const float x = p.px[i], y = p.py[i], z = p.pz[i];
-		float v[6];
-		v[0] = __fmaf_rn(y, nn.z, -__fmul_rn(z, nn.y));
-		v[1] = __fmaf_rn(z, nn.x, -__fmul_rn(x, nn.z));
-		v[2] = __fmaf_rn(nn.y, x, -__fmul_rn(y, nn.x));
-		v[3] = nn.x; v[4] = nn.y; v[5] = nn.z;
-		int k = 0;
+	for (int k = 0; k < 28; k++) acc[k] = 0.0;
+	const bool reject = (p.flags & ICPB_FLAG_REJECT_UNMATCHED) != 0;
+	for (int i0 = RP * (blockIdx.x * RB + threadIdx.x); i0 < p.n; i0 += RP * gridDim.x * RB) {
+		const Corr4 c = resolve4(p, i0, reject);
+		float4 q[RP], nv[RP];
 #pragma unroll
-		for (int r = 0; r < 6; r++)
+		for (int r = 0; r < RP; r++) {
+			q[r] = c.use[r] ? __ldg(p.q4 + c.j[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+			nv[r] = c.use[r] ? __ldg(p.nrm4 + c.j[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		const float4 X = *reinterpret_cast<const float4*>(p.px + i0), Y = *reinterpret_cast<const float4*>(p.py + i0), Z = *reinterpret_cast<const float4*>(p.pz + i0);
+		const float xs[RP] = { X.x, X.y, X.z, X.w }, ys[RP] = { Y.x, Y.y, Y.z, Y.w }, zs[RP] = { Z.x, Z.y, Z.z, Z.w };
 #pragma unroll
-			for (int c = r; c < 6; c++) acc[k++] += (double)__fmul_rn(v[r], v[c]);
-		const float d0 = __fsub_rn(x, q.x), d1 = __fsub_rn(y, q.y), d2 = __fsub_rn(z, q.z);
-		const float aux = __fmaf_rn(nn.z, d2, __fmaf_rn(nn.x, d0, __fmul_rn(nn.y, d1)));
+		for (int r = 0; r < RP; r++) {
+			if (!c.use[r]) continue;
+			const float x = xs[r], y = ys[r], z = zs[r];
+			const float4 nn = nv[r];
+			float v[6];
+			v[0] = __fmaf_rn(y, nn.z, -__fmul_rn(z, nn.y));
+			v[1] = __fmaf_rn(z, nn.x, -__fmul_rn(x, nn.z));
+			v[2] = __fmaf_rn(nn.y, x, -__fmul_rn(y, nn.x));
+			v[3] = nn.x; v[4] = nn.y; v[5] = nn.z;
+			int k = 0;
 #pragma unroll
-		for (int r = 0; r < 6; r++) acc[21 + r] += (double)__fmul_rn(v[r], -aux);
+			for (int a = 0; a < 6; a++)
+#pragma unroll
+				for (int b = a; b < 6; b++) acc[k++] += (double)__fmul_rn(v[a], v[b]);
+			const float d0 = __fsub_rn(x, q[r].x), d1 = __fsub_rn(y, q[r].y), d2 = __fsub_rn(z, q[r].z);
+			const float aux = __fmaf_rn(nn.z, d2, __fmaf_rn(nn.x, d0, __fmul_rn(nn.y, d1)));
+#pragma unroll
+			for (int a = 0; a < 6; a++) acc[21 + a] += (double)__fmul_rn(v[a], -aux);
+			acc[27] += 1.0;
+		}
 	}
 	double* row = p.partials + (size_t)blockIdx.x * 32;
-	block_reduce<27>(acc, red, row);
-	if (last_block_sum<27>(p.partials, &p.st->ticket_a, p.st->moments)) {
-		if (threadIdx.x == 0) p.st->moments[27] = (double)p.n;
+	block_reduce<28>(acc, red, row);
+	if (last_block_sum<28>(p.partials, &p.st->ticket_a, p.st->moments)) {
 		bool ok = true;
 		if (p.peer.world > 1) { __syncthreads(); ok = peer_allreduce_block(p.peer, p.st->moments, 28); }
 		if (threadIdx.x == 0) {
@@ -166,8 +239,9 @@ __global__ void __launch_bounds__(RB) moments_p2plane_kernel(const ReduceParams 
 // ------------------------------------------------------------------------------------------------
 __device__ void finish_iteration(IterState* st, float* errors)
 {
-	// src/ICP_point_to_point.cu:415-422
-	const float err = (float)(sqrt(st->err_sum) / sqrt(st->n_total));
+	// src/ICP_point_to_point.cu:415-422; with ICPB_FLAG_REJECT_UNMATCHED the RMS is over the points that were matched
+	const double npts = (st->flags & ICPB_FLAG_REJECT_UNMATCHED) ? fmax(st->moments[st->count_slot], 1.0) : st->n_total;
+	const float err = (float)(sqrt(st->err_sum) / sqrt(npts));
 	const int it = st->iteration;
 	errors[it + 1] = err;
 	st->last_err = err;
@@ -189,21 +263,49 @@ __global__ void __launch_bounds__(RB) transform_kernel(const ReduceParams p)
 {
 	if (p.st->done) return;
 	__shared__ double red[(RB / 32) * 1];
+	double acc[1] = { 0.0 };
+	const int i_first = RP * (blockIdx.x * RB + threadIdx.x);
+	// everything that does not depend on this iteration's R,T is loaded first (with programmatic dependent launch this
+	// part overlaps the tail of the moments kernel: the last-block sum and the 3x3 / 6x6 solve)
+	float4 X = make_float4(0.f, 0.f, 0.f, 0.f), Y = X, Z = X;
+	int4 J = make_int4(-1, -1, -1, -1);
+	if (i_first < p.n) {
+		X = *reinterpret_cast<const float4*>(p.px + i_first); Y = *reinterpret_cast<const float4*>(p.py + i_first); Z = *reinterpret_cast<const float4*>(p.pz + i_first);
+		J = *reinterpret_cast<const int4*>(p.idx + i_first);
+	}
 	const float* R = p.st->R; const float* T = p.st->T;
 	const float r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6], r7 = R[7], r8 = R[8];
 	const float t0 = T[0], t1 = T[1], t2 = T[2];
-	double acc[1] = { 0.0 };
-	for (int i = blockIdx.x * RB + threadIdx.x; i < p.n; i += gridDim.x * RB) {
-		const float x = p.px[i], y = p.py[i], z = p.pz[i];
-		// RyT (src/ICP_point_to_point.cu:85-87) as nvcc schedules it: FMUL (R[.,1]*y), FFMA (R[.,0]*x), FFMA (R[.,2]*z), FADD T
-		const float nx = __fadd_rn(__fmaf_rn(r6, z, __fmaf_rn(r0, x, __fmul_rn(r3, y))), t0);
-		const float ny = __fadd_rn(__fmaf_rn(r7, z, __fmaf_rn(r1, x, __fmul_rn(r4, y))), t1);
-		const float nz = __fadd_rn(__fmaf_rn(r8, z, __fmaf_rn(r2, x, __fmul_rn(r5, y))), t2);
-		p.ox[i] = nx; p.oy[i] = ny; p.oz[i] = nz;
-		const float4 q = __ldg(p.q4 + p.idx[i]);
-		const float ex = __fsub_rn(nx, q.x), ey = __fsub_rn(ny, q.y), ez = __fsub_rn(nz, q.z);
-		acc[0] += (double)ex * (double)ex + (double)ey * (double)ey + (double)ez * (double)ez;
-		p.keys[i] = KEY_UNMATCHED;   // arm the next matching step
+	for (int i0 = i_first; i0 < p.n; i0 += RP * gridDim.x * RB) {
+		if (i0 != i_first) {
+			X = *reinterpret_cast<const float4*>(p.px + i0); Y = *reinterpret_cast<const float4*>(p.py + i0); Z = *reinterpret_cast<const float4*>(p.pz + i0);
+			J = *reinterpret_cast<const int4*>(p.idx + i0);
+		}
+		const int js[RP] = { J.x, J.y, J.z, J.w };
+		float4 q[RP];
+#pragma unroll
+		for (int r = 0; r < RP; r++) q[r] = (i0 + r < p.n && js[r] >= 0) ? __ldg(p.q4 + js[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+		const float xs[RP] = { X.x, X.y, X.z, X.w }, ys[RP] = { Y.x, Y.y, Y.z, Y.w }, zs[RP] = { Z.x, Z.y, Z.z, Z.w };
+		float ox[RP], oy[RP], oz[RP];
+#pragma unroll
+		for (int r = 0; r < RP; r++) {
+			const float x = xs[r], y = ys[r], z = zs[r];
+			// RyT (src/ICP_point_to_point.cu:85-87) as nvcc schedules it: FMUL (R[.,1]*y), FFMA (R[.,0]*x), FFMA (R[.,2]*z), FADD T
+			ox[r] = __fadd_rn(__fmaf_rn(r6, z, __fmaf_rn(r0, x, __fmul_rn(r3, y))), t0);
+			oy[r] = __fadd_rn(__fmaf_rn(r7, z, __fmaf_rn(r1, x, __fmul_rn(r4, y))), t1);
+			oz[r] = __fadd_rn(__fmaf_rn(r8, z, __fmaf_rn(r2, x, __fmul_rn(r5, y))), t2);
+			if (i0 + r < p.n && js[r] >= 0) {
+				const float ex = __fsub_rn(ox[r], q[r].x), ey = __fsub_rn(oy[r], q[r].y), ez = __fsub_rn(oz[r], q[r].z);
+				acc[0] += (double)ex * (double)ex + (double)ey * (double)ey + (double)ez * (double)ez;
+			}
+		}
+		// the arrays are padded to a block multiple: whole 16-byte stores, also across the end of the cloud (the padding
+		// holds transformed zeros, which nothing reads)
+		*reinterpret_cast<float4*>(p.ox + i0) = make_float4(ox[0], ox[1], ox[2], ox[3]);
+		*reinterpret_cast<float4*>(p.oy + i0) = make_float4(oy[0], oy[1], oy[2], oy[3]);
+		*reinterpret_cast<float4*>(p.oz + i0) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+		const ulonglong2 un = make_ulonglong2(KEY_UNMATCHED, KEY_UNMATCHED);     // arm the next matching step
+		*reinterpret_cast<ulonglong2*>(p.keys + i0) = un; *reinterpret_cast<ulonglong2*>(p.keys + i0 + 2) = un;
 	}
 	double* row = p.partials + (size_t)blockIdx.x * 32;
 	block_reduce<1>(acc, red, row);
@@ -286,11 +388,12 @@ static ReduceParams make_params(Ctx* c, int metric)
 	p.peer = c->peer;
 	p.fuse_tail = (c->world == 1 || c->peer.world > 1) ? 1 : 0;
 	p.metric = metric;
+	p.flags = c->run_flags;
 	return p;
 }
 static int reduce_grid_for(Ctx* c)
 {
-	int g = (c->n + RB - 1) / RB;
+	int g = (c->n + RB * RP - 1) / (RB * RP);      // RP consecutive points per thread and pass
 	if (g > c->reduce_grid) g = c->reduce_grid;
 	if (g < 1) g = 1;
 	return g;

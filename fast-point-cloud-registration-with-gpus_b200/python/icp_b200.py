@@ -14,7 +14,7 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "libicp_b200.so"))
 DIST_SQ, DIST_SQRT, DIST_STD = 0, 1, 2
 POINT_TO_POINT, POINT_TO_PLANE = 0, 1
 NN_BRUTE, NN_GRID, NN_BRUTE_DIRECT = 0, 1, 2
-FLAG_FIX_REFLECTION, FLAG_PROFILE, FLAG_GRAPH = 1, 2, 4
+FLAG_FIX_REFLECTION, FLAG_PROFILE, FLAG_GRAPH, FLAG_REJECT_UNMATCHED = 1, 2, 4, 8
 
 
 class Params(C.Structure):
@@ -276,6 +276,17 @@ class Context:
         t = np.zeros((batch, 3), dtype=np.float64)
         ms = C.c_float()
         self._ck(lib.icpb_run_batched(self.h, C.byref(params), batch, _ptr(sources), n, _ptr(targets), m,
+                                      _ptr(errors), _ptr(iters), _ptr(R), _ptr(t), C.byref(ms)), "run_batched")
+        return errors, iters, R, t, ms.value
+
+    def run_batched_ptr(self, params, batch, n, m, sources_ptr, targets_ptr):
+        """Same, with the clouds given as raw addresses (device pointers are used in place: the device-resident timing)."""
+        errors = np.zeros((batch, params.max_iter + 1), dtype=np.float32)
+        iters = np.zeros(batch, dtype=np.int32)
+        R = np.zeros((batch, 9), dtype=np.float64)
+        t = np.zeros((batch, 3), dtype=np.float64)
+        ms = C.c_float()
+        self._ck(lib.icpb_run_batched(self.h, C.byref(params), batch, C.c_void_p(sources_ptr), n, C.c_void_p(targets_ptr), m,
                                       _ptr(errors), _ptr(iters), _ptr(R), _ptr(t), C.byref(ms)), "run_batched")
         return errors, iters, R, t, ms.value
 

@@ -59,6 +59,12 @@ extern "C" {
                                         per pass, one GPU). Identical results; match_ms is then reported as 0. Pays off only
                                         when many registrations of one size reuse the instantiated graph. */
 
+#define ICPB_FLAG_REJECT_UNMATCHED 8   /* max-distance rejection: a source with no target below `sentinel` is dropped from the
+                                        moment sums and from the RMS of that iteration and reports correspondence -1, instead of
+                                        keeping its previous correspondence as the reference does (its LiDAR programs raise the
+                                        sentinel to 1e6 precisely because real scans have outliers,
+                                        src/CUDA/GPU_point_to_point_real.cu:18,44). The RMS is then over the matched points. */
+
 typedef struct icpb_ctx icpb_ctx;
 
 typedef struct icpb_params {

@@ -24,6 +24,18 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1), "the CPU arm must use every host core whatever OMP_NUM_THREADS says"
 
 
+def test_reference_arm_every_config():
+    """--config 2, 3, 5 of the CPU arm: one contract line each, naming the configuration it measured."""
+    for cfg, extra in ((2, ["--width", "48"]), (3, ["--width", "48"]), (5, ["--batch", "16"])):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", str(cfg), "--steps", "1", "--warmup", "0",
+                            "--skip-ref-binary"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["impl"] == "reference" and d["config"]["config_id"] == cfg and d["value"] > 0 and d["unit"] == "pairs/s"
+        assert ("batched" in d["config"]["workload"]) == (cfg == 5)
+        assert ("point-to-plane" in d["config"]["workload"]) == (cfg == 3)
+
+
 def test_gpu_arm_fails_loudly_without_a_device():
     import ctypes
     n = ctypes.c_int(0)

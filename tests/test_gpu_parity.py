@@ -359,3 +359,47 @@ def test_1m_full_registration_properties(ctx, ib, orc):
     assert np.abs(np.array(res.t[:]) - [0.8, -0.3, 0.2]).max() < 1e-5
     e = err[1: res.iterations_run + 1]
     assert np.all(np.diff(e) < 1e-6) and e[-1] < 1e-5
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("nn", ["brute", "grid"])
+def test_reject_unmatched_equals_registration_of_the_inliers(ib, orc, metric, nn):
+    """ICPB_FLAG_REJECT_UNMATCHED (the reference's LiDAR programs only raise the sentinel,
+    src/CUDA/GPU_point_to_point_real.cu:18,44): sources with no target below the sentinel are dropped from the moments
+    and from the RMS and report correspondence -1. With outliers that stay beyond the sentinel for the whole run, the
+    registration must be the registration of the inliers alone: same iteration count, same trajectory and transform (to
+    FP64 summation-order noise), same correspondences. Without the flag the same outliers keep correspondence 0 and
+    drag the transform (the reference's behaviour), which the test also checks."""
+    D, M = orc.synth_p2p(96)
+    rng = np.random.default_rng(31)
+    out_at = np.sort(rng.choice(D.shape[0], 300, replace=False))
+    P = D.copy()
+    P[out_at] += np.float32(60.0) + rng.random((300, 3)).astype(np.float32)          # far from everything, forever
+    keep = np.setdiff1d(np.arange(D.shape[0]), out_at)
+    mode = ib.DIST_SQRT if metric else ib.DIST_SQ
+    sentinel = 8.0 if metric else 64.0                                                # same radius in both distance domains
+    nnm = ib.NN_GRID if nn == "grid" else ib.NN_BRUTE
+    base = dict(metric=metric, dist_mode=mode, nn_method=nnm, max_iter=60, sentinel=sentinel)
+    with ib.Context(0) as ctx:
+        ctx.set_target(M)
+        if metric:
+            ctx.estimate_normals(4)
+        ctx.set_source(P)
+        e_r, r_r = ctx.run(ib.default_params(flags=ib.FLAG_REJECT_UNMATCHED, **base))
+        idx_r = ctx.correspondences()
+        ctx.set_source(np.ascontiguousarray(P[keep]))
+        e_i, r_i = ctx.run(ib.default_params(**base))
+        idx_i = ctx.correspondences()
+        if metric == 0:
+            ctx.set_source(P)
+            e_n, r_n = ctx.run(ib.default_params(**base))
+            idx_n = ctx.correspondences()
+    assert (r_r.iterations, r_r.iterations_run) == (r_i.iterations, r_i.iterations_run)
+    k = r_i.iterations + 2
+    assert np.all(np.abs(e_r[:k] - e_i[:k]) <= 1e-6 * np.abs(e_i[:k]) + 1e-7)
+    assert np.abs(np.array(r_r.R[:]) - np.array(r_i.R[:])).max() < 1e-8 and np.abs(np.array(r_r.t[:]) - np.array(r_i.t[:])).max() < 1e-8
+    assert np.array_equal(idx_r[keep], idx_i) and np.all(idx_r[out_at] == -1)
+    # the reference's rule: unmatched sources keep their previous correspondence (0 after the upload) and stay in the sums
+    if metric == 0:
+        assert np.all(idx_n[out_at] == 0)
+        assert np.abs(np.array(r_n.R[:]) - np.array(r_i.R[:])).max() > 1e-3

@@ -52,7 +52,7 @@ static HostGrid build(const std::vector<float>& Q)
 			unsigned char o = 0;
 			for (int i = 0; i < 8; i++) {
 				const int cx = 2 * x + (i & 1), cy = 2 * y + ((i >> 1) & 1), cz = 2 * z + ((i >> 2) & 1);
-				if (cx < nxc && cy < nyc && cz < nzc) o |= G.occ[(size_t)G.py.off[L - 1] + cx + (size_t)nxc * (cy + (size_t)nyc * cz)];
+				if (cx < nxc && cy < nyc && cz < nzc && G.occ[(size_t)G.py.off[L - 1] + cx + (size_t)nxc * (cy + (size_t)nyc * cz)]) o |= (unsigned char)(1u << i);
 			}
 			G.occ[(size_t)G.py.off[L] + x + (size_t)G.py.nx[L] * (y + (size_t)G.py.ny[L] * z)] = o;
 		}
@@ -85,7 +85,7 @@ static float sqrt_domain_threshold(float sentinel)
 }
 
 static int failures = 0;
-template <int MODE> static void check(const char* name, const std::vector<float>& P, const std::vector<float>& Q, float sentinel, bool warm)
+template <int MODE> static void check(const char* name, const std::vector<float>& P, const std::vector<float>& Q, float sentinel, int warm)
 {
 	HostGrid G = build(Q);
 	const int n = (int)P.size() / 3;
@@ -94,15 +94,30 @@ template <int MODE> static void check(const char* name, const std::vector<float>
 	for (int i = 0; i < n; i++) {
 		const u64 want = brute<MODE>(&P[3 * i], Q, sentinel);
 		u64 start = KEY_UNMATCHED;
-		if (warm) {                                   // warm start from an arbitrary real candidate (index i mod m)
-			const int j = i % (int)(Q.size() / 3);
+		if (warm) {                                   // warm start from a real candidate: 1 = arbitrary (index i mod m); 2 = the target next to the
+			                                          // answer (a tight bound: the near-field enumeration must still find the answer); 3 = the
+			                                          // HIGHEST-indexed target as close as the answer (a tie: equality must not prune the lower index)
+			int j = i % (int)(Q.size() / 3);
+			if (warm >= 2 && want != KEY_UNMATCHED) {
+				const int wj = (int)(unsigned)(want & 0xffffffffull), mq = (int)(Q.size() / 3);
+				j = (wj + 1) % mq;
+				if (warm == 3) {
+					unsigned wb = (unsigned)(want >> 32);
+					for (int t = mq - 1; t > wj; t--) {
+						float dt = gt_chain(P[3 * i], P[3 * i + 1], P[3 * i + 2], Q[3 * t], Q[3 * t + 1], Q[3 * t + 2]);
+						if (MODE == ICPB_DIST_SQRT) dt = sqrtf(dt);
+						unsigned tb; memcpy(&tb, &dt, 4);
+						if (tb == wb) { j = t; break; }
+					}
+				}
+			}
 			float d = gt_chain(P[3 * i], P[3 * i + 1], P[3 * i + 2], Q[3 * j], Q[3 * j + 1], Q[3 * j + 2]);
 			if (d < thr0) { if (MODE == ICPB_DIST_SQRT) d = sqrtf(d); unsigned db; memcpy(&db, &d, 4); start = ((u64)db << 32) | (u64)(unsigned)j; }
 		}
 		const u64 got = grid_tree_nn<MODE>(P[3 * i], P[3 * i + 1], P[3 * i + 2], G.g, G.py, G.cell_start.data(), G.sorted4.data(), thr0, start, &seen, &nodes);
 		if (got != want) { if (bad < 3) printf("  MISMATCH %s source %d: got %016llx want %016llx\n", name, i, (unsigned long long)got, (unsigned long long)want); bad++; }
 	}
-	printf("%-44s mode %d %s  grid %dx%dx%d levels %d  %6.1f points + %6.1f nodes per source (of %zu points)  %s\n", name, MODE, warm ? "warm" : "cold",
+	printf("%-44s mode %d %s  grid %dx%dx%d levels %d  %6.1f points + %6.1f nodes per source (of %zu points)  %s\n", name, MODE, warm == 0 ? "cold" : warm == 1 ? "warm" : warm == 2 ? "near" : "tie ",
 	       G.g.nx, G.g.ny, G.g.nz, G.py.levels, (double)seen / n, (double)nodes / n, Q.size() / 3, bad ? "FAIL" : "ok");
 	failures += bad;
 }
@@ -176,6 +191,10 @@ int main(int argc, char** argv)
 	for (int i = 0; i < 40; i++) for (int k = 0; k < 3; k++) P[3 * i + k] += 40.0f;
 	for (int i = 40; i < 50; i++) for (int k = 0; k < 3; k++) P[3 * i + k] -= 1e3f;
 	for (int warm = 0; warm < 2; warm++) { check<0>("lattice with ties, duplicates, outliers", P, Q, 100000.0f, warm); check<1>("lattice with ties, duplicates, outliers", P, Q, 100000.0f, warm); }
+	for (int warm = 2; warm <= 3; warm++) { check<0>("lattice with ties, duplicates, outliers", P, Q, 100000.0f, warm); check<1>("lattice with ties, duplicates, outliers", P, Q, 100000.0f, warm); }
+	check<0>("saddle, initial pose (far field)", Dsub, M, 100000.0f, 2);
+	check<1>("saddle, converged (near field)", Pn, M, 100000.0f, 2);
+	check<0>("saddle, converged (near field)", Pn, M, 100000.0f, 3);
 	// sentinel rule
 	std::normal_distribution<float> nd(0.f, 1.f);
 	std::vector<float> Qn(3 * 2000), Pw(3 * 600);
@@ -184,6 +203,8 @@ int main(int argc, char** argv)
 	check<0>("random cloud, sentinel 0.05", Pw, Qn, 0.05f, false);
 	check<1>("random cloud, sentinel 0.05", Pw, Qn, 0.05f, true);
 	check<0>("random cloud", Pw, Qn, 100000.0f, true);
+	check<0>("random cloud", Pw, Qn, 100000.0f, 2);
+	check<1>("random cloud, sentinel 0.05", Pw, Qn, 0.05f, 2);
 	// degenerate boxes
 	std::vector<float> line(3 * 300, 0.f), pl;
 	for (int j = 0; j < 300; j++) line[3 * j] = (float)j / 299.0f;
@@ -197,7 +218,7 @@ int main(int argc, char** argv)
 		std::vector<float> L(3 * 100000, 0.f), PL;
 		for (int j = 0; j < 100000; j++) { L[3 * j] = (float)j * 1e-3f; }
 		for (int j = 0; j < 100000; j += 331) { PL.push_back(L[3 * j] + 4e-4f); PL.push_back((j % 2) ? 0.0f : 0.01f); PL.push_back((j % 3) ? 0.0f : -0.02f); }
-		for (int warm = 0; warm < 2; warm++) { check<0>("100k collinear target", PL, L, 100000.0f, warm); check<1>("100k collinear target", PL, L, 100000.0f, warm); }
+		for (int warm = 0; warm < 3; warm++) { check<0>("100k collinear target", PL, L, 100000.0f, warm); check<1>("100k collinear target", PL, L, 100000.0f, warm); }
 		std::uniform_real_distribution<float> u(0.f, 1.f);
 		std::vector<float> T(3 * 100000), PT;
 		for (int j = 0; j < 100000; j++) { T[3 * j] = 200.0f * u(rng); T[3 * j + 1] = 0.01f * u(rng); T[3 * j + 2] = 0.01f * u(rng); }      // thin rod
@@ -222,6 +243,7 @@ int main(int argc, char** argv)
 	for (size_t k = 0; k < Qu.size(); k++) Qu[k] = Qu[k] + (k % 3 == 0 ? 1e6f : k % 3 == 1 ? -2.5e5f : 3e3f);
 	for (size_t k = 0; k < Pu.size(); k++) Pu[k] = Pu[k] + (k % 3 == 0 ? 1e6f : k % 3 == 1 ? -2.5e5f : 3e3f);
 	check<0>("unit cloud at (1e6,-2.5e5,3e3)", Pu, Qu, 3e38f, false);
+	check<0>("unit cloud at (1e6,-2.5e5,3e3)", Pu, Qu, 3e38f, 2);
 	check<1>("unit cloud at (1e6,-2.5e5,3e3)", Pu, Qu, 3e38f, true);
 	// sources exactly on cell faces and corners of the grid's frame
 	{
@@ -229,6 +251,7 @@ int main(int argc, char** argv)
 		std::vector<float> Pf;
 		for (int i = 0; i < 400; i++) { Pf.push_back(G.g.ox + (float)(i % 17) * G.g.h); Pf.push_back(G.g.oy + (float)((i / 3) % 15) * G.g.h); Pf.push_back(G.g.oz + (float)((i / 7) % 18) * G.g.h); }
 		check<0>("sources on cell faces / corners", Pf, Qn, 100000.0f, false);
+		check<0>("sources on cell faces / corners", Pf, Qn, 100000.0f, 2);
 		check<1>("sources on cell faces / corners", Pf, Qn, 100000.0f, true);
 	}
 	// non-finite sources

@@ -10,20 +10,72 @@ __device__ __forceinline__ u64 pack2(float a, float b){ u64 r; asm("mov.b64 %0, 
 __device__ __forceinline__ void unpack2(u64 v, float&a, float&b){ asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c){ u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ float min3(float a, float b, float c){ float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+// FORM 7: 2-D bound with the running minimum replaced by a threshold test accumulated in a PREDICATE per source
+//         (FSETP.LE.OR P_s, e, tau_s, P_s: tools/ubench_pipes.cu measured ~0.2 cycles per value against 1.2 per value pair
+//         for FMNMX3); the filter never needs the minimum itself, only "is any e~ <= tau".
+#define PRED_DECL() asm volatile(".reg .pred pq0, pq1, pq2, pq3, pq4, pq5, pq6, pq7;")
+template<int SIDX> __device__ __forceinline__ void pred_clear() {
+  if (SIDX==0) asm volatile("setp.ne.u32 pq0, 0, 0;"); if (SIDX==1) asm volatile("setp.ne.u32 pq1, 0, 0;");
+  if (SIDX==2) asm volatile("setp.ne.u32 pq2, 0, 0;"); if (SIDX==3) asm volatile("setp.ne.u32 pq3, 0, 0;");
+  if (SIDX==4) asm volatile("setp.ne.u32 pq4, 0, 0;"); if (SIDX==5) asm volatile("setp.ne.u32 pq5, 0, 0;");
+  if (SIDX==6) asm volatile("setp.ne.u32 pq6, 0, 0;"); if (SIDX==7) asm volatile("setp.ne.u32 pq7, 0, 0;");
+}
+template<int SIDX> __device__ __forceinline__ void pred_test(float e, float tau) {
+  if (SIDX==0) asm volatile("setp.le.or.f32 pq0, %0, %1, pq0;" :: "f"(e), "f"(tau)); if (SIDX==1) asm volatile("setp.le.or.f32 pq1, %0, %1, pq1;" :: "f"(e), "f"(tau));
+  if (SIDX==2) asm volatile("setp.le.or.f32 pq2, %0, %1, pq2;" :: "f"(e), "f"(tau)); if (SIDX==3) asm volatile("setp.le.or.f32 pq3, %0, %1, pq3;" :: "f"(e), "f"(tau));
+  if (SIDX==4) asm volatile("setp.le.or.f32 pq4, %0, %1, pq4;" :: "f"(e), "f"(tau)); if (SIDX==5) asm volatile("setp.le.or.f32 pq5, %0, %1, pq5;" :: "f"(e), "f"(tau));
+  if (SIDX==6) asm volatile("setp.le.or.f32 pq6, %0, %1, pq6;" :: "f"(e), "f"(tau)); if (SIDX==7) asm volatile("setp.le.or.f32 pq7, %0, %1, pq7;" :: "f"(e), "f"(tau));
+}
+template<int SIDX> __device__ __forceinline__ unsigned pred_read() {
+  unsigned r = 0;
+  if (SIDX==0) asm volatile("selp.u32 %0, 1, 0, pq0;" : "=r"(r)); if (SIDX==1) asm volatile("selp.u32 %0, 1, 0, pq1;" : "=r"(r));
+  if (SIDX==2) asm volatile("selp.u32 %0, 1, 0, pq2;" : "=r"(r)); if (SIDX==3) asm volatile("selp.u32 %0, 1, 0, pq3;" : "=r"(r));
+  if (SIDX==4) asm volatile("selp.u32 %0, 1, 0, pq4;" : "=r"(r)); if (SIDX==5) asm volatile("selp.u32 %0, 1, 0, pq5;" : "=r"(r));
+  if (SIDX==6) asm volatile("selp.u32 %0, 1, 0, pq6;" : "=r"(r)); if (SIDX==7) asm volatile("selp.u32 %0, 1, 0, pq7;" : "=r"(r));
+  return r;
+}
+template<int S, int SIDX> struct PredLoop {
+  static __device__ __forceinline__ void clear() { pred_clear<SIDX>(); PredLoop<S, SIDX+1>::clear(); }
+  static __device__ __forceinline__ void step(const float* ax, const float* ay, const float* tau, u64 x01, u64 x23, u64 y01, u64 y23, u64 w01, u64 w23) {
+    u64 AX=bcast2v(ax[SIDX]),AY=bcast2v(ay[SIDX]);
+    u64 e=fma2(AX,x01,fma2(AY,y01,w01)); float a,b; unpack2(e,a,b); pred_test<SIDX>(a,tau[SIDX]); pred_test<SIDX>(b,tau[SIDX]);
+    e=fma2(AX,x23,fma2(AY,y23,w23)); unpack2(e,a,b); pred_test<SIDX>(a,tau[SIDX]); pred_test<SIDX>(b,tau[SIDX]);
+    PredLoop<S, SIDX+1>::step(ax,ay,tau,x01,x23,y01,y23,w01,w23);
+  }
+  static __device__ __forceinline__ void read(float* m) { m[SIDX] += (float)pred_read<SIDX>(); PredLoop<S, SIDX+1>::read(m); }
+};
+template<int S> struct PredLoop<S, S> {
+  static __device__ __forceinline__ void clear() {}
+  static __device__ __forceinline__ void step(const float*, const float*, const float*, u64, u64, u64, u64, u64, u64) {}
+  static __device__ __forceinline__ void read(float*) {}
+};
 // FORM 0: scalar-broadcast a (R.F32), targets packed by pairs.   FORM 1: a kept as duplicated register pairs.
 // FORM 2: "transposed": TWO SOURCES packed per register pair, target coordinate broadcast (R.F32) -> min per source is a plain FMNMX on each half
 template<int S, int FORM, int TT> __global__ void __launch_bounds__(256,2) filt(const float4* __restrict__ tiles, int ntiles, const float* __restrict__ src, float* out)
 {
   extern __shared__ float4 sm[];
   float ax[S],ay[S],az[S],m[S];
+  if (FORM==7) PRED_DECL();
   #pragma unroll
-  for(int s=0;s<S;s++){ int i=(blockIdx.x*S+s)*256+threadIdx.x; ax[s]=src[3*i]; ay[s]=src[3*i+1]; az[s]=src[3*i+2]; m[s]=1e30f; }
+  for(int s=0;s<S;s++){ int i=(blockIdx.x*S+s)*256+threadIdx.x; ax[s]=src[3*i]; ay[s]=src[3*i+1]; az[s]=src[3*i+2]; m[s]=(FORM==7)?0.f:1e30f; }
   for (int t=0;t<ntiles;t++){
     __syncthreads();
     for (int i=threadIdx.x;i<TT;i+=256) sm[i]=tiles[(size_t)t*TT+i];
     __syncthreads();
     constexpr int NQ=TT/4;
-    if (FORM==3) {
+    if (FORM==7) {
+      // sub-tiles of 128 targets as in k1_filter: clear the predicates, 32 quads of tests, read them back
+      for (int sub=0; sub<TT/128; sub++) {
+        PredLoop<S,0>::clear();
+        #pragma unroll 2
+        for (int j=sub*32;j<sub*32+32;j++){
+          float4 X=sm[j],Y=sm[NQ+j],W=sm[3*NQ+j];
+          u64 x01=pack2(X.x,X.y),x23=pack2(X.z,X.w),y01=pack2(Y.x,Y.y),y23=pack2(Y.z,Y.w),w01=pack2(W.x,W.y),w23=pack2(W.z,W.w);
+          PredLoop<S,0>::step(ax,ay,az,x01,x23,y01,y23,w01,w23);        // az[] doubles as tau[]
+        }
+        PredLoop<S,0>::read(m);
+      }
+    } else if (FORM==3) {
       // scalar FFMA: 12 FFMA + 2 FMNMX3 per source x 4 targets
       constexpr int NQ2=TT/4;
       #pragma unroll 2
@@ -150,6 +202,10 @@ int main(){
   run<4,4,1024>(tiles,M,src,out,N,"2-D bound, packed");
   run<8,5,1024>(tiles,M,src,out,N,"2-D bound, scalar FFMA");
   run<16,5,1024>(tiles,M,src,out,N,"2-D bound, scalar FFMA");
+  run<8,7,1024>(tiles,M,src,out,N,"2-D bound, FSETP.OR predicate per source");
+  run<6,7,1024>(tiles,M,src,out,N,"2-D bound, FSETP.OR predicate per source");
+  run<4,7,1024>(tiles,M,src,out,N,"2-D bound, FSETP.OR predicate per source");
+  run<7,7,1024>(tiles,M,src,out,N,"2-D bound, FSETP.OR predicate per source");
   run<8,6,1024>(tiles,M,src,out,N,"1-D bound, packed");
   run<16,6,1024>(tiles,M,src,out,N,"1-D bound, packed");
   return 0;

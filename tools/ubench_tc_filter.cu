@@ -32,7 +32,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// REDUCE: 0 = one FMNMX per load (keeps the load alive, measures TMEM read alone), 1 = full min over every value (FMNMX3 per 2 values)
+// REDUCE: 0 = one FMNMX per load (keeps the load alive, measures TMEM read alone), 1 = full min over every value (FMNMX3 per 2 values),
+//         2 = threshold test accumulated in one predicate (FSETP.LE.OR per value): all the filter needs is "any e~ <= tau"
 template <int COLS, int REDUCE>
 __global__ void __launch_bounds__(256) epi_kernel(float* out, int reps)
 {
@@ -52,23 +53,32 @@ __global__ void __launch_bounds__(256) epi_kernel(float* out, int reps)
 	const int c_hi = (nw > 4 && warp < 4) ? COLS / 2 : COLS;
 	float m = 3e38f;
 	float a[32], b[32];
+	const float tau = -1e30f + (float)reps;                 // never true on the garbage TMEM holds... whatever it holds, the work is the same
+	if (REDUCE == 2) { asm volatile(".reg .pred pe;"); asm volatile("setp.ne.u32 pe, 0, 0;"); }
 	for (int r = 0; r < reps; r++) {
 		tmem_ld32(base + c_lo, a);
 		for (int c = c_lo; c < c_hi; c += 64) {
 			tmem_wait_ld();
 			tmem_ld32(base + c + 32, b);
-			if (REDUCE) {
+			if (REDUCE == 1) {
 #pragma unroll
 				for (int k = 0; k < 32; k += 2) m = min3(m, a[k], a[k + 1]);
-			} else m = fminf(m, a[r & 31]);
+			} else if (REDUCE == 2) {
+#pragma unroll
+				for (int k = 0; k < 32; k++) asm volatile("setp.le.or.f32 pe, %0, %1, pe;" :: "f"(a[k]), "f"(tau));
+			} else m = fminf(m, a[0]);
 			tmem_wait_ld();
 			if (c + 64 < c_hi) tmem_ld32(base + c + 64, a);
-			if (REDUCE) {
+			if (REDUCE == 1) {
 #pragma unroll
 				for (int k = 0; k < 32; k += 2) m = min3(m, b[k], b[k + 1]);
-			} else m = fminf(m, b[r & 31]);
+			} else if (REDUCE == 2) {
+#pragma unroll
+				for (int k = 0; k < 32; k++) asm volatile("setp.le.or.f32 pe, %0, %1, pe;" :: "f"(b[k]), "f"(tau));
+			} else m = fminf(m, b[31]);
 		}
 	}
+	if (REDUCE == 2) { unsigned f; asm volatile("selp.u32 %0, 1, 0, pe;" : "=r"(f)); m = (float)f; }
 	out[blockIdx.x * blockDim.x + threadIdx.x] = m;
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
@@ -219,6 +229,11 @@ int main(int argc, char** argv)
 		run_epi<256, 1>("tcgen05.ld + FMNMX3 min", out, sms, 2, 128);
 		run_epi<256, 1>("tcgen05.ld + FMNMX3 min", out, sms, 2, 256);
 		run_epi<128, 1>("tcgen05.ld + FMNMX3 min", out, sms, 4, 128);
+		run_epi<512, 2>("tcgen05.ld + FSETP.OR threshold test", out, sms, 1, 128);
+		run_epi<512, 2>("tcgen05.ld + FSETP.OR threshold test", out, sms, 1, 256);
+		run_epi<256, 2>("tcgen05.ld + FSETP.OR threshold test", out, sms, 2, 128);
+		run_epi<256, 2>("tcgen05.ld + FSETP.OR threshold test", out, sms, 2, 256);
+		run_epi<128, 2>("tcgen05.ld + FSETP.OR threshold test", out, sms, 4, 128);
 	} else {
 		run_mma<1, 0>("mma tf32 128x256x8 + ld only", out, sms);
 		run_mma<1, 1>("mma tf32 128x256x8 + ld + min", out, sms);
