@@ -271,6 +271,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
+	cudaFree(c->grid_counts); cudaFree(c->grid_cell_of); cudaFree(c->grid_sums); cudaFree(c->grid_mm);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);
 	if (c->k9.one) cudaFreeHost(c->k9.one);
@@ -647,6 +648,13 @@ int icpb_iterate_host(icpb_ctx* ctx, const icpb_params* params, const float* sou
 	if (rms) *rms = err[1];
 	return ICPB_OK;
 }
+
+int icpb_host_alloc(void** ptr, unsigned long long bytes)
+{
+	if (!ptr || bytes == 0) return ICPB_ERR_BADARG;
+	return cudaMallocHost(ptr, (size_t)bytes) == cudaSuccess ? ICPB_OK : ICPB_ERR_NOMEM;
+}
+int icpb_host_free(void* ptr) { return (ptr && cudaFreeHost(ptr) == cudaSuccess) ? ICPB_OK : ICPB_ERR_BADARG; }
 
 // ---- measurement helpers ---------------------------------------------------------------------------------
 int icpb_measure_fp32_peak(icpb_ctx* ctx, double* tflops)

@@ -238,8 +238,16 @@ int launch_match_brute_remap(Ctx* c, int dist_mode, float sentinel, const int* r
 static int build_grid(Ctx* c)
 {
 	const int m = c->m;
-	unsigned* mm = nullptr;
-	ICPB_CUDA(c, cudaMalloc((void**)&mm, 6 * sizeof(unsigned)));
+	// every buffer of the build is kept in the context and only grows: cudaMalloc/cudaFree pairs cost more than the build
+	auto grow = [&](void** ptr, size_t& cap, size_t need, size_t elem) -> cudaError_t {
+		if (need <= cap && *ptr) return cudaSuccess;
+		cudaFree(*ptr); *ptr = nullptr; cap = 0;
+		const cudaError_t e = cudaMalloc(ptr, need * elem);
+		if (e == cudaSuccess) cap = need;
+		return e;
+	};
+	if (!c->grid_mm) ICPB_CUDA(c, cudaMalloc((void**)&c->grid_mm, 8 * sizeof(unsigned)));
+	unsigned* mm = c->grid_mm;
 	unsigned init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
 	ICPB_CUDA(c, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
 	grid_bbox_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->q4, m, mm);
@@ -247,7 +255,6 @@ static int build_grid(Ctx* c)
 	unsigned h_mm[6];
 	ICPB_CUDA(c, cudaMemcpyAsync(h_mm, mm, sizeof h_mm, cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-	cudaFree(mm);
 	auto dec = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
 	float lo[3], hi[3];
 	for (int k = 0; k < 3; k++) { lo[k] = dec(h_mm[k]); hi[k] = dec(h_mm[3 + k]); }
@@ -256,14 +263,18 @@ static int build_grid(Ctx* c)
 	c->grid_dim[0] = g.nx; c->grid_dim[1] = g.ny; c->grid_dim[2] = g.nz;
 	c->grid_origin[0] = g.ox; c->grid_origin[1] = g.oy; c->grid_origin[2] = g.oz; c->grid_cell = g.h;
 
-	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); c->grid_cell_start = nullptr; c->grid_sorted4 = nullptr;
-	int *counts = nullptr, *cell_of = nullptr, *sums = nullptr;
 	const int nb = (int)((ncell + 1 + 1023) / 1024);
-	ICPB_CUDA(c, cudaMalloc((void**)&c->grid_cell_start, sizeof(int) * (ncell + 1)));
-	ICPB_CUDA(c, cudaMalloc((void**)&c->grid_sorted4, sizeof(float4) * (size_t)m));
-	ICPB_CUDA(c, cudaMalloc((void**)&counts, sizeof(int) * (ncell + 1)));
-	ICPB_CUDA(c, cudaMalloc((void**)&cell_of, sizeof(int) * (size_t)m));
-	ICPB_CUDA(c, cudaMalloc((void**)&sums, sizeof(int) * (size_t)nb));
+	{
+		size_t cap_cells = c->grid_cells_cap, cap_cells2 = c->grid_cells_cap, cap_pts = c->grid_pts_cap, cap_pts2 = c->grid_pts_cap;
+		ICPB_CUDA(c, grow((void**)&c->grid_cell_start, cap_cells, ncell + 1, sizeof(int)));
+		ICPB_CUDA(c, grow((void**)&c->grid_counts, cap_cells2, ncell + 1, sizeof(int)));
+		c->grid_cells_cap = cap_cells < cap_cells2 ? cap_cells : cap_cells2;
+		ICPB_CUDA(c, grow((void**)&c->grid_sorted4, cap_pts, (size_t)m, sizeof(float4)));
+		ICPB_CUDA(c, grow((void**)&c->grid_cell_of, cap_pts2, (size_t)m, sizeof(int)));
+		c->grid_pts_cap = cap_pts < cap_pts2 ? cap_pts : cap_pts2;
+		ICPB_CUDA(c, grow((void**)&c->grid_sums, c->grid_sums_cap, (size_t)nb, sizeof(int)));
+	}
+	int *counts = c->grid_counts, *cell_of = c->grid_cell_of, *sums = c->grid_sums;
 	ICPB_CUDA(c, cudaMemsetAsync(counts, 0, sizeof(int) * (ncell + 1), c->stream));
 	grid_count_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->q4, m, g, counts, cell_of);
 	scan_block_kernel<<<nb, 1024, 0, c->stream>>>(counts, c->grid_cell_start, sums, (int)(ncell + 1));
@@ -273,8 +284,6 @@ static int build_grid(Ctx* c)
 	grid_scatter_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(c->q4, m, cell_of, c->grid_cell_start, counts, c->grid_sorted4);
 	c->launches += 5;
 	ICPB_CUDA(c, cudaGetLastError());
-	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-	cudaFree(counts); cudaFree(cell_of); cudaFree(sums);
 	if (!c->grid_open_list || c->grid_open_cap < c->n_cap) {
 		cudaFree(c->grid_open_list); c->grid_open_list = nullptr;
 		ICPB_CUDA(c, cudaMalloc((void**)&c->grid_open_list, sizeof(int) * (size_t)(c->n_cap > 0 ? c->n_cap : 1)));
@@ -285,8 +294,7 @@ static int build_grid(Ctx* c)
 	if (c->grid_pyramid) {
 		GridPyramid& py = c->grid_py;
 		const long long total = pyramid_layout(g, py);
-		cudaFree(c->grid_occ); c->grid_occ = nullptr;
-		ICPB_CUDA(c, cudaMalloc((void**)&c->grid_occ, (size_t)total));
+		ICPB_CUDA(c, grow((void**)&c->grid_occ, c->grid_occ_cap, (size_t)total, 1));
 		py.occ = c->grid_occ;
 		pyr_level0_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, c->stream>>>(c->grid_cell_start, (long long)ncell, c->grid_occ);
 		c->launches++;

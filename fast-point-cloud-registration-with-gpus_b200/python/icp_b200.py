@@ -73,6 +73,8 @@ def _load():
         "icpb_get_filter_stats": (C.c_int, [vp, dp, dp]),
         "icpb_get_filter_config": (C.c_int, [vp, ip, ip, ip, dp]),
         "icpb_launch_count": (C.c_longlong, [vp]),
+        "icpb_host_alloc": (C.c_int, [C.POINTER(vp), C.c_ulonglong]),
+        "icpb_host_free": (C.c_int, [vp]),
         "icpb_group_create": (C.c_int, [C.POINTER(vp), ip, C.c_int]),
         "icpb_group_destroy": (C.c_int, [vp]),
         "icpb_group_size": (C.c_int, [vp]),

@@ -204,12 +204,21 @@ int  icpb_iterate_host(icpb_ctx* ctx, const icpb_params* params, const float* so
                        const float* target_xyz, int m, int* idx_out, float R[9], float T[3], float* rms);
 
 /* ---- batched registration (BASELINE.json config 5) ------------------------------------------- */
-/* `batch` independent registrations, one per thread-block cluster, whole loop in one kernel.
- * sources: batch*n*3 floats, targets: batch*m*3 floats (host). errors: batch*(max_iter+1);
- * iterations: batch; R: batch*9 (accumulated, column-major, double); t: batch*3. */
+/* `batch` independent registrations, one per thread block (CTA), the whole loop of each inside one persistent kernel
+ * (registrations are drawn from an atomic counter: their iteration counts differ).
+ * sources: batch*n*3 floats, targets: batch*m*3 floats — host memory (pinned: streamed in chunks of 32 registrations
+ * behind the running kernel; pageable: uploaded first) or device memory (used in place). errors: batch*(max_iter+1);
+ * iterations: batch; R: batch*9 (accumulated, column-major, double); t: batch*3 — host. Device buffers are kept in
+ * the context between calls. */
 int  icpb_run_batched(icpb_ctx* ctx, const icpb_params* params, int batch, const float* sources, int n,
                       const float* targets, int m, float* errors, int* iterations, double* R, double* t,
                       float* elapsed_ms);
+
+/* Page-locked host memory for callers that have no CUDA of their own (the drop-in programs are plain C++): clouds handed
+ * to icpb_run_batched from such a buffer are uploaded in chunks BEHIND the running kernel; from ordinary memory they are
+ * uploaded first. Also what icpb_set_source / icpb_get_source transfer fastest from. */
+int  icpb_host_alloc(void** ptr, unsigned long long bytes);
+int  icpb_host_free(void* ptr);
 
 /* ---- dataset front ends ----------------------------------------------- */
 /* These work on caller buffers (host, or device when `on_device` != 0), not on the context's clouds; the context only

@@ -152,9 +152,10 @@ def test_100k_point_to_plane_properties(ctx, ib, orc):
 
 
 def test_knn_through_the_pyramid_equals_the_tiled_scan(ib, orc, golden_dir):
-    """ICPB_KNN_PYRAMID=1: K5's neighbour lists by best-first descent of the grid's occupancy pyramid — same lists as the
-    default kernels, the reference knn kernel's golden output and the oracle, in both ranking modes, on ties / ragged
-    sizes / the sqrt-merge case / clouds spread beyond the 10000 cut-off."""
+    """K5's neighbour lists by best-first descent of the grid's occupancy pyramid (the default since round 2;
+    ICPB_KNN_PYRAMID=0 selects the tiled brute-force scan) — same lists as the tiled scan, the reference knn kernel's
+    golden output and the oracle, in both ranking modes, on ties / ragged sizes / the sqrt-merge case / clouds spread
+    beyond the 10000 cut-off."""
     os.environ["ICPB_KNN_PYRAMID"] = "1"
     try:
         c = ib.Context(0)
@@ -176,7 +177,12 @@ def test_knn_through_the_pyramid_equals_the_tiled_scan(ib, orc, golden_dir):
         assert np.array_equal(c.neighbors(4), orc.knn(Q, 5))
         D, M = orc.synth_p2p(317, 100000)
         c.set_target(M); ms = c.estimate_normals(4)
-        with ib.Context(0) as ref:
+        os.environ["ICPB_KNN_PYRAMID"] = "0"
+        try:
+            ref = ib.Context(0)
+        finally:
+            del os.environ["ICPB_KNN_PYRAMID"]
+        with ref:
             ref.set_target(M); ms_ref = ref.estimate_normals(4)
             assert np.array_equal(c.neighbors(4), ref.neighbors(4))
         print("normals at 100k points: pyramid %.3f ms, tiled scan %.3f ms" % (ms, ms_ref))
