@@ -125,6 +125,9 @@ int  launch_knn_tree(Ctx* c, int k1, int knn_dist_mode, int* nbr);   // K5 throu
 int  launch_match_filter(Ctx* c, int dist_mode, float sentinel);
 int  kf_policy_update(Ctx* c);
 int  prepare_match_filter(Ctx* c);
+int  build_filter_tc_data(Ctx* c);
+int  launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel);
+int  filter_tc_check(Ctx* c);
 int  launch_moments(Ctx* c, int metric);
 int  launch_solve(Ctx* c, int metric);
 int  launch_transform(Ctx* c);
@@ -236,6 +239,13 @@ struct Ctx {
 	bool    kf_use_seed = true;         // warm start from the previous correspondences
 	double  kf_min_pairs = 1e9;         // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS)
 	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)
+	// K1T: the filter on the tensor cores (nn_filter_tc.cu)
+	bool    k1_use_tc = false;          // ICPB_K1_TC=1
+	int     kt_variant = 0;             // ICPB_KT_VAR: pipeline shape of K1T (nn_filter_tc.cu)
+	bool    kt_ready = false;
+	float*  kt_tiles = nullptr;         // [nt][B operand block 16 KB | X Y Z originals 3 KB], 256 targets per tile
+	int     kt_tiles_cap = 0, kt_nt = 0;
+	int*    kt_fail = nullptr;          // device flag: a bounded mbarrier wait of the pipeline timed out
 
 	// iteration state
 	IterState* st = nullptr;     // device

@@ -178,6 +178,8 @@ int create_context(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_GRID")) c->k1_grid_override = atoi(e);
 	if (const char* e = getenv("ICPB_K1_FILTER")) c->k1_use_filter = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_SEED")) c->kf_use_seed = atoi(e) != 0;
+	if (const char* e = getenv("ICPB_K1_TC")) c->k1_use_tc = atoi(e) != 0;
+	if (const char* e = getenv("ICPB_KT_VAR")) c->kt_variant = atoi(e);
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
@@ -271,6 +273,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
+	cudaFree(c->kt_tiles); cudaFree(c->kt_fail);
 	cudaFree(c->grid_counts); cudaFree(c->grid_cell_of); cudaFree(c->grid_sums); cudaFree(c->grid_mm);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);
@@ -325,7 +328,7 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 		if ((rc = dev_alloc(c, &c->nbr, (size_t)0)) != ICPB_OK) return rc;
 	}
 	if (m != c->m) c->seed_n = -1;      // seeds are indices into the target: only a different size invalidates them
-	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->step_state_ready = false; c->graph_gen++;
+	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->kt_ready = false; c->step_state_ready = false; c->graph_gen++;
 	const float* src = xyz;
 	if (!on_device) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)m)) != ICPB_OK) return rc;
@@ -443,7 +446,7 @@ int icpb_match(icpb_ctx* ctx, int dist_mode, int nn_method, float sentinel)
 	if ((rc = launch_match(c, dist_mode, nn_method, sentinel)) != ICPB_OK) return rc;
 	if ((rc = launch_resolve(c, sentinel)) != ICPB_OK) return rc;
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-	return ICPB_OK;
+	return filter_tc_check(c);
 }
 
 int icpb_minimize(icpb_ctx* ctx, int metric, float R[9], float T[3])

@@ -541,6 +541,7 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	// in the normal range. Anything else (non-finite coordinates, clouds of radius > 1e15 or < 1e-15) goes through
 	// the direct kernel.
 	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f || c->kf_rq < 1e-15f) return launch_match_brute(c, dist_mode, sentinel);
+	if (c->k1_use_tc) return launch_match_filter_tc(c, dist_mode, sentinel);      // K1T: the same bound on the tensor cores (nn_filter_tc.cu)
 	return (c->kf_s == 16) ? launch_filter_cfg<16, 1>(c, dist_mode, sentinel) : launch_filter_cfg<8, 2>(c, dist_mode, sentinel);
 }
 
@@ -555,6 +556,7 @@ int kf_policy_update(Ctx* c)
 	unsigned long long h[2] = { 0, 0 };
 	ICPB_CUDA(c, cudaMemcpyAsync(h, c->kf_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->k1_use_tc) { const int rc = filter_tc_check(c); if (rc != ICPB_OK) return rc; }
 	const double dt = (double)(h[0] - c->kf_stats_seen[0]), de = (double)(h[1] - c->kf_stats_seen[1]);
 	c->kf_stats_seen[0] = h[0]; c->kf_stats_seen[1] = h[1];
 	if (dt <= 0.0) return ICPB_OK;

@@ -1,0 +1,590 @@
+// nn_filter_tc.cu — K1T: the lower-bound filter of K1F evaluated on the 5th-generation tensor cores.
+//
+// Same contract and same bits as K1 / K1F (nn_bruteforce.cu, nn_filter.cu): idx[i] = argmin_j d_chain(P_i,Q_j) with the
+// lowest j on ties; every index and every distance that is returned comes from the reference's exact FP32 chain. What
+// changes is WHO evaluates the bracket  e~_j = |q_j - c|^2 - 2 (p - c).(q_j - c)  whose minimum over a 128-target
+// sub-tile decides whether the sub-tile can be skipped:
+//     K1F: 2-3 FFMA2 per source and target pair on the FP32 pipe + half an FMNMX3 on the ALU pipe   (37 pairs/clk/SM)
+//     K1T: one tcgen05.mma kind::tf32 128x256x16 per [128 sources x 256 targets] into TMEM; the FP32 pipe is left with
+//          the exact pass only, the ALU pipe with the running minimum of what tcgen05.ld brings back (tools/
+//          ubench_tc_filter.cu: 65-75 pairs/clk/SM for tcgen05.ld + FMNMX3; the MMA itself would do 128-256).
+// North star: "Tensor cores are used only if ncu shows the |p|^2+|q|^2-2p.q contraction beats the FP32 FMA path at K=3".
+//
+// TF32 keeps 11 significant bits, so each operand goes in as a hi + lo pair (round-to-nearest splits, residual
+// <= 2^-22 |x|) and the product p.q as the three terms hi*hi + hi*lo + lo*hi per coordinate; with w = |q-c|^2 as hi + lo
+// against a constant 1 that is 11 of the 16 K slots of two K=8 instructions:
+//     A row (source):  ax_hi ax_hi ax_lo | ay_hi ay_hi ay_lo | az_hi az_hi az_lo | 1    1    | 0 ...      a = -2 (p - c)
+//     B row (target):  qx_hi qx_lo qx_hi | qy_hi qy_lo qy_hi | qz_hi qz_lo qz_hi | w_hi w_lo | 0 ...      q = q_j - c
+// Products of TF32 values are exact in FP32; the accumulation inside the tensor core is not IEEE round-to-nearest, its
+// error relative to sum |a_k b_k| is measured by `tools/ubench_tc_filter check` (a few 2^-24). The bound used here is
+// K1F's with eps multiplied by TC_EPS_SCALE = 16:  16 u (8 Rq^2 + 10 Rp Rq + 2 Rp^2) covers the split residuals
+// (2^-22 = 4u per term: 4u (Rq^2 + 6 Rp Rq)), w's own rounding (3u Rq^2) and an accumulation error of up to 60 u of
+// sum |terms| <= Rq^2 + 2 Rp Rq. The price of the larger eps is a few more exact passes (the test fails for sub-tiles
+// within sqrt(thr + eps) instead of sqrt(thr)); measured exact-pass rate in bench.py's line.
+//
+// Kernel: one CTA per SM, 10 warps.
+//   warp 0   : TMA producer — streams target tiles (B operand block in the canonical K-major no-swizzle UMMA layout +
+//              the original coordinates for the exact pass, one 19 KB cp.async.bulk per 256 targets) through a 3-stage ring
+//   warp 1   : MMA issuer — for every tile, every one of the 8 source slabs (128 sources each, A operand built in shared
+//              memory by the CTA) and both 128-target sub-tiles: two tcgen05.mma (K = 2 x 8) into one of four 128-column
+//              TMEM accumulators, tcgen05.commit
+//   warps 2-9: two epilogue groups of 4 warps (one warp per TMEM lane quarter); group g owns the slabs a = g, g+2, g+4,
+//              g+6 and the accumulators g and g+2, which its (slab, sub-tile) units use alternately — the MMA of the next
+//              unit runs while this one is read: tcgen05.ld 32 columns at a time, running minimum over the sub-tile,
+//              ballot against tau, exact pass (K1's packed chain from the original coordinates in the ring) where needed.
+//              (First version: one 256-column accumulator per group; the group then sat idle for the ~300 cycles of every
+//              MMA: 1.52e13 pairs/s. Measured numbers in DESIGN.md.)
+// A source's state (threshold, remembered sub-tile, tau) is touched by exactly one thread, sub-tiles are visited in
+// ascending order: the tie rule is K1's. Every mbarrier wait is bounded: a protocol error ends the kernel with a flag
+// instead of hanging the GPU.
+#include "common.cuh"
+#include "k1_device.cuh"
+#include <cmath>
+
+namespace icpb {
+
+constexpr int TC_TN         = 256;                      // targets per tile = MMA N
+constexpr int TC_K          = 16;                       // K slots (two K=8 TF32 instructions)
+constexpr int TC_SLABS      = 8;                        // 128-source slabs per CTA pass
+constexpr int TC_SB         = 128 * TC_SLABS;           // sources per source block
+constexpr int TC_STAGES     = 3;
+constexpr int TC_B_BYTES    = TC_TN * TC_K * 4;         // 16384
+constexpr int TC_B_FLOATS   = TC_B_BYTES / 4;
+constexpr int TC_TILE_BYTES = TC_B_BYTES + 3 * TC_TN * 4;   // + X | Y | Z originals = 19456
+constexpr int TC_TILE_FLOATS = TC_TILE_BYTES / 4;
+constexpr int TC_A_BYTES    = 128 * TC_K * 4;           // 8192 per slab
+constexpr int TC_THREADS    = 320;
+constexpr int TC_TRK        = 128;                      // filter / tracking sub-tile: two per tile
+constexpr float TC_U        = 5.9604644775390625e-08f;  // 2^-24
+constexpr float TC_EPS_SCALE = 16.0f;
+constexpr size_t TC_SMEM    = (size_t)TC_SLABS * TC_A_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + (size_t)6 * TC_SB * 4 + 1024;
+
+struct KTParams {
+	const float* px; const float* py; const float* pz;
+	const float* tiles;       // [nt][TC_TILE_FLOATS]
+	const float4* q4;
+	const int*   seed_idx;
+	u64*         keys;
+	int          n, m, nt;
+	long long    total_units;        // source blocks x nt
+	int          min_chunk, max_chunk, gss_div;
+	unsigned long long* work_counter;
+	float        thr0;
+	float        cx, cy, cz, rq;
+	const int*   done;
+	unsigned long long* stats;       // [0] sub-tile tests, [1] exact passes
+	int*         fail;               // set on a protocol time-out
+};
+
+// element (row r, slot k) of an operand block in the canonical K-major no-swizzle layout: core matrices of 8 rows x 16 B,
+// the 4 core matrices of a row group contiguous (LBO = 128 B), row groups 512 B apart (SBO)
+__host__ __device__ __forceinline__ int tc_elem(int r, int k) { return (r >> 3) * 128 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }
+
+__device__ __forceinline__ float tf32_rn(float x)
+{
+	unsigned u = __float_as_uint(x);
+	u += 0xfffu + ((u >> 13) & 1u);
+	return __uint_as_float(u & 0xffffe000u);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) { hi = tf32_rn(x); lo = tf32_rn(__fsub_rn(x, hi)); }
+
+__global__ void tc_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, float cx, float cy, float cz, float* __restrict__ tiles)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m_pad) return;
+	float* tile = tiles + (size_t)(j / TC_TN) * TC_TILE_FLOATS;
+	const int r = j % TC_TN;
+	float v[TC_K];
+#pragma unroll
+	for (int k = 0; k < TC_K; k++) v[k] = 0.0f;
+	float x = __int_as_float(0x7f800000), y = x, z = x;
+	if (j < m) {
+		const float4 q = q4[j];
+		x = q.x; y = q.y; z = q.z;
+		const float xc = __fsub_rn(x, cx), yc = __fsub_rn(y, cy), zc = __fsub_rn(z, cz);
+		const float w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
+		float h, l;
+		tf32_split(xc, h, l); v[0] = h; v[1] = l; v[2] = h;
+		tf32_split(yc, h, l); v[3] = h; v[4] = l; v[5] = h;
+		tf32_split(zc, h, l); v[6] = h; v[7] = l; v[8] = h;
+		tf32_split(w, h, l);  v[9] = h; v[10] = l;
+	} else {
+		v[9] = 3.0e38f;                 // padding: e~ = 3e38 for every source, never below any tau; originals +inf
+	}
+#pragma unroll
+	for (int k = 0; k < TC_K; k++) tile[tc_elem(r, k)] = v[k];
+	tile[TC_B_FLOATS + r] = x; tile[TC_B_FLOATS + TC_TN + r] = y; tile[TC_B_FLOATS + 2 * TC_TN + r] = z;
+}
+
+// ---- small PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity)
+{
+	for (int spin = 0; spin < (1 << 26); spin++) {
+		uint32_t ok;
+		asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (ok) return true;
+	}
+	return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+	// start >> 4 [0,14), LBO = 128 B >> 4 at [16,30), SBO = 512 B >> 4 at [32,46), descriptor version 1 at [46,48), no swizzle
+	return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+	uint32_t* u = reinterpret_cast<uint32_t*>(v);
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+	             : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]),
+	               "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]),
+	               "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+	             : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void min32(const float (&v)[32], float& m0, float& m1)
+{
+#pragma unroll
+	for (int k = 0; k < 32; k += 4) { m0 = min3(m0, v[k], v[k + 1]); m1 = min3(m1, v[k + 2], v[k + 3]); }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+	uint32_t* u = reinterpret_cast<uint32_t*>(v);
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]),
+	               "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+	             : "r"(taddr));
+}
+__device__ __forceinline__ void min16(const float (&v)[16], float& m0, float& m1)
+{
+#pragma unroll
+	for (int k = 0; k < 16; k += 4) { m0 = min3(m0, v[k], v[k + 1]); m1 = min3(m1, v[k + 2], v[k + 3]); }
+}
+// minimum over the 128 columns of this thread's TMEM lane starting at taddr (double-buffered loads of LDW columns)
+template <int LDW> __device__ __forceinline__ float subtile_min(uint32_t taddr)
+{
+	const float inf = __int_as_float(0x7f800000);
+	float m0 = inf, m1 = inf;
+	if constexpr (LDW == 32) {
+		float va[32], vb[32];
+		tmem_ld32(taddr, va);
+		tmem_wait_ld(); tmem_ld32(taddr + 32, vb); min32(va, m0, m1);
+		tmem_wait_ld(); tmem_ld32(taddr + 64, va); min32(vb, m0, m1);
+		tmem_wait_ld(); tmem_ld32(taddr + 96, vb); min32(va, m0, m1);
+		tmem_wait_ld(); min32(vb, m0, m1);
+	} else {
+		float va[16], vb[16];
+		tmem_ld16(taddr, va);
+#pragma unroll
+		for (int c = 0; c < 128; c += 32) {
+			tmem_wait_ld(); tmem_ld16(taddr + c + 16, vb); min16(va, m0, m1);
+			tmem_wait_ld(); if (c + 32 < 128) tmem_ld16(taddr + c + 32, va);
+			min16(vb, m0, m1);
+		}
+	}
+	return fminf(m0, m1);
+}
+
+// NS       sub-tiles (128 targets) per MMA: 2 = one 256-column instruction per (slab, tile), 1 = two 128-column ones
+// NACC_G   TMEM accumulators per epilogue group (1: the group waits out every MMA; 2: the next unit's MMA runs meanwhile)
+// SLABS    128-source slabs per CTA pass, STAGES ring depth, MINB CTAs per SM (2: each CTA takes half the SM's TMEM)
+template <int MODE, int NS, int NACC_G, int SLABS, int STAGES, int MINB, int LDW>
+__global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams p)
+{
+	constexpr int SUBS = TC_TN / TC_TRK;      // 2 sub-tiles per tile
+	constexpr int UPT = SUBS / NS;            // MMA units per (slab, tile)
+	constexpr int UNIT_COLS = NS * TC_TRK;
+	constexpr int TMEM_COLS = 2 * NACC_G * UNIT_COLS;
+	constexpr int SBN = 128 * SLABS;          // sources per source block
+	static_assert(TMEM_COLS * MINB <= 512 && (TMEM_COLS == 256 || TMEM_COLS == 512), "TMEM budget");
+	static_assert(SLABS % 2 == 0 && SLABS <= TC_SLABS, "slabs are dealt to two epilogue groups");
+	if (p.done != nullptr && *p.done) return;
+	extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+	// 1 KB alignment by hand (the dynamic segment is only guaranteed 16 B)
+	unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+	__shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[4], tempty_bar[4];
+	__shared__ uint32_t tmem_base_s;
+	__shared__ unsigned long long s_u0;
+	__shared__ int s_len, s_fail;
+
+	float* a_slabs = reinterpret_cast<float*>(tc_smem);
+	float* ring    = reinterpret_cast<float*>(tc_smem + (size_t)SLABS * TC_A_BYTES);
+	float* thr_s   = reinterpret_cast<float*>(tc_smem + (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TC_TILE_BYTES);
+	int*   best_s  = reinterpret_cast<int*>(thr_s + SBN);
+	float* ox_s    = thr_s + 2 * SBN;
+	float* oy_s    = thr_s + 3 * SBN;
+	float* oz_s    = thr_s + 4 * SBN;
+	float* kk_s    = thr_s + 5 * SBN;
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const bool is_epi = warp >= 2;
+	const int ew = warp - 2;                  // epilogue warp 0..7
+	const int grp = ew >> 2;                  // epilogue group: slab parity and accumulator set this warp serves
+	const int quarter = warp & 3;             // TMEM lane quarter a warp may read: warp index mod 4
+	const int row = quarter * 32 + lane;      // source row inside a slab
+
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8); }
+		for (int a = 0; a < 4; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+		s_fail = 0;
+		fence_mbar_init();
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tmem_base = tmem_base_s;
+	// kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UNIT_COLS >> 3) << 17) | ((128u >> 4) << 24);
+
+	int it = 0;                   // tiles this CTA has streamed so far: ring stage and parities follow it across segments
+	unsigned long long n_tests = 0, n_exact = 0;
+	const float inf = __int_as_float(0x7f800000);
+	const float one8u = 1.0f + 8.0f * TC_U;
+	float tau[SLABS / 2];                       // per owned slab (epilogue threads)
+#pragma unroll
+	for (int q = 0; q < SLABS / 2; q++) tau[q] = -inf;
+	bool failed = false;
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) {
+			const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(p.work_counter);
+			const long long left = p.total_units - (long long)seen;
+			long long len = left / ((long long)p.gss_div * (long long)gridDim.x);
+			if (len < p.min_chunk) len = p.min_chunk;
+			if (len > p.max_chunk) len = p.max_chunk;
+			s_len = (int)len;
+			s_u0 = atomicAdd(p.work_counter, (unsigned long long)len);
+		}
+		__syncthreads();
+		if ((long long)s_u0 >= p.total_units || s_fail) break;
+		long long u = (long long)s_u0;
+		const long long u_end = min(p.total_units, u + (long long)s_len);
+		while (u < u_end) {
+			const int sb = (int)(u / p.nt);
+			const int t0 = (int)(u - (long long)sb * p.nt);
+			const int t1 = (int)min((long long)p.nt, (long long)t0 + (u_end - u));
+			u += t1 - t0;
+			__syncthreads();                       // previous segment fully consumed (A slabs, per-source state, ring)
+			// ---- per-source state and the A operand of the segment's sources (epilogue threads: SLABS / 2 sources each) ----
+			if (is_epi) {
+#pragma unroll
+				for (int q = 0; q < SLABS / 2; q++) {
+					const int a = grp + 2 * q;
+					const int sidx = a * 128 + row;
+					const int i = sb * SBN + sidx;
+					const float x = p.px[i], y = p.py[i], z = p.pz[i];       // arrays are padded beyond n
+					ox_s[sidx] = x; oy_s[sidx] = y; oz_s[sidx] = z;
+					const float pcx = __fsub_rn(x, p.cx), pcy = __fsub_rn(y, p.cy), pcz = __fsub_rn(z, p.cz);
+					const float p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
+					const float p2lo = __fmul_rd(p2, 1.0f - 8.0f * TC_U);
+					const float rp = __fmul_ru(__fsqrt_ru(p2), 1.0f + 8.0f * TC_U);
+					float e = __fmul_ru(8.0f * p.rq, p.rq);
+					e = __fmaf_ru(10.0f * rp, p.rq, e);
+					e = __fmaf_ru(2.0f * rp, rp, e);
+					e = __fmul_ru(e, 1.05f * TC_EPS_SCALE * TC_U);
+					const float kk = __fsub_ru(e, p2lo);
+					kk_s[sidx] = kk;
+					float th = p.thr0;
+					if (p.seed_idx != nullptr && i < p.n) {
+						const int j0 = p.seed_idx[i];
+						if (j0 >= 0 && j0 < p.m) {
+							const float4 qq = __ldg(p.q4 + j0);
+							const float us = dist_chain(x, y, z, qq.x, qq.y, qq.z);
+							const float up = (MODE == ICPB_DIST_SQRT) ? __fmul_ru(us, one8u) : us;
+							const float nx = __uint_as_float(__float_as_uint(up) + 1u);
+							if (us == us && nx < th) th = nx;
+						}
+					}
+					thr_s[sidx] = th; best_s[sidx] = -1;
+					// sources past the end of the cloud, and non-finite ones, never ask for an exact pass
+					const bool live = (i < p.n) && (p2 == p2) && (p2 < inf);
+					tau[q] = live ? __fadd_ru(__fmul_ru(th, one8u), kk) : -inf;
+					// A row: a = -2 (p - c) as hi + lo; slots ax_hi ax_hi ax_lo | ay.. | az.. | 1 1 | 0...
+					float* A = a_slabs + (size_t)a * (TC_A_BYTES / 4);
+					float h, l;
+					const float ax = live ? -2.0f * pcx : 0.0f, ay = live ? -2.0f * pcy : 0.0f, az = live ? -2.0f * pcz : 0.0f;
+					tf32_split(ax, h, l); A[tc_elem(row, 0)] = h; A[tc_elem(row, 1)] = h; A[tc_elem(row, 2)] = l;
+					tf32_split(ay, h, l); A[tc_elem(row, 3)] = h; A[tc_elem(row, 4)] = h; A[tc_elem(row, 5)] = l;
+					tf32_split(az, h, l); A[tc_elem(row, 6)] = h; A[tc_elem(row, 7)] = h; A[tc_elem(row, 8)] = l;
+					A[tc_elem(row, 9)] = 1.0f; A[tc_elem(row, 10)] = 1.0f;
+#pragma unroll
+					for (int k = 11; k < TC_K; k++) A[tc_elem(row, k)] = 0.0f;
+				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of A -> visible to the tensor core
+			}
+			__syncthreads();
+
+			if (warp == 0) {
+				// ---- TMA producer ----
+				if (lane == 0) {
+					for (int t = t0; t < t1 && !failed; t++) {
+						const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
+						if (use >= 1 && !mbar_wait_bounded(&empty_bar[st], (uint32_t)((use - 1) & 1))) { failed = true; break; }
+						mbar_expect_tx(&full_bar[st], TC_TILE_BYTES);
+						tma_load_1d(ring + (size_t)st * TC_TILE_FLOATS, p.tiles + (size_t)t * TC_TILE_FLOATS, TC_TILE_BYTES, &full_bar[st]);
+					}
+				}
+			} else if (warp == 1) {
+				// ---- MMA issuer ----
+				if (lane == 0) {
+					for (int t = t0; t < t1 && !failed; t++) {
+						const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
+						if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
+						const uint32_t sB = smem_u32(ring + (size_t)st * TC_TILE_FLOATS);
+#pragma unroll 1
+						for (int a = 0; a < SLABS && !failed; a++) {
+							const uint32_t sA = smem_u32(a_slabs + (size_t)a * (TC_A_BYTES / 4));
+#pragma unroll 1
+							for (int un = 0; un < UPT; un++) {
+								// unit (slab a, MMA un) of group g = a & 1; the group's units rotate through its NACC_G accumulators
+								const int g = a & 1;
+								const int v = (k * (SLABS / 2) + (a >> 1)) * UPT + un;            // units of group g so far
+								const int acc = g * NACC_G + (v % NACC_G);
+								const int j = v / NACC_G;                                        // use counter of accumulator `acc`
+								if (j >= 1 && !mbar_wait_bounded(&tempty_bar[acc], (uint32_t)((j - 1) & 1))) { failed = true; break; }
+								asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+								for (int kk2 = 0; kk2 < 2; kk2++) {
+									// K advances by two 128 B core matrices; unit `un` starts at row un * UNIT_COLS of the B block (row groups of 512 B)
+									const uint64_t dA = umma_desc(sA + kk2 * 256), dB = umma_desc(sB + un * (UNIT_COLS / 8) * 512 + kk2 * 256);
+									asm volatile("{\n.reg .pred pacc;\nsetp.ne.b32 pacc, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pacc;\n}\n"
+									             :: "r"(tmem_base + (uint32_t)(acc * UNIT_COLS)), "l"(dA), "l"(dB), "r"(idesc), "r"((uint32_t)kk2));
+								}
+								asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&tfull_bar[acc])) : "memory");
+							}
+						}
+					}
+				}
+			} else {
+				// ---- epilogue: running minimum per sub-tile, test against tau, exact pass where it cannot be excluded ----
+				for (int t = t0; t < t1 && !failed; t++) {
+					const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
+					if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
+					const float* tile = ring + (size_t)st * TC_TILE_FLOATS;
+					const float4* X4 = reinterpret_cast<const float4*>(tile + TC_B_FLOATS);
+					const float4* Y4 = X4 + TC_TN / 4;
+					const float4* Z4 = Y4 + TC_TN / 4;
+#pragma unroll
+					for (int q = 0; q < SLABS / 2; q++) {
+						if (failed) break;
+						const int a = grp + 2 * q;
+						const int sidx = a * 128 + row;
+#pragma unroll 1
+						for (int un = 0; un < UPT; un++) {
+							const int v = (k * (SLABS / 2) + q) * UPT + un;
+							const int acc = grp * NACC_G + (v % NACC_G);
+							const int j = v / NACC_G;
+							if (!mbar_wait_bounded(&tfull_bar[acc], (uint32_t)(j & 1))) { failed = true; break; }
+							asm volatile("tcgen05.fence::after_thread_sync;");
+							const uint32_t taddr = tmem_base + (uint32_t)(acc * UNIT_COLS) + ((uint32_t)(quarter * 32) << 16);
+							float em[NS];
+#pragma unroll
+							for (int hs = 0; hs < NS; hs++) em[hs] = subtile_min<LDW>(taddr + hs * TC_TRK);
+							// the accumulator is in registers: hand it back to the MMA warp before the (rare) exact pass
+							asm volatile("tcgen05.fence::before_thread_sync;");
+							__syncwarp();
+							if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+							for (int hs = 0; hs < NS; hs++) {
+								const int h = un * NS + hs;                   // sub-tile of the tile
+								const unsigned need = __ballot_sync(0xffffffffu, em[hs] <= tau[q]);
+								n_tests += 1;
+								if (need) {                                   // warp-uniform
+									n_exact += 1;
+									const int j0 = h * (TC_TRK / 4), j1 = j0 + TC_TRK / 4;
+									const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
+									const float th = thr_s[sidx];
+									const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
+									float mm = th;
+#pragma unroll 4
+									for (int jq = j0; jq < j1; jq++) {
+										const float4 Xo = X4[jq], Yo = Y4[jq], Zo = Z4[jq];
+										u64 dx = sub2(PX, pack2(Xo.x, Xo.y)), dy = sub2(PY, pack2(Yo.x, Yo.y)), dz = sub2(PZ, pack2(Zo.x, Zo.y));
+										u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+										float aa, bb;
+										unpack2(d, aa, bb);
+										mm = min3(mm, aa, bb);
+										dx = sub2(PX, pack2(Xo.z, Xo.w)); dy = sub2(PY, pack2(Yo.z, Yo.w)); dz = sub2(PZ, pack2(Zo.z, Zo.w));
+										d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+										unpack2(d, aa, bb);
+										mm = min3(mm, aa, bb);
+									}
+									if (mm < th) {
+										const float nt_ = lower_threshold<MODE>(mm);
+										thr_s[sidx] = nt_; best_s[sidx] = t * SUBS + h;
+										if (tau[q] > -inf) tau[q] = __fadd_ru(__fmul_ru(nt_, one8u), kk_s[sidx]);
+									}
+								}
+							}
+						}
+					}
+					// this warp is done with the tile's originals: release the ring stage (8 epilogue warps)
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&empty_bar[st]);
+				}
+			}
+			if (failed) s_fail = 1;
+			it += t1 - t0;
+			__syncthreads();
+			if (s_fail) break;
+			// ---- index recovery: the first target of the remembered sub-tile that attains the exact minimum ----
+			if (is_epi) {
+#pragma unroll 1
+				for (int q = 0; q < SLABS / 2; q++) {
+					const int a = grp + 2 * q;
+					const int sidx = a * 128 + row;
+					const int i = sb * SBN + sidx;
+					const int bs = best_s[sidx];
+					if (i < p.n && bs >= 0) {
+						const float th = thr_s[sidx];
+						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
+						const float* gx = p.tiles + (size_t)(bs / SUBS) * TC_TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % SUBS) * TC_TRK;
+						const float4* GX = reinterpret_cast<const float4*>(gx);
+						const float4* GY = reinterpret_cast<const float4*>(gx + TC_TN);
+						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TC_TN);
+						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
+						int found = -1;
+						for (int jq = 0; jq < TC_TRK / 4 && found < 0; jq++) {
+							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
+							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
+							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
+							float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
+							float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
+							if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+							if (d0 <= target) found = 4 * jq;
+							else if (d1 <= target) found = 4 * jq + 1;
+							else if (d2 <= target) found = 4 * jq + 2;
+							else if (d3 <= target) found = 4 * jq + 3;
+						}
+						if (found >= 0) {
+							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * TC_TRK + found);
+							atomicMin(p.keys + i, key);
+						}
+					}
+				}
+			}
+		}
+		if (s_fail) break;
+	}
+	__syncthreads();
+	if (s_fail && tid == 0) *p.fail = 1;
+	if (p.stats != nullptr && is_epi) {
+		for (int o = 16; o > 0; o >>= 1) { n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o); n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o); }
+		if (lane == 0) { atomicAdd(p.stats, n_tests / 32); atomicAdd(p.stats + 1, n_exact / 32); }
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+
+// Operand tiles of the current target (needs the centre chosen by build_filter_data); kept across targets of one size.
+int build_filter_tc_data(Ctx* c)
+{
+	const int m = c->m;
+	const int nt = (m + TC_TN - 1) / TC_TN;
+	if (nt > c->kt_tiles_cap) {
+		cudaFree(c->kt_tiles); c->kt_tiles = nullptr; c->kt_tiles_cap = 0;
+		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_tiles, sizeof(float) * (size_t)nt * TC_TILE_FLOATS));
+		c->kt_tiles_cap = nt;
+	}
+	if (!c->kt_fail) { ICPB_CUDA(c, cudaMalloc((void**)&c->kt_fail, sizeof(int))); ICPB_CUDA(c, cudaMemsetAsync(c->kt_fail, 0, sizeof(int), c->stream)); }
+	tc_pack_kernel<<<(nt * TC_TN + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * TC_TN, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	c->kt_nt = nt;
+	c->kt_ready = true;
+	return ICPB_OK;
+}
+
+static float sqrt_domain_threshold_tc(float sentinel)
+{
+	if (!(sentinel > 0.0f)) return 0.0f;
+	float y = sentinel * sentinel;
+	if (std::isinf(y)) return y;
+	while (sqrtf(y) < sentinel) y = nextafterf(y, INFINITY);
+	while (y > 0.0f && sqrtf(nextafterf(y, 0.0f)) >= sentinel) y = nextafterf(y, 0.0f);
+	return y;
+}
+
+template <int NS, int NACC_G, int SLABS, int STAGES, int MINB, int LDW>
+static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
+{
+	constexpr int SBN = 128 * SLABS;
+	constexpr size_t SMEM = (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TC_TILE_BYTES + (size_t)6 * SBN * 4 + 1024;
+	const int nb = (c->n + SBN - 1) / SBN;
+	p.total_units = (long long)nb * p.nt;
+	// guided self-scheduling as in K1F, in tiles of 256 targets x SBN sources
+	p.min_chunk = 8; p.max_chunk = 128; p.gss_div = 4;
+	if (c->kf_gss[0] > 0) { p.min_chunk = c->kf_gss[0]; p.max_chunk = c->kf_gss[1]; p.gss_div = c->kf_gss[2]; }
+	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
+	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
+	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc<ICPB_DIST_SQRT, NS, NACC_G, SLABS, STAGES, MINB, LDW> : k1_filter_tc<ICPB_DIST_SQ, NS, NACC_G, SLABS, STAGES, MINB, LDW>;
+	static bool attr_set[2][8][64] = {};
+	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 7][c->device & 63];
+	if (!done) { ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); done = true; }
+	long long grid = (long long)c->sm_count * MINB;             // the CTAs of an SM share its 512 TMEM columns
+	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
+	const long long max_ctas = (p.total_units + p.min_chunk - 1) / p.min_chunk;
+	if (grid > max_ctas) grid = max_ctas;
+	ICPB_CUDA(c, cudaMemsetAsync(c->kf_work_counter, 0, sizeof(unsigned long long), c->stream));
+	kern<<<(unsigned)grid, TC_THREADS, SMEM, c->stream>>>(p);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+
+int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
+{
+	int rc;
+	if (!c->kt_ready) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
+	KTParams p;
+	p.px = c->px; p.py = c->py; p.pz = c->pz;
+	p.tiles = c->kt_tiles; p.q4 = c->q4; p.seed_idx = c->kf_use_seed ? c->seed : nullptr; p.keys = c->keys;
+	p.n = c->n; p.m = c->m; p.nt = c->kt_nt;
+	p.thr0 = (dist_mode == ICPB_DIST_SQRT) ? sqrt_domain_threshold_tc(sentinel) : sentinel;
+	p.cx = c->kf_center[0]; p.cy = c->kf_center[1]; p.cz = c->kf_center[2]; p.rq = c->kf_rq;
+	p.done = &c->st->done;
+	p.stats = c->kf_stats;
+	p.fail = c->kt_fail;
+	c->kf_dims_last = 4;                       // reported as "4" = the 3-D bound on the tensor cores
+	c->kf_seeded = true;
+	c->pairs_acc += (double)c->n * (double)c->m;
+	if (!c->kf_work_counter) ICPB_CUDA(c, cudaMalloc((void**)&c->kf_work_counter, sizeof(unsigned long long)));
+	p.work_counter = c->kf_work_counter;
+	// ICPB_KT_VAR selects the pipeline shape (experiments; results are identical):
+	//   0: one 256-column MMA per (slab, tile), one accumulator per epilogue group, 8 slabs, 1 CTA/SM
+	//   1: two 128-column MMAs per (slab, tile), two accumulators per group (MMA of the next unit overlaps the read of this one)
+	//   2: two CTAs per SM, each with half the TMEM: 128-column MMAs, one accumulator per group, 4 slabs, 2-stage ring
+	//   3: as 2 with 16-column TMEM loads (fewer registers)
+	switch (c->kt_variant) {
+	case 1:  return launch_tc_variant<1, 2, 8, 3, 1, 32>(c, dist_mode, p, 1);
+	case 2:  return launch_tc_variant<1, 1, 4, 2, 2, 32>(c, dist_mode, p, 2);
+	case 3:  return launch_tc_variant<1, 1, 4, 2, 2, 16>(c, dist_mode, p, 3);
+	case 4:  return launch_tc_variant<2, 1, 8, 3, 1, 16>(c, dist_mode, p, 4);
+	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
+	}
+}
+
+// after a synchronisation point: did any launch report a protocol time-out?
+int filter_tc_check(Ctx* c)
+{
+	if (!c->kt_fail) return ICPB_OK;
+	int h = 0;
+	ICPB_CUDA(c, cudaMemcpyAsync(&h, c->kt_fail, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (h) { snprintf(c->err, sizeof c->err, "k1_filter_tc: an mbarrier wait timed out (tensor-core pipeline protocol error)"); return ICPB_ERR_CUDA; }
+	return ICPB_OK;
+}
+
+} // namespace icpb

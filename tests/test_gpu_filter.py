@@ -23,7 +23,7 @@ def _context(ib, **env):
 
 # every test runs with the bound chosen automatically (full on cold passes, planar on warm ones, switched by the
 # measured exact-pass rate), with the planar bound forced for each choice of the dropped axis, and with the full one
-@pytest.fixture(scope="module", params=["auto", "planar-x", "planar-y", "planar-z", "full"])
+@pytest.fixture(scope="module", params=["auto", "planar-x", "planar-y", "planar-z", "full", "tc"])
 def ctx(ib, request):
     """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
     use the direct kernel, which would make most of these small cases vacuous)."""
@@ -32,6 +32,8 @@ def ctx(ib, request):
         env.update(ICPB_KF_DIMS=2, ICPB_KF_DROP="xyz".index(request.param[-1]))
     elif request.param == "full":
         env.update(ICPB_KF_DIMS=3)
+    elif request.param == "tc":                    # K1T: the 3-D bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
+        env.update(ICPB_K1_TC=1)
     c = _context(ib, **env)
     c.variant = request.param
     yield c
@@ -47,7 +49,7 @@ def _check(ctx, ib, orc, P, Q, modes=(0, 1), sentinel=100000.0, oracle=True, exp
             assert (ctx.filter_stats()["subtile_tests"] > s0) == expect_filter, "which kernel ran is part of the test"
             if expect_filter:
                 cfg = ctx.filter_config()
-                want = {"planar": 2, "full": 3}.get(ctx.variant.split("-")[0])
+                want = {"planar": 2, "full": 3, "tc": 4}.get(ctx.variant.split("-")[0])
                 assert want is None or cfg["dims_last"] == want, (ctx.variant, cfg)
                 if ctx.variant.startswith("planar"):
                     assert cfg["drop_axis"] == "xyz".index(ctx.variant[-1])

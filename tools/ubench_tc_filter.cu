@@ -213,8 +213,151 @@ template <int KSTEPS, int REDUCE> static void run_mma(const char* name, float* o
 	printf("%-40s K=%2d: %7.3f ms  %7.1f pairs/clk/SM  (%.0f cycles per 128x256 tile)\n", name, 8 * KSTEPS, best, pairs_per_sm / cyc, cyc / tiles);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// part C (mode "check"): numerical validation of the descriptors. A [128 x 16] and B [256 x 16] hold random values that are
+// exact in TF32; D = A B^T is accumulated over two K=8 instructions, read back with tcgen05.ld and compared with a
+// double-precision product on the host. Also reports the largest accumulation error relative to sum |a_k b_k|
+// (the tensor core's FP32 accumulate is not IEEE round-to-nearest; the filter's error bound needs a measured constant).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) check_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	__shared__ uint32_t tmem_base_s;
+	__shared__ __align__(8) uint64_t bar;
+	const int warp = threadIdx.x >> 5;
+	float* sAf = reinterpret_cast<float*>(smem);                 // 128 x 16 floats, canonical K-major no-swizzle: LBO 128 B, SBO 512 B
+	float* sBf = sAf + 128 * 16;                                 // 256 x 16
+	for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) { const int r = i / 16, k = i % 16; sAf[(r / 8) * 128 + (k / 4) * 32 + (r % 8) * 4 + (k % 4)] = A[i]; }
+	for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) { const int r = i / 16, k = i % 16; sBf[(r / 8) * 128 + (k / 4) * 32 + (r % 8) * 4 + (k % 4)] = B[i]; }
+	if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "n"(256));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tbase = tmem_base_s;
+	const uint32_t sA = (uint32_t)__cvta_generic_to_shared(sAf), sB = (uint32_t)__cvta_generic_to_shared(sBf);
+	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+	if (threadIdx.x == 0) {
+		for (int k = 0; k < 2; k++) {
+			const uint64_t dA = smem_desc(sA + k * 256, 128, 512), dB = smem_desc(sB + k * 256, 128, 512);     // K advances by 2 core matrices = 256 B
+			asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+			             :: "r"(tbase), "l"(dA), "l"(dB), "r"(idesc), "r"((uint32_t)(k > 0)));
+		}
+		asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&bar)) : "memory");
+	}
+	const bool ok = mbar_wait(&bar, 0);
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	if (ok) {
+		const uint32_t base = tbase + ((uint32_t)(warp * 32) << 16);
+		float v[32];
+		for (int c = 0; c < 256; c += 32) {
+			tmem_ld32(base + c, v);
+			tmem_wait_ld();
+			for (int k = 0; k < 32; k++) D[(size_t)threadIdx.x * 256 + c + k] = v[k];
+		}
+	} else if (threadIdx.x == 0) g_timeout = 3;
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "n"(256));
+}
+
+// part D (mode "lat"): latency of one tcgen05.mma batch — issue, tcgen05.commit, mbarrier wait — as the issuing thread sees it
+template <int N, int NMMA>
+__global__ void __launch_bounds__(128) lat_kernel(long long* out, int reps)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	__shared__ uint32_t tmem_base_s;
+	__shared__ __align__(8) uint64_t bar;
+	const int warp = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < (4096 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+	if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "n"(256));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tbase = tmem_base_s;
+	const uint32_t sA = (uint32_t)__cvta_generic_to_shared(smem), sB = sA + 4096;
+	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+	const uint64_t dA = smem_desc(sA, 128, 256), dB = smem_desc(sB, 128, 256);
+	if (threadIdx.x == 0) {
+		long long best = 1ll << 60, sum = 0;
+		for (int r = 0; r < reps; r++) {
+			const long long t0 = clock64();
+#pragma unroll
+			for (int k = 0; k < NMMA; k++)
+				asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" :: "r"(tbase), "l"(dA), "l"(dB), "r"(idesc), "r"((uint32_t)(k > 0)));
+			asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&bar)) : "memory");
+			if (!mbar_wait(&bar, (uint32_t)(r & 1))) { g_timeout = 4; break; }
+			const long long dt = clock64() - t0;
+			if (dt < best) best = dt;
+			sum += dt;
+		}
+		out[0] = best; out[1] = sum / reps;
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "n"(256));
+}
+template <int N, int NMMA> static void run_lat()
+{
+	long long* d; CK(cudaMalloc(&d, 16));
+	const size_t smem = 4096 + 8192 + 1024;
+	CK(cudaFuncSetAttribute(lat_kernel<N, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	lat_kernel<N, NMMA><<<1, 128, smem>>>(d, 200);
+	CK(cudaDeviceSynchronize());
+	long long h[2]; CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+	printf("latency issue -> commit -> mbarrier seen: %d x tcgen05.mma tf32 128x%dx8: min %lld cycles, mean %lld\n", NMMA, N, h[0], h[1]);
+	cudaFree(d);
+}
+
+static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; memcpy(&x, &u, 4); return x; }
+
+static int run_check()
+{
+	const int M = 128, N = 256, K = 16;
+	float *hA = new float[M * K], *hB = new float[N * K], *hD = new float[M * N];
+	uint32_t st = 12345u;
+	auto rnd = [&]() { st = st * 1664525u + 1013904223u; return (float)((st >> 8) & 0xffff) / 32768.0f - 1.0f; };
+	for (int i = 0; i < M * K; i++) hA[i] = tf32_trunc(rnd() * 7.0f);
+	for (int i = 0; i < N * K; i++) hB[i] = tf32_trunc(rnd() * 3.0f);
+	float *dA, *dB, *dD;
+	CK(cudaMalloc(&dA, M * K * 4)); CK(cudaMalloc(&dB, N * K * 4)); CK(cudaMalloc(&dD, M * N * 4));
+	CK(cudaMemcpy(dA, hA, M * K * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB, N * K * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemset(dD, 0xff, M * N * 4));
+	const size_t smem = (128 + 256) * 16 * 4 + 1024;
+	CK(cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	check_kernel<<<1, 128, smem>>>(dA, dB, dD);
+	CK(cudaDeviceSynchronize());
+	int to = 0; CK(cudaMemcpyFromSymbol(&to, g_timeout, sizeof to));
+	if (to) { printf("check: TIMED OUT (%d)\n", to); return 1; }
+	CK(cudaMemcpy(hD, dD, M * N * 4, cudaMemcpyDeviceToHost));
+	double max_abs = 0, max_rel = 0; int bad = 0;
+	for (int i = 0; i < M; i++)
+		for (int j = 0; j < N; j++) {
+			double ref = 0, mag = 0;
+			for (int k = 0; k < K; k++) { ref += (double)hA[i * K + k] * hB[j * K + k]; mag += fabs((double)hA[i * K + k] * hB[j * K + k]); }
+			const double err = fabs((double)hD[i * N + j] - ref);
+			if (err > max_abs) max_abs = err;
+			if (err / mag > max_rel) max_rel = err / mag;
+			if (err > 1e-4 * mag + 1e-6) { if (bad < 5) printf("  D[%d][%d] = %g, expected %g\n", i, j, hD[i * N + j], ref); bad++; }
+		}
+	printf("check: tcgen05.mma kind::tf32 128x256x16 (2 instructions, no-swizzle K-major descriptors): %s; max |err| %.3e, max |err| / sum|a_k b_k| = %.3e = %.2f x 2^-24\n",
+	       bad ? "MISMATCH" : "matches the host product", max_abs, max_rel, max_rel * 16777216.0);
+	return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv)
 {
+	if (argc > 1 && !strcmp(argv[1], "check")) return run_check();
+	if (argc > 1 && !strcmp(argv[1], "lat")) { run_lat<128, 1>(); run_lat<128, 2>(); run_lat<256, 1>(); run_lat<256, 2>(); run_lat<256, 4>(); run_lat<64, 2>(); return 0; }
 	cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
 	const int sms = prop.multiProcessorCount;
 	float* out; CK(cudaMalloc(&out, (size_t)sms * 4 * 256 * 4));
