@@ -125,6 +125,7 @@ int  launch_knn_tree(Ctx* c, int k1, int knn_dist_mode, int* nbr);   // K5 throu
 int  launch_match_filter(Ctx* c, int dist_mode, float sentinel);
 int  kf_policy_update(Ctx* c);
 int  prepare_match_filter(Ctx* c);
+int  prepare_match_grid(Ctx* c);
 int  build_filter_tc_data(Ctx* c);
 int  launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel);
 int  filter_tc_check(Ctx* c);

@@ -544,7 +544,9 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	// per-target data of the matching method is built before the clock starts (as the reference's cudaMalloc block is)
 	if (p.nn_method == ICPB_NN_BRUTE && c->k1_use_filter && p.dist_mode != ICPB_DIST_STD && (double)c->n * (double)c->m >= c->kf_min_pairs) {
 		if ((rc = prepare_match_filter(c)) != ICPB_OK) return rc;
+		if (c->k1_use_tc && !c->kt_ready && (rc = build_filter_tc_data(c)) != ICPB_OK) return rc;
 	}
+	if (p.nn_method == ICPB_NN_GRID && p.dist_mode != ICPB_DIST_STD) { if ((rc = prepare_match_grid(c)) != ICPB_OK) return rc; }
 	// Opt-in (ICPB_FLAG_GRAPH / ICPB_GRAPHS=1) for launch-latency-bound small problems: after a first plain iteration
 	// (which also builds lazily created data and caches launch attributes) the remaining ones are replayed from a CUDA
 	// graph holding `sync_every` iterations; the instantiated graph is reused by later runs on clouds of the same size.

@@ -340,6 +340,14 @@ int launch_knn_tree(Ctx* c, int k1, int knn_dist_mode, int* nbr)
 	return ICPB_OK;
 }
 
+// Builds the grid of the current target OUTSIDE the timed loop (icpb_run calls this before it records its first event,
+// as it does for the filter data; launch_match_grid still builds lazily for the step-wise API).
+int prepare_match_grid(Ctx* c)
+{
+	if (c->m <= 0 || (c->grid_ready && c->grid_open_cap >= c->n_cap)) return ICPB_OK;
+	return build_grid(c);
+}
+
 int launch_match_grid(Ctx* c, int dist_mode, float sentinel)
 {
 	if (dist_mode == ICPB_DIST_STD) { snprintf(c->err, sizeof c->err, "ICPB_NN_GRID supports ICPB_DIST_SQ and ICPB_DIST_SQRT"); return ICPB_ERR_BADARG; }

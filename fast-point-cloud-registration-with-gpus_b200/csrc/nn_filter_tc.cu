@@ -483,6 +483,304 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams 
 	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K1T, split form (the default). Two warps per TMEM lane quarter read one accumulator: warps that share a quarter share
+// its 32 sources and take one 128-target sub-tile of the unit each, so a (slab, tile) unit is read by 8 warps at once and
+// a handshake with the MMA warp buys half as much reading per warp — which is what lets 16 epilogue warps (GROUPS = 2,
+// two groups of 8, group g on accumulator g and the slabs of parity g) keep the ALU pipe busy across each other's
+// handshakes: the MMA's issue -> commit -> visible latency (389 cycles for the two K=8 instructions, `tools/
+// ubench_tc_filter lat`) plus the barrier round trips cost more than reading a unit. GROUPS = 1: one group of 8 warps on
+// two accumulators used alternately.
+// Two warps now work on one source concurrently, so its state is one 64-bit word
+//     key = (bits of the exact threshold) << 32 | remembered sub-tile            (0xffffffff = none yet)
+// updated with atomicMin in shared memory: smallest threshold first, lowest sub-tile among equal thresholds — exactly what
+// visiting the sub-tiles in ascending order with a strict `<` gives, whatever order the warps get there in. For that the
+// exact pass always takes the sub-tile's true minimum and offers it whenever its threshold is <= the current one (an
+// equal distance in an EARLIER sub-tile must still win; the key order decides). The starting threshold is the largest
+// float below the sentinel's, so that "<=" keeps the reference's strict `d < sentinel`. A stale threshold read can only
+// cost an unnecessary exact pass, never change the result.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW>
+__global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const KTParams p)
+{
+	constexpr int SUBS = TC_TN / TC_TRK;                 // 2 sub-tiles per tile = per MMA unit
+	constexpr int UNIT_COLS = TC_TN;                     // one 256-column accumulator per (slab, tile) unit
+	constexpr int TMEM_COLS = 2 * UNIT_COLS;
+	constexpr int SBN = 128 * SLABS;                     // sources per source block
+	constexpr int NEPI = 8 * GROUPS;                     // epilogue warps
+	constexpr int SPT = SBN / (32 * NEPI);               // sources each epilogue thread sets up and flushes
+	static_assert(GROUPS == 1 || GROUPS == 2, "one or two epilogue groups");
+	static_assert(SLABS % (2 * GROUPS) == 0 && SLABS <= TC_SLABS && SPT >= 1, "slab count");
+	if (p.done != nullptr && *p.done) return;
+	extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+	unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);      // 1 KB alignment by hand
+	__shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+	__shared__ uint32_t tmem_base_s;
+	__shared__ unsigned long long s_u0;
+	__shared__ int s_len, s_fail;
+
+	float* a_slabs = reinterpret_cast<float*>(tc_smem);
+	float* ring    = reinterpret_cast<float*>(tc_smem + (size_t)SLABS * TC_A_BYTES);
+	u64*   key_s   = reinterpret_cast<u64*>(tc_smem + (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TC_TILE_BYTES);
+	float* ox_s    = reinterpret_cast<float*>(key_s + SBN);
+	float* oy_s    = ox_s + SBN;
+	float* oz_s    = oy_s + SBN;
+	float* kk_s    = oz_s + SBN;
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	// the two single-thread roles get the HIGHEST warp indices: the scheduler favours high warp ids among eligible warps, and
+	// every cycle the MMA issuer waits for an issue slot behind busy epilogue warps is added to each unit's handshake
+	const bool is_epi = warp < NEPI;
+	const int ew = warp;                      // epilogue warp 0 .. NEPI-1
+	const int w_tma = NEPI, w_mma = NEPI + 1;
+	const int quarter = warp & 3;             // TMEM lane quarter a warp may read: warp index mod 4
+	const int wq = ew >> 2;                   // which of the quarter's warps this is: 0 .. 2*GROUPS-1
+	const int half = wq & 1;                  // the 128-target sub-tile of a unit this warp reads
+	const int grp = wq >> 1;                  // epilogue group (GROUPS = 2), else 0
+	const int row = quarter * 32 + lane;      // source row inside a slab
+
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NEPI); }
+		for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+		s_fail = 0;
+		fence_mbar_init();
+	}
+	if (warp == w_mma) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;");
+	const uint32_t tmem_base = tmem_base_s;
+	// kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UNIT_COLS >> 3) << 17) | ((128u >> 4) << 24);
+
+	int it = 0;                   // tiles this CTA has streamed so far: ring stage and parities follow it across segments
+	unsigned long long n_tests = 0, n_exact = 0;
+	const float inf = __int_as_float(0x7f800000);
+	const float one8u = 1.0f + 8.0f * TC_U;
+	// largest float below the starting threshold: with it, "threshold <= current" is the reference's strict d < sentinel
+	const float thr_start = (p.thr0 > 0.0f) ? __uint_as_float(__float_as_uint(p.thr0) - 1u) : -1.0f;
+	bool failed = false;
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) {
+			const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(p.work_counter);
+			const long long left = p.total_units - (long long)seen;
+			long long len = left / ((long long)p.gss_div * (long long)gridDim.x);
+			if (len < p.min_chunk) len = p.min_chunk;
+			if (len > p.max_chunk) len = p.max_chunk;
+			s_len = (int)len;
+			s_u0 = atomicAdd(p.work_counter, (unsigned long long)len);
+		}
+		__syncthreads();
+		if ((long long)s_u0 >= p.total_units || s_fail) break;
+		long long u = (long long)s_u0;
+		const long long u_end = min(p.total_units, u + (long long)s_len);
+		while (u < u_end) {
+			const int sb = (int)(u / p.nt);
+			const int t0 = (int)(u - (long long)sb * p.nt);
+			const int t1 = (int)min((long long)p.nt, (long long)t0 + (u_end - u));
+			u += t1 - t0;
+			__syncthreads();                       // previous segment fully consumed (A slabs, per-source state, ring)
+			// ---- per-source state and the A operand of the segment's sources (SPT sources per epilogue thread) ----
+			if (is_epi) {
+#pragma unroll
+				for (int q = 0; q < SPT; q++) {
+					const int a = wq + 2 * GROUPS * q;           // the slabs of this thread: wq, wq + 2 GROUPS, ...
+					const int sidx = a * 128 + row;
+					const int i = sb * SBN + sidx;
+					const float x = p.px[i], y = p.py[i], z = p.pz[i];       // arrays are padded beyond n
+					ox_s[sidx] = x; oy_s[sidx] = y; oz_s[sidx] = z;
+					const float pcx = __fsub_rn(x, p.cx), pcy = __fsub_rn(y, p.cy), pcz = __fsub_rn(z, p.cz);
+					const float p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
+					const float p2lo = __fmul_rd(p2, 1.0f - 8.0f * TC_U);
+					const float rp = __fmul_ru(__fsqrt_ru(p2), 1.0f + 8.0f * TC_U);
+					float e = __fmul_ru(8.0f * p.rq, p.rq);
+					e = __fmaf_ru(10.0f * rp, p.rq, e);
+					e = __fmaf_ru(2.0f * rp, rp, e);
+					e = __fmul_ru(e, 1.05f * TC_EPS_SCALE * TC_U);
+					// sources past the end of the cloud, and non-finite ones, never ask for an exact pass: kk = -inf makes tau = -inf
+					const bool live = (i < p.n) && (p2 == p2) && (p2 < inf);
+					kk_s[sidx] = live ? __fsub_ru(e, p2lo) : -inf;
+					float th = thr_start;
+					if (p.seed_idx != nullptr && i < p.n) {
+						const int j0 = p.seed_idx[i];
+						if (j0 >= 0 && j0 < p.m) {
+							const float4 qq = __ldg(p.q4 + j0);
+							const float us = dist_chain(x, y, z, qq.x, qq.y, qq.z);
+							const float up = (MODE == ICPB_DIST_SQRT) ? __fmul_ru(us, one8u) : us;     // covers the floats sqrt.rn merges with us
+							if (us == us && up < th) th = up;            // the seed itself (or an equal, lower-indexed target) is offered by the exact pass
+						}
+					}
+					key_s[sidx] = ((u64)__float_as_uint(th) << 32) | 0xffffffffull;
+					// A row: a = -2 (p - c) as hi + lo; slots ax_hi ax_hi ax_lo | ay.. | az.. | 1 1 | 0...
+					float* A = a_slabs + (size_t)a * (TC_A_BYTES / 4);
+					float h, l;
+					const float ax = live ? -2.0f * pcx : 0.0f, ay = live ? -2.0f * pcy : 0.0f, az = live ? -2.0f * pcz : 0.0f;
+					tf32_split(ax, h, l); A[tc_elem(row, 0)] = h; A[tc_elem(row, 1)] = h; A[tc_elem(row, 2)] = l;
+					tf32_split(ay, h, l); A[tc_elem(row, 3)] = h; A[tc_elem(row, 4)] = h; A[tc_elem(row, 5)] = l;
+					tf32_split(az, h, l); A[tc_elem(row, 6)] = h; A[tc_elem(row, 7)] = h; A[tc_elem(row, 8)] = l;
+					A[tc_elem(row, 9)] = 1.0f; A[tc_elem(row, 10)] = 1.0f;
+#pragma unroll
+					for (int k = 11; k < TC_K; k++) A[tc_elem(row, k)] = 0.0f;
+				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of A -> visible to the tensor core
+			}
+			__syncthreads();
+
+			if (warp == w_tma) {
+				// ---- TMA producer ----
+				if (lane == 0) {
+					for (int t = t0; t < t1 && !failed; t++) {
+						const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
+						if (use >= 1 && !mbar_wait_bounded(&empty_bar[st], (uint32_t)((use - 1) & 1))) { failed = true; break; }
+						mbar_expect_tx(&full_bar[st], TC_TILE_BYTES);
+						tma_load_1d(ring + (size_t)st * TC_TILE_FLOATS, p.tiles + (size_t)t * TC_TILE_FLOATS, TC_TILE_BYTES, &full_bar[st]);
+					}
+				}
+			} else if (warp == w_mma) {
+				// ---- MMA issuer ----
+				if (lane == 0) {
+					for (int t = t0; t < t1 && !failed; t++) {
+						const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
+						if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
+						const uint32_t sB = smem_u32(ring + (size_t)st * TC_TILE_FLOATS);
+#pragma unroll 1
+						for (int a = 0; a < SLABS; a++) {
+							// GROUPS = 2: slab a belongs to group a & 1 and goes to accumulator a & 1; GROUPS = 1: the units alternate
+							const int v = (GROUPS == 2) ? (k * (SLABS / 2) + (a >> 1)) : (k * SLABS + a);
+							const int acc = (GROUPS == 2) ? (a & 1) : (v & 1);
+							const int j = (GROUPS == 2) ? v : (v >> 1);                       // use counter of accumulator `acc`
+							if (j >= 1 && !mbar_wait_bounded(&tempty_bar[acc], (uint32_t)((j - 1) & 1))) { failed = true; break; }
+							asm volatile("tcgen05.fence::after_thread_sync;");
+							const uint32_t sA = smem_u32(a_slabs + (size_t)a * (TC_A_BYTES / 4));
+#pragma unroll
+							for (int kk2 = 0; kk2 < 2; kk2++) {
+								const uint64_t dA = umma_desc(sA + kk2 * 256), dB = umma_desc(sB + kk2 * 256);   // K advances by two 128 B core matrices
+								asm volatile("{\n.reg .pred pacc;\nsetp.ne.b32 pacc, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pacc;\n}\n"
+								             :: "r"(tmem_base + (uint32_t)(acc * UNIT_COLS)), "l"(dA), "l"(dB), "r"(idesc), "r"((uint32_t)kk2));
+							}
+							asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&tfull_bar[acc])) : "memory");
+						}
+					}
+				}
+			} else {
+				// ---- epilogue: minimum over this warp's sub-tile, test against tau, exact pass where it cannot be excluded ----
+				for (int t = t0; t < t1 && !failed; t++) {
+					const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
+					if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
+					const float* tile = ring + (size_t)st * TC_TILE_FLOATS;
+					const float4* X4 = reinterpret_cast<const float4*>(tile + TC_B_FLOATS);
+					const float4* Y4 = X4 + TC_TN / 4;
+					const float4* Z4 = Y4 + TC_TN / 4;
+#pragma unroll 1
+					for (int a = grp; a < SLABS; a += GROUPS) {
+						const int sidx = a * 128 + row;
+						const int v = (GROUPS == 2) ? (k * (SLABS / 2) + (a >> 1)) : (k * SLABS + a);
+						const int acc = (GROUPS == 2) ? grp : (v & 1);
+						const int j = (GROUPS == 2) ? v : (v >> 1);
+						if (!mbar_wait_bounded(&tfull_bar[acc], (uint32_t)(j & 1))) { failed = true; break; }
+						asm volatile("tcgen05.fence::after_thread_sync;");
+						const uint32_t taddr = tmem_base + (uint32_t)(acc * UNIT_COLS + half * TC_TRK) + ((uint32_t)(quarter * 32) << 16);
+						const float em = subtile_min<LDW>(taddr);
+						// the accumulator is in registers: hand it back to the MMA warp before the (rare) exact pass
+						asm volatile("tcgen05.fence::before_thread_sync;");
+						__syncwarp();
+						if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+						const float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));
+						const float tau = __fadd_ru(__fmul_ru(th, one8u), kk_s[sidx]);      // -inf for dead rows
+						const unsigned need = __ballot_sync(0xffffffffu, em <= tau);
+						n_tests += 1;
+						if (need) {                                       // warp-uniform
+							n_exact += 1;
+							const int j0 = half * (TC_TRK / 4), j1 = j0 + TC_TRK / 4;
+							const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
+							const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
+							float mm = inf;                               // the sub-tile's true minimum (see the tie rule above)
+#pragma unroll 4
+							for (int jq = j0; jq < j1; jq++) {
+								const float4 Xo = X4[jq], Yo = Y4[jq], Zo = Z4[jq];
+								u64 dx = sub2(PX, pack2(Xo.x, Xo.y)), dy = sub2(PY, pack2(Yo.x, Yo.y)), dz = sub2(PZ, pack2(Zo.x, Zo.y));
+								u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+								float aa, bb;
+								unpack2(d, aa, bb);
+								mm = min3(mm, aa, bb);
+								dx = sub2(PX, pack2(Xo.z, Xo.w)); dy = sub2(PY, pack2(Yo.z, Yo.w)); dz = sub2(PZ, pack2(Zo.z, Zo.w));
+								d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+								unpack2(d, aa, bb);
+								mm = min3(mm, aa, bb);
+							}
+							// offered whenever its threshold is <= the one read above — compared AFTER lower_threshold: in sqrt mode a
+							// distance of the current class above the class floor still ties with it (NaN / inf never pass)
+							const float nt_ = (mm < inf) ? lower_threshold<MODE>(mm) : inf;
+							if (nt_ <= th && kk_s[sidx] > -inf) {
+								atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * SUBS + half));
+							}
+						}
+					}
+					// this warp is done with the tile's originals: release the ring stage (all epilogue warps)
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&empty_bar[st]);
+				}
+			}
+			if (failed) s_fail = 1;
+			it += t1 - t0;
+			__syncthreads();
+			if (s_fail) break;
+			// ---- index recovery: the first target of the remembered sub-tile that attains the exact minimum ----
+			if (is_epi) {
+#pragma unroll 1
+				for (int q = 0; q < SPT; q++) {
+					const int a = wq + 2 * GROUPS * q;
+					const int sidx = a * 128 + row;
+					const int i = sb * SBN + sidx;
+					const u64 kv = key_s[sidx];
+					const int bs = (int)(uint32_t)(kv & 0xffffffffull);          // -1: nothing below the starting threshold
+					if (i < p.n && bs >= 0) {
+						const float th = __uint_as_float((unsigned)(kv >> 32));
+						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
+						const float* gx = p.tiles + (size_t)(bs / SUBS) * TC_TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % SUBS) * TC_TRK;
+						const float4* GX = reinterpret_cast<const float4*>(gx);
+						const float4* GY = reinterpret_cast<const float4*>(gx + TC_TN);
+						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TC_TN);
+						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
+						int found = -1;
+						for (int jq = 0; jq < TC_TRK / 4 && found < 0; jq++) {
+							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
+							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
+							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
+							float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
+							float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
+							if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+							if (d0 <= target) found = 4 * jq;
+							else if (d1 <= target) found = 4 * jq + 1;
+							else if (d2 <= target) found = 4 * jq + 2;
+							else if (d3 <= target) found = 4 * jq + 3;
+						}
+						if (found >= 0) {
+							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * TC_TRK + found);
+							atomicMin(p.keys + i, key);
+						}
+					}
+				}
+			}
+		}
+		if (s_fail) break;
+	}
+	__syncthreads();
+	if (s_fail && tid == 0) *p.fail = 1;
+	if (p.stats != nullptr && is_epi) {      // one test = one (warp, slab, sub-tile), as in K1F
+		for (int o = 16; o > 0; o >>= 1) { n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o); n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o); }
+		if (lane == 0) { atomicAdd(p.stats, n_tests / 32); atomicAdd(p.stats + 1, n_exact / 32); }
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;");
+	__syncthreads();
+	if (warp == w_mma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS));
+}
+
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +842,33 @@ static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
 	return ICPB_OK;
 }
 
+template <int GROUPS, int SLABS, int STAGES, int LDW>
+static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
+{
+	constexpr int SBN = 128 * SLABS;
+	constexpr size_t SMEM = (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TC_TILE_BYTES + (size_t)6 * SBN * 4 + 1024;
+	const int nb = (c->n + SBN - 1) / SBN;
+	p.total_units = (long long)nb * p.nt;
+	p.min_chunk = 8; p.max_chunk = 128; p.gss_div = 4;
+	if (c->kf_gss[0] > 0) { p.min_chunk = c->kf_gss[0]; p.max_chunk = c->kf_gss[1]; p.gss_div = c->kf_gss[2]; }
+	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
+	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
+	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW>;
+	static bool attr_set[2][8][64] = {};
+	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 7][c->device & 63];
+	if (!done) { ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); done = true; }
+	long long grid = c->sm_count;
+	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
+	const long long max_ctas = (p.total_units + p.min_chunk - 1) / p.min_chunk;
+	if (grid > max_ctas) grid = max_ctas;
+	ICPB_CUDA(c, cudaMemsetAsync(c->kf_work_counter, 0, sizeof(unsigned long long), c->stream));
+	kern<<<(unsigned)grid, 64 + 256 * GROUPS, SMEM, c->stream>>>(p);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+
 int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 {
 	int rc;
@@ -566,12 +891,17 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	//   0: one 256-column MMA per (slab, tile), one accumulator per epilogue group, 8 slabs, 1 CTA/SM
 	//   1: two 128-column MMAs per (slab, tile), two accumulators per group (MMA of the next unit overlaps the read of this one)
 	//   2: two CTAs per SM, each with half the TMEM: 128-column MMAs, one accumulator per group, 4 slabs, 2-stage ring
-	//   3: as 2 with 16-column TMEM loads (fewer registers)
+	//   3: as 2 with 16-column TMEM loads (fewer registers); 4: as 0 with 16-column loads
+	//   5 / 6: split form, one group of 8 warps on two accumulators (per-source state merged with atomicMin), 32- / 16-column loads
+	//   7: split form, two groups of 8 warps (16 epilogue warps), 16-column loads
 	switch (c->kt_variant) {
 	case 1:  return launch_tc_variant<1, 2, 8, 3, 1, 32>(c, dist_mode, p, 1);
 	case 2:  return launch_tc_variant<1, 1, 4, 2, 2, 32>(c, dist_mode, p, 2);
 	case 3:  return launch_tc_variant<1, 1, 4, 2, 2, 16>(c, dist_mode, p, 3);
 	case 4:  return launch_tc_variant<2, 1, 8, 3, 1, 16>(c, dist_mode, p, 4);
+	case 5:  return launch_tc_split<1, 8, 3, 32>(c, dist_mode, p, 5);
+	case 6:  return launch_tc_split<1, 8, 3, 16>(c, dist_mode, p, 6);
+	case 7:  return launch_tc_split<2, 8, 3, 16>(c, dist_mode, p, 7);
 	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
 	}
 }

@@ -97,3 +97,19 @@ int main(void) { return icpb_version() == ICPB_VERSION ? 0 : 1; }
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", PKG, "-licp_b200", "-Wl,-rpath," + PKG], check=True, capture_output=True, text=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_cmake_project_configures_with_the_reference_targets(tmp_path):
+    """CMakeLists.txt (the reference builds with CMake, /root/reference/CMakeLists.txt:1-28): the project configures for
+    sm_100a and offers the reference's target names icp_lib and icp_test next to the engine library and the programs.
+    (Configure only: the full build is what `make` / __graft_entry__.build() already does.)"""
+    import shutil
+    if shutil.which("cmake") is None:
+        pytest.skip("cmake not installed")
+    b = tmp_path / "b"
+    r = subprocess.run(["cmake", "-S", ROOT, "-B", str(b), "-G", "Ninja"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ninja = open(b / "build.ninja").read()
+    assert "compute_100a" in ninja and "sm_100a" in ninja and "sm_90" not in ninja, "sm_100a only"
+    for name in ("libicp_lib.a", "libicp_b200.so", "icp_test", "icp_standard", "icp_point_to_point", "icp_point_to_plane", "icp_batched"):
+        assert ("build %s:" % name) in ninja, name
