@@ -440,6 +440,7 @@ def run_stream_config(args, env, emit):
 
     fcfg = ctx.filter_config()
     used_filter = fcfg["dims_last"] in (2, 3)
+    used_tc = fcfg["dims_last"] == 4                 # K1T: the bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
     # Extras, outside every timed region and never allowed to disturb the contract line (config 4, one GPU only):
     #  (1) the same registration from its initial pose to convergence with the exact uniform-grid variant (ICPB_NN_GRID:
     #      occupancy pyramid over the cells, identical correspondences), device time from the engine's events;
@@ -492,6 +493,8 @@ def run_stream_config(args, env, emit):
     if rank == 0:
         fma_per_pair = fcfg["dims_last"] if used_filter else 3
         executed_frac = (achieved / 8.0) * (fma_per_pair * 2.0 if used_filter else 12.0) / fp32_peak
+        if used_tc:        # the FP32 pipe only runs the exact chain (6 ops = 12 FLOP-slots per pair) on the sub-tiles the bound cannot exclude
+            executed_frac = (achieved / 8.0) * 12.0 * fcfg["last_exact_fraction"] / fp32_peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -526,7 +529,11 @@ def run_stream_config(args, env, emit):
                          "peak_source": "FFMA microbenchmark measured in this process (icpb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
                          "kernel": ("k1_filter (brute-force NN: a %d-FMA lower bound on every pair + the reference's chain on the sub-tiles it cannot exclude)" % fcfg["dims_last"])
-                                   if used_filter else "k1_match (the reference's chain on every pair)",
+                                   if used_filter else ("k1_filter_tc (brute-force NN: the 3-D lower bound of every pair by tcgen05.mma kind::tf32 into TMEM, tcgen05.ld + FMNMX3 "
+                                                        "minimum per sub-tile, the reference's chain on the sub-tiles it cannot exclude)" if used_tc
+                                                        else "k1_match (the reference's chain on every pair)"),
+                         "tensor": ({"tf32_tflops": achieved / 8.0 * 32.0, "what": "K = 16 TF32 MACs per (source, MMA column) = 32 FLOP; dense TF32 nominal 1100 TFLOP/s; "
+                                     "the kernel is bound by the TMEM read-out + minimum and the accumulator hand-shake, not by the MMA (profiles/r02_k1t_*)"} if used_tc else None),
                          "flop_per_pair": 8, "filter": fcfg,
                          "traffic": traffic,
                          "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"},

@@ -245,7 +245,9 @@ struct Ctx {
 	int     kt_variant = 0;             // ICPB_KT_VAR: pipeline shape of K1T (nn_filter_tc.cu)
 	bool    kt_ready = false;
 	float*  kt_tiles = nullptr;         // [nt][B operand block 16 KB | X Y Z originals 3 KB], 256 targets per tile
-	int     kt_tiles_cap = 0, kt_nt = 0;
+	size_t  kt_tiles_cap = 0;           // floats allocated
+	int     kt_nt = 0;
+	bool    kt_pairs = false, kt_built_pairs = false;   // paired form (one MMA column per two consecutive targets)
 	int*    kt_fail = nullptr;          // device flag: a bounded mbarrier wait of the pipeline timed out
 
 	// iteration state

@@ -116,6 +116,94 @@ __global__ void tc_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, 
 	tile[TC_B_FLOATS + r] = x; tile[TC_B_FLOATS + TC_TN + r] = y; tile[TC_B_FLOATS + 2 * TC_TN + r] = z;
 }
 
+// ---- paired form: one MMA column per PAIR of consecutive targets -----------------------------------------------------
+// K1T is bound by what the epilogue can read out of TMEM and min-reduce, and by the MMA hand-shake per accumulator —
+// both per COLUMN. A column can stand for two targets: for a virtual target m (the float midpoint of q1, q2) and
+// h >= max(|q1 - m|, |q2 - m|),   |p - q_k|^2 >= |p - m|^2 - 2 |p - m| h   (k = 1, 2; the dropped term |q_k - m|^2 >= 0),
+// so the bracket of m, e~_m = |m - c|^2 - 2 (p - c).(m - c), evaluated by the same MMA, excludes BOTH targets when
+//     e~_m > tau + 2 H x_up,        H = max h over the sub-tile, x_up >= |p - m| for every m of the sub-tile
+// (x_up = |p - c_s| + rho_s with c_s, rho_s a ball around the sub-tile's midpoints: one distance per source and sub-tile,
+// computed in the epilogue with upward rounding). Targets that are consecutive in index are neighbours in space for
+// scan-ordered clouds (the reference's raster saddle, LiDAR sweeps): H is half the point spacing and the extra slack is
+// small exactly where it matters (near the source x_up is small). For clouds in arbitrary order H is large, every
+// sub-tile goes to the exact pass, and the host's exact-pass-rate policy falls back to one target per column.
+// Tile (512 targets): B block of the 256 midpoints | X Y Z originals of the 512 targets | per sub-tile {c_s, rho_s, H_s}.
+constexpr int TC2_TT          = 2 * TC_TN;                                   // targets per paired tile
+constexpr int TC2_HDR_FLOATS  = 16;                                          // 2 sub-tiles x {cx, cy, cz, rho, H, 0, 0, 0}
+constexpr int TC2_TILE_FLOATS = TC_B_FLOATS + 3 * TC2_TT + TC2_HDR_FLOATS;   // 5648
+constexpr int TC2_TILE_BYTES  = TC2_TILE_FLOATS * 4;                         // 22592 (a multiple of 16: one bulk copy)
+
+// one block of 128 threads per sub-tile (128 columns = 256 targets)
+__global__ void __launch_bounds__(128) tc_pack_pairs_kernel(const float4* __restrict__ q4, int m, float cx, float cy, float cz, float* __restrict__ tiles)
+{
+	const int sub = blockIdx.x;                      // global sub-tile
+	const int col = threadIdx.x;                     // column inside the sub-tile
+	float* tile = tiles + (size_t)(sub >> 1) * TC2_TILE_FLOATS;
+	const int r = (sub & 1) * 128 + col;             // B row inside the tile
+	const int j1 = sub * 256 + 2 * col, j2 = j1 + 1;
+	const float inf = __int_as_float(0x7f800000);
+	float v[TC_K];
+#pragma unroll
+	for (int k = 0; k < TC_K; k++) v[k] = 0.0f;
+	float mx = 0.f, my = 0.f, mz = 0.f, h = 0.f;
+	const bool have = j1 < m;
+	float4 a = make_float4(inf, inf, inf, 0.f), b = a;
+	if (have) {
+		a = q4[j1]; b = (j2 < m) ? q4[j2] : a;
+		mx = 0.5f * a.x + 0.5f * b.x; my = 0.5f * a.y + 0.5f * b.y; mz = 0.5f * a.z + 0.5f * b.z;     // any float point works as m
+		// h >= max |q_k - m|: the differences are exact or rounded (relative u), squares and sums rounded up, then a safety factor
+		const float d1 = __fmaf_ru(a.z - mz, a.z - mz, __fmaf_ru(a.x - mx, a.x - mx, __fmul_ru(a.y - my, a.y - my)));
+		const float d2 = __fmaf_ru(b.z - mz, b.z - mz, __fmaf_ru(b.x - mx, b.x - mx, __fmul_ru(b.y - my, b.y - my)));
+		h = __fmul_ru(__fsqrt_ru(fmaxf(d1, d2)), 1.0f + 16.0f * TC_U);
+		const float xc = __fsub_rn(mx, cx), yc = __fsub_rn(my, cy), zc = __fsub_rn(mz, cz);
+		const float w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
+		float hi, lo;
+		tf32_split(xc, hi, lo); v[0] = hi; v[1] = lo; v[2] = hi;
+		tf32_split(yc, hi, lo); v[3] = hi; v[4] = lo; v[5] = hi;
+		tf32_split(zc, hi, lo); v[6] = hi; v[7] = lo; v[8] = hi;
+		tf32_split(w, hi, lo);  v[9] = hi; v[10] = lo;
+	} else {
+		v[9] = 3.0e38f;                              // padding column: never below any tau
+	}
+#pragma unroll
+	for (int k = 0; k < TC_K; k++) tile[tc_elem(r, k)] = v[k];
+	float* X = tile + TC_B_FLOATS + (sub & 1) * 256;
+	X[2 * col] = a.x; X[2 * col + 1] = (j2 < m) ? b.x : inf;
+	X[TC2_TT + 2 * col] = a.y; X[TC2_TT + 2 * col + 1] = (j2 < m) ? b.y : inf;
+	X[2 * TC2_TT + 2 * col] = a.z; X[2 * TC2_TT + 2 * col + 1] = (j2 < m) ? b.z : inf;
+	// ball around the sub-tile's midpoints (bounding-box centre, largest distance to it) and the largest h
+	__shared__ float s_lo[4][3], s_hi[4][3], s_r[4], s_h[4], s_c[3];
+	float lo3[3] = { have ? mx : inf, have ? my : inf, have ? mz : inf }, hi3[3] = { have ? mx : -inf, have ? my : -inf, have ? mz : -inf };
+	for (int k = 0; k < 3; k++)
+		for (int o = 16; o > 0; o >>= 1) { lo3[k] = fminf(lo3[k], __shfl_xor_sync(0xffffffffu, lo3[k], o)); hi3[k] = fmaxf(hi3[k], __shfl_xor_sync(0xffffffffu, hi3[k], o)); }
+	if ((col & 31) == 0) for (int k = 0; k < 3; k++) { s_lo[col >> 5][k] = lo3[k]; s_hi[col >> 5][k] = hi3[k]; }
+	__syncthreads();
+	if (col < 3) {
+		float l = inf, u = -inf;
+		for (int w = 0; w < 4; w++) { l = fminf(l, s_lo[w][col]); u = fmaxf(u, s_hi[w][col]); }
+		float ctr = 0.5f * l + 0.5f * u;
+		if (!(ctr == ctr) || fabsf(ctr) == inf) ctr = 0.0f;
+		s_c[col] = ctr;
+	}
+	__syncthreads();
+	float rr = 0.f;
+	if (have) {
+		const float ex = mx - s_c[0], ey = my - s_c[1], ez = mz - s_c[2];
+		rr = __fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey)))), 1.0f + 16.0f * TC_U);
+	}
+	float hh = h;
+	for (int o = 16; o > 0; o >>= 1) { rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o)); hh = fmaxf(hh, __shfl_xor_sync(0xffffffffu, hh, o)); }
+	if ((col & 31) == 0) { s_r[col >> 5] = rr; s_h[col >> 5] = hh; }
+	__syncthreads();
+	if (col == 0) {
+		float* hdr = tile + TC_B_FLOATS + 3 * TC2_TT + (sub & 1) * 8;
+		hdr[0] = s_c[0]; hdr[1] = s_c[1]; hdr[2] = s_c[2];
+		hdr[3] = fmaxf(fmaxf(s_r[0], s_r[1]), fmaxf(s_r[2], s_r[3]));
+		hdr[4] = fmaxf(fmaxf(s_h[0], s_h[1]), fmaxf(s_h[2], s_h[3]));
+		hdr[5] = 0.f; hdr[6] = 0.f; hdr[7] = 0.f;
+	}
+}
+
 // ---- small PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity)
 {
@@ -500,9 +588,14 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams 
 // float below the sentinel's, so that "<=" keeps the reference's strict `d < sentinel`. A stale threshold read can only
 // cost an unnecessary exact pass, never change the result.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW>
+// TPC = targets per MMA column: 1, or 2 = the paired form (tiles of 512 targets, see tc_pack_pairs_kernel)
+template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC>
 __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const KTParams p)
 {
+	constexpr int TILE_T = TC_TN * TPC;                  // targets per tile
+	constexpr int TRK_T = TC_TRK * TPC;                  // targets per sub-tile (filter test / tracking unit)
+	constexpr int TILE_FLOATS = (TPC == 2) ? TC2_TILE_FLOATS : (TC_B_FLOATS + 3 * TC_TN);
+	constexpr int TILE_BYTES = TILE_FLOATS * 4;
 	constexpr int SUBS = TC_TN / TC_TRK;                 // 2 sub-tiles per tile = per MMA unit
 	constexpr int UNIT_COLS = TC_TN;                     // one 256-column accumulator per (slab, tile) unit
 	constexpr int TMEM_COLS = 2 * UNIT_COLS;
@@ -521,7 +614,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 
 	float* a_slabs = reinterpret_cast<float*>(tc_smem);
 	float* ring    = reinterpret_cast<float*>(tc_smem + (size_t)SLABS * TC_A_BYTES);
-	u64*   key_s   = reinterpret_cast<u64*>(tc_smem + (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TC_TILE_BYTES);
+	u64*   key_s   = reinterpret_cast<u64*>(tc_smem + (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TILE_BYTES);
 	float* ox_s    = reinterpret_cast<float*>(key_s + SBN);
 	float* oy_s    = ox_s + SBN;
 	float* oz_s    = oy_s + SBN;
@@ -637,8 +730,8 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					for (int t = t0; t < t1 && !failed; t++) {
 						const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
 						if (use >= 1 && !mbar_wait_bounded(&empty_bar[st], (uint32_t)((use - 1) & 1))) { failed = true; break; }
-						mbar_expect_tx(&full_bar[st], TC_TILE_BYTES);
-						tma_load_1d(ring + (size_t)st * TC_TILE_FLOATS, p.tiles + (size_t)t * TC_TILE_FLOATS, TC_TILE_BYTES, &full_bar[st]);
+						mbar_expect_tx(&full_bar[st], TILE_BYTES);
+						tma_load_1d(ring + (size_t)st * TILE_FLOATS, p.tiles + (size_t)t * TILE_FLOATS, TILE_BYTES, &full_bar[st]);
 					}
 				}
 			} else if (warp == w_mma) {
@@ -647,7 +740,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					for (int t = t0; t < t1 && !failed; t++) {
 						const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
 						if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
-						const uint32_t sB = smem_u32(ring + (size_t)st * TC_TILE_FLOATS);
+						const uint32_t sB = smem_u32(ring + (size_t)st * TILE_FLOATS);
 #pragma unroll 1
 						for (int a = 0; a < SLABS; a++) {
 							// GROUPS = 2: slab a belongs to group a & 1 and goes to accumulator a & 1; GROUPS = 1: the units alternate
@@ -672,10 +765,13 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 				for (int t = t0; t < t1 && !failed; t++) {
 					const int k = it + (t - t0), st = k % STAGES, use = k / STAGES;
 					if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
-					const float* tile = ring + (size_t)st * TC_TILE_FLOATS;
+					const float* tile = ring + (size_t)st * TILE_FLOATS;
 					const float4* X4 = reinterpret_cast<const float4*>(tile + TC_B_FLOATS);
-					const float4* Y4 = X4 + TC_TN / 4;
-					const float4* Z4 = Y4 + TC_TN / 4;
+					const float4* Y4 = X4 + TILE_T / 4;
+					const float4* Z4 = Y4 + TILE_T / 4;
+					// paired form: ball {c_s, rho_s} around this warp's sub-tile midpoints and H_s = the largest pair half-width
+					float hcx = 0.f, hcy = 0.f, hcz = 0.f, hrho = 0.f, hH = 0.f;
+					if (TPC == 2) { const float* hdr = tile + TC_B_FLOATS + 3 * TILE_T + half * 8; hcx = hdr[0]; hcy = hdr[1]; hcz = hdr[2]; hrho = hdr[3]; hH = hdr[4]; }
 #pragma unroll 1
 					for (int a = grp; a < SLABS; a += GROUPS) {
 						const int sidx = a * 128 + row;
@@ -691,12 +787,18 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						__syncwarp();
 						if (lane == 0) mbar_arrive(&tempty_bar[acc]);
 						const float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));
-						const float tau = __fadd_ru(__fmul_ru(th, one8u), kk_s[sidx]);      // -inf for dead rows
+						float tau = __fadd_ru(__fmul_ru(th, one8u), kk_s[sidx]);            // -inf for dead rows
+						if (TPC == 2) {
+							// + 2 H x_up, x_up >= |p - m| for every midpoint of the sub-tile, every operation rounded up
+							const float ex = ox_s[sidx] - hcx, ey = oy_s[sidx] - hcy, ez = oz_s[sidx] - hcz;
+							const float xup = __fadd_ru(__fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey)))), 1.0f + 16.0f * TC_U), hrho);
+							tau = __fmaf_ru(__fmul_ru(2.0f + 32.0f * TC_U, hH), xup, tau);
+						}
 						const unsigned need = __ballot_sync(0xffffffffu, em <= tau);
 						n_tests += 1;
 						if (need) {                                       // warp-uniform
 							n_exact += 1;
-							const int j0 = half * (TC_TRK / 4), j1 = j0 + TC_TRK / 4;
+							const int j0 = half * (TRK_T / 4), j1 = j0 + TRK_T / 4;
 							const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
 							const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
 							float mm = inf;                               // the sub-tile's true minimum (see the tie rule above)
@@ -742,13 +844,13 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					if (i < p.n && bs >= 0) {
 						const float th = __uint_as_float((unsigned)(kv >> 32));
 						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
-						const float* gx = p.tiles + (size_t)(bs / SUBS) * TC_TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % SUBS) * TC_TRK;
+						const float* gx = p.tiles + (size_t)(bs / SUBS) * TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % SUBS) * TRK_T;
 						const float4* GX = reinterpret_cast<const float4*>(gx);
-						const float4* GY = reinterpret_cast<const float4*>(gx + TC_TN);
-						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TC_TN);
+						const float4* GY = reinterpret_cast<const float4*>(gx + TILE_T);
+						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TILE_T);
 						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
 						int found = -1;
-						for (int jq = 0; jq < TC_TRK / 4 && found < 0; jq++) {
+						for (int jq = 0; jq < TRK_T / 4 && found < 0; jq++) {
 							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
 							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
 							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
@@ -761,7 +863,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 							else if (d3 <= target) found = 4 * jq + 3;
 						}
 						if (found >= 0) {
-							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * TC_TRK + found);
+							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * TRK_T + found);
 							atomicMin(p.keys + i, key);
 						}
 					}
@@ -786,20 +888,27 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 // ------------------------------------------------------------------------------------------------
 
 // Operand tiles of the current target (needs the centre chosen by build_filter_data); kept across targets of one size.
+// pairs = true: the paired form (one column per two consecutive targets, 512 targets per tile).
 int build_filter_tc_data(Ctx* c)
 {
 	const int m = c->m;
-	const int nt = (m + TC_TN - 1) / TC_TN;
-	if (nt > c->kt_tiles_cap) {
+	const bool pairs = c->kt_pairs;
+	const int tile_t = pairs ? TC2_TT : TC_TN;
+	const int tile_f = pairs ? TC2_TILE_FLOATS : TC_TILE_FLOATS;
+	const int nt = (m + tile_t - 1) / tile_t;
+	const size_t need = (size_t)nt * tile_f;
+	if (need > c->kt_tiles_cap) {
 		cudaFree(c->kt_tiles); c->kt_tiles = nullptr; c->kt_tiles_cap = 0;
-		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_tiles, sizeof(float) * (size_t)nt * TC_TILE_FLOATS));
-		c->kt_tiles_cap = nt;
+		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_tiles, sizeof(float) * need));
+		c->kt_tiles_cap = need;
 	}
 	if (!c->kt_fail) { ICPB_CUDA(c, cudaMalloc((void**)&c->kt_fail, sizeof(int))); ICPB_CUDA(c, cudaMemsetAsync(c->kt_fail, 0, sizeof(int), c->stream)); }
-	tc_pack_kernel<<<(nt * TC_TN + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * TC_TN, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	if (pairs) tc_pack_pairs_kernel<<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	else tc_pack_kernel<<<(nt * TC_TN + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * TC_TN, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	c->kt_nt = nt;
+	c->kt_built_pairs = pairs;
 	c->kt_ready = true;
 	return ICPB_OK;
 }
@@ -842,21 +951,22 @@ static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
 	return ICPB_OK;
 }
 
-template <int GROUPS, int SLABS, int STAGES, int LDW>
+template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC>
 static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 {
 	constexpr int SBN = 128 * SLABS;
-	constexpr size_t SMEM = (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TC_TILE_BYTES + (size_t)6 * SBN * 4 + 1024;
+	constexpr size_t TILE_BYTES = (TPC == 2) ? TC2_TILE_BYTES : TC_TILE_BYTES;
+	constexpr size_t SMEM = (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TILE_BYTES + (size_t)6 * SBN * 4 + 1024;
 	const int nb = (c->n + SBN - 1) / SBN;
 	p.total_units = (long long)nb * p.nt;
-	p.min_chunk = 8; p.max_chunk = 128; p.gss_div = 4;
+	p.min_chunk = 8 / TPC; p.max_chunk = 128 / TPC; p.gss_div = 4;
 	if (c->kf_gss[0] > 0) { p.min_chunk = c->kf_gss[0]; p.max_chunk = c->kf_gss[1]; p.gss_div = c->kf_gss[2]; }
 	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
 	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
 	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
-	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW>;
-	static bool attr_set[2][8][64] = {};
-	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 7][c->device & 63];
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC>;
+	static bool attr_set[2][16][64] = {};
+	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 15][c->device & 63];
 	if (!done) { ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); done = true; }
 	long long grid = c->sm_count;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
@@ -872,7 +982,9 @@ static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 {
 	int rc;
-	if (!c->kt_ready) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
+	// variants 8+ are the paired form: its tiles have another layout, rebuilt when the form changes
+	c->kt_pairs = c->kt_variant >= 8;
+	if (!c->kt_ready || c->kt_built_pairs != c->kt_pairs) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
 	KTParams p;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
 	p.tiles = c->kt_tiles; p.q4 = c->q4; p.seed_idx = c->kf_use_seed ? c->seed : nullptr; p.keys = c->keys;
@@ -894,14 +1006,17 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	//   3: as 2 with 16-column TMEM loads (fewer registers); 4: as 0 with 16-column loads
 	//   5 / 6: split form, one group of 8 warps on two accumulators (per-source state merged with atomicMin), 32- / 16-column loads
 	//   7: split form, two groups of 8 warps (16 epilogue warps), 16-column loads
+	//   8 / 9: as 7 / 6 in the PAIRED form: one column per two consecutive targets (tc_pack_pairs_kernel)
 	switch (c->kt_variant) {
 	case 1:  return launch_tc_variant<1, 2, 8, 3, 1, 32>(c, dist_mode, p, 1);
 	case 2:  return launch_tc_variant<1, 1, 4, 2, 2, 32>(c, dist_mode, p, 2);
 	case 3:  return launch_tc_variant<1, 1, 4, 2, 2, 16>(c, dist_mode, p, 3);
 	case 4:  return launch_tc_variant<2, 1, 8, 3, 1, 16>(c, dist_mode, p, 4);
-	case 5:  return launch_tc_split<1, 8, 3, 32>(c, dist_mode, p, 5);
-	case 6:  return launch_tc_split<1, 8, 3, 16>(c, dist_mode, p, 6);
-	case 7:  return launch_tc_split<2, 8, 3, 16>(c, dist_mode, p, 7);
+	case 5:  return launch_tc_split<1, 8, 3, 32, 1>(c, dist_mode, p, 5);
+	case 6:  return launch_tc_split<1, 8, 3, 16, 1>(c, dist_mode, p, 6);
+	case 7:  return launch_tc_split<2, 8, 3, 16, 1>(c, dist_mode, p, 7);
+	case 8:  return launch_tc_split<2, 8, 3, 16, 2>(c, dist_mode, p, 8);
+	case 9:  return launch_tc_split<1, 8, 3, 16, 2>(c, dist_mode, p, 9);
 	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
 	}
 }

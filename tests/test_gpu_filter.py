@@ -23,7 +23,7 @@ def _context(ib, **env):
 
 # every test runs with the bound chosen automatically (full on cold passes, planar on warm ones, switched by the
 # measured exact-pass rate), with the planar bound forced for each choice of the dropped axis, and with the full one
-@pytest.fixture(scope="module", params=["auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2"])
+@pytest.fixture(scope="module", params=["auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2", "tc-pair", "tc-pair1"])
 def ctx(ib, request):
     """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
     use the direct kernel, which would make most of these small cases vacuous)."""
@@ -33,7 +33,7 @@ def ctx(ib, request):
     elif request.param == "full":
         env.update(ICPB_KF_DIMS=3)
     elif request.param.startswith("tc"):           # K1T: the 3-D bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
-        env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7}[request.param])
+        env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7, "tc-pair": 8, "tc-pair1": 9}[request.param])
     c = _context(ib, **env)
     c.variant = request.param
     yield c
