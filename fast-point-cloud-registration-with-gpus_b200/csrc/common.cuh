@@ -241,13 +241,15 @@ struct Ctx {
 	double  kf_min_pairs = 1e9;         // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS)
 	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)
 	// K1T: the filter on the tensor cores (nn_filter_tc.cu)
-	bool    k1_use_tc = false;          // ICPB_K1_TC=1
-	int     kt_variant = 0;             // ICPB_KT_VAR: pipeline shape of K1T (nn_filter_tc.cu)
+	bool    k1_use_tc = true;           // ICPB_NN_BRUTE goes through K1T (ICPB_K1_TC=0: the FP32 filter kernel K1F)
+	int     kt_variant = -1;            // ICPB_KT_VAR: forces a pipeline shape of K1T (nn_filter_tc.cu); -1 = automatic
+	int     kt_tpc_start = 4;           // ICPB_KT_TPC: where the policy starts for a new target (1, 2, 4, 8)
+	int     kt_tpc_auto = 4;            // targets per MMA column the policy currently uses (4 -> 2 -> 1 when exact passes pile up)
 	bool    kt_ready = false;
 	float*  kt_tiles = nullptr;         // [nt][B operand block 16 KB | X Y Z originals 3 KB], 256 targets per tile
 	size_t  kt_tiles_cap = 0;           // floats allocated
 	int     kt_nt = 0;
-	bool    kt_pairs = false, kt_built_pairs = false;   // paired form (one MMA column per two consecutive targets)
+	int     kt_tpc = 1, kt_built_tpc = 0;   // targets per MMA column: 1, or 2 / 4 = the grouped forms (consecutive targets share a column)
 	int*    kt_fail = nullptr;          // device flag: a bounded mbarrier wait of the pipeline timed out
 
 	// iteration state

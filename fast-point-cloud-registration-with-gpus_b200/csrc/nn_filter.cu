@@ -453,6 +453,7 @@ static int build_filter_data(Ctx* c)
 	c->kf_rq = nextafterf(sqrtf(r2) * (1.0f + 8.0f * KF_U), INFINITY);
 	c->kf_nt = nt;
 	c->kf_dims = 2; c->kf_bounces = 0; c->kf_hold = 0;     // a new target: optimistic again
+	c->kt_tpc_auto = c->kt_tpc_start;
 	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 2 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 2 * sizeof(unsigned long long), c->stream)); }
 	c->kf_ready = true;
 	return ICPB_OK;
@@ -562,6 +563,12 @@ int kf_policy_update(Ctx* c)
 	if (dt <= 0.0) return ICPB_OK;
 	const double frac = de / dt;
 	c->kf_last_frac = frac;
+	if (c->kf_dims_last == 4) {
+		// K1T: grouped columns (4 or 2 consecutive targets per MMA column) pay off while consecutive targets are neighbours in
+		// space; when more than a fifth of the quarter tests end in the exact pass the group size is halved for this target
+		if (c->kt_variant < 0 && frac > 0.20 && c->kt_tpc_auto > 1) c->kt_tpc_auto /= 2;
+		return ICPB_OK;
+	}
 	if (c->kf_dims_last == 2 && frac > 0.10) { c->kf_dims = 3; c->kf_bounces++; c->kf_hold = 8 << c->kf_bounces; }
 	else if (c->kf_dims_last == 3 && c->kf_dims == 3 && frac < 0.01 && c->kf_bounces < 3 && c->kf_hold <= 0) c->kf_dims = 2;
 	return ICPB_OK;
@@ -578,6 +585,16 @@ extern "C" int icpb_get_filter_config(icpb_ctx* ctx, int* dims_next, int* dims_l
 	if (dims_last) *dims_last = c->kf_dims_last;
 	if (drop_axis) *drop_axis = c->kf_ready ? c->kf_drop : -1;
 	if (last_exact_fraction) *last_exact_fraction = c->kf_last_frac;
+	return ICPB_OK;
+}
+
+extern "C" int icpb_get_filter_tc_config(icpb_ctx* ctx, int* enabled, int* targets_per_column)
+{
+	using namespace icpb;
+	if (!ctx) return ICPB_ERR_BADARG;
+	Ctx* c = reinterpret_cast<Ctx*>(ctx);
+	if (enabled) *enabled = (c->k1_use_tc && c->k1_use_filter) ? 1 : 0;
+	if (targets_per_column) *targets_per_column = (c->kt_variant >= 0) ? c->kt_tpc : c->kt_tpc_auto;
 	return ICPB_OK;
 }
 

@@ -127,34 +127,46 @@ __global__ void tc_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, 
 // scan-ordered clouds (the reference's raster saddle, LiDAR sweeps): H is half the point spacing and the extra slack is
 // small exactly where it matters (near the source x_up is small). For clouds in arbitrary order H is large, every
 // sub-tile goes to the exact pass, and the host's exact-pass-rate policy falls back to one target per column.
-// Tile (512 targets): B block of the 256 midpoints | X Y Z originals of the 512 targets | per sub-tile {c_s, rho_s, H_s}.
-constexpr int TC2_TT          = 2 * TC_TN;                                   // targets per paired tile
-constexpr int TC2_HDR_FLOATS  = 16;                                          // 2 sub-tiles x {cx, cy, cz, rho, H, 0, 0, 0}
-constexpr int TC2_TILE_FLOATS = TC_B_FLOATS + 3 * TC2_TT + TC2_HDR_FLOATS;   // 5648
-constexpr int TC2_TILE_BYTES  = TC2_TILE_FLOATS * 4;                         // 22592 (a multiple of 16: one bulk copy)
+// The same holds for a group of any size around any point m; quads (TPC = 4, m = the centroid of four consecutive targets)
+// halve the columns again at the price of a larger H.
+// Tile (256 TPC targets): B block of the 256 group centres | X Y Z originals | per sub-tile {c_s, rho_s, H_s}.
+// grouped tiles: TPC targets per column (2 = pairs, 4 = quads of consecutive targets; m = their float centroid)
+__host__ __device__ constexpr int tcg_tile_targets(int tpc) { return TC_TN * tpc; }
+__host__ __device__ constexpr int tcg_tile_floats(int tpc) { return tpc == 1 ? TC_TILE_FLOATS : TC_B_FLOATS + 3 * TC_TN * tpc + 16; }   // + 2 x {cx, cy, cz, rho, H, 0, 0, 0}
 
-// one block of 128 threads per sub-tile (128 columns = 256 targets)
-__global__ void __launch_bounds__(128) tc_pack_pairs_kernel(const float4* __restrict__ q4, int m, float cx, float cy, float cz, float* __restrict__ tiles)
+// one block of 128 threads per sub-tile (128 columns = 128 TPC targets)
+template <int TPC>
+__global__ void __launch_bounds__(128) tc_pack_group_kernel(const float4* __restrict__ q4, int m, float cx, float cy, float cz, float* __restrict__ tiles)
 {
+	constexpr int TT = TC_TN * TPC;
 	const int sub = blockIdx.x;                      // global sub-tile
 	const int col = threadIdx.x;                     // column inside the sub-tile
-	float* tile = tiles + (size_t)(sub >> 1) * TC2_TILE_FLOATS;
+	float* tile = tiles + (size_t)(sub >> 1) * tcg_tile_floats(TPC);
 	const int r = (sub & 1) * 128 + col;             // B row inside the tile
-	const int j1 = sub * 256 + 2 * col, j2 = j1 + 1;
+	const int j0 = (sub * 128 + col) * TPC;
 	const float inf = __int_as_float(0x7f800000);
 	float v[TC_K];
 #pragma unroll
 	for (int k = 0; k < TC_K; k++) v[k] = 0.0f;
 	float mx = 0.f, my = 0.f, mz = 0.f, h = 0.f;
-	const bool have = j1 < m;
-	float4 a = make_float4(inf, inf, inf, 0.f), b = a;
+	const bool have = j0 < m;
+	float4 q[TPC];
+#pragma unroll
+	for (int k = 0; k < TPC; k++) q[k] = (j0 + k < m) ? q4[j0 + k] : make_float4(inf, inf, inf, 0.f);
 	if (have) {
-		a = q4[j1]; b = (j2 < m) ? q4[j2] : a;
-		mx = 0.5f * a.x + 0.5f * b.x; my = 0.5f * a.y + 0.5f * b.y; mz = 0.5f * a.z + 0.5f * b.z;     // any float point works as m
-		// h >= max |q_k - m|: the differences are exact or rounded (relative u), squares and sums rounded up, then a safety factor
-		const float d1 = __fmaf_ru(a.z - mz, a.z - mz, __fmaf_ru(a.x - mx, a.x - mx, __fmul_ru(a.y - my, a.y - my)));
-		const float d2 = __fmaf_ru(b.z - mz, b.z - mz, __fmaf_ru(b.x - mx, b.x - mx, __fmul_ru(b.y - my, b.y - my)));
-		h = __fmul_ru(__fsqrt_ru(fmaxf(d1, d2)), 1.0f + 16.0f * TC_U);
+		// m: any float point works; the centroid of the group's real members (missing ones repeat the first)
+#pragma unroll
+		for (int k = 0; k < TPC; k++) { const float4 t = (j0 + k < m) ? q[k] : q[0]; mx += t.x * (1.0f / TPC); my += t.y * (1.0f / TPC); mz += t.z * (1.0f / TPC); }
+		// h >= max |q_k - m|: differences rounded (relative u), squares and sums rounded up, then a safety factor
+		float d = 0.f;
+#pragma unroll
+		for (int k = 0; k < TPC; k++) {
+			if (j0 + k < m) {
+				const float ex = q[k].x - mx, ey = q[k].y - my, ez = q[k].z - mz;
+				d = fmaxf(d, __fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey))));
+			}
+		}
+		h = __fmul_ru(__fsqrt_ru(d), 1.0f + 16.0f * TC_U);
 		const float xc = __fsub_rn(mx, cx), yc = __fsub_rn(my, cy), zc = __fsub_rn(mz, cz);
 		const float w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
 		float hi, lo;
@@ -167,11 +179,10 @@ __global__ void __launch_bounds__(128) tc_pack_pairs_kernel(const float4* __rest
 	}
 #pragma unroll
 	for (int k = 0; k < TC_K; k++) tile[tc_elem(r, k)] = v[k];
-	float* X = tile + TC_B_FLOATS + (sub & 1) * 256;
-	X[2 * col] = a.x; X[2 * col + 1] = (j2 < m) ? b.x : inf;
-	X[TC2_TT + 2 * col] = a.y; X[TC2_TT + 2 * col + 1] = (j2 < m) ? b.y : inf;
-	X[2 * TC2_TT + 2 * col] = a.z; X[2 * TC2_TT + 2 * col + 1] = (j2 < m) ? b.z : inf;
-	// ball around the sub-tile's midpoints (bounding-box centre, largest distance to it) and the largest h
+	float* X = tile + TC_B_FLOATS + (sub & 1) * 128 * TPC + col * TPC;
+#pragma unroll
+	for (int k = 0; k < TPC; k++) { X[k] = q[k].x; X[TT + k] = q[k].y; X[2 * TT + k] = q[k].z; }
+	// ball around the sub-tile's centroids (bounding-box centre, largest distance to it) and the largest h
 	__shared__ float s_lo[4][3], s_hi[4][3], s_r[4], s_h[4], s_c[3];
 	float lo3[3] = { have ? mx : inf, have ? my : inf, have ? mz : inf }, hi3[3] = { have ? mx : -inf, have ? my : -inf, have ? mz : -inf };
 	for (int k = 0; k < 3; k++)
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(128) tc_pack_pairs_kernel(const float4* __rest
 	if ((col & 31) == 0) { s_r[col >> 5] = rr; s_h[col >> 5] = hh; }
 	__syncthreads();
 	if (col == 0) {
-		float* hdr = tile + TC_B_FLOATS + 3 * TC2_TT + (sub & 1) * 8;
+		float* hdr = tile + TC_B_FLOATS + 3 * TT + (sub & 1) * 8;
 		hdr[0] = s_c[0]; hdr[1] = s_c[1]; hdr[2] = s_c[2];
 		hdr[3] = fmaxf(fmaxf(s_r[0], s_r[1]), fmaxf(s_r[2], s_r[3]));
 		hdr[4] = fmaxf(fmaxf(s_h[0], s_h[1]), fmaxf(s_h[2], s_h[3]));
@@ -272,6 +283,22 @@ template <int LDW> __device__ __forceinline__ float subtile_min(uint32_t taddr)
 		}
 	}
 	return fminf(m0, m1);
+}
+
+// four partial minima of the 128 columns starting at taddr: columns [32 q, 32 q + 32), 16-column loads double-buffered
+__device__ __forceinline__ void subtile_min4(uint32_t taddr, float (&mq)[4])
+{
+	const float inf = __int_as_float(0x7f800000);
+	float va[16], vb[16];
+	tmem_ld16(taddr, va);
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		float m0 = inf, m1 = inf;
+		tmem_wait_ld(); tmem_ld16(taddr + 32 * q + 16, vb); min16(va, m0, m1);
+		tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+		min16(vb, m0, m1);
+		mq[q] = fminf(m0, m1);
+	}
 }
 
 // NS       sub-tiles (128 targets) per MMA: 2 = one 256-column instruction per (slab, tile), 1 = two 128-column ones
@@ -588,13 +615,17 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams 
 // float below the sentinel's, so that "<=" keeps the reference's strict `d < sentinel`. A stale threshold read can only
 // cost an unnecessary exact pass, never change the result.
 // ---------------------------------------------------------------------------------------------------------------------
-// TPC = targets per MMA column: 1, or 2 = the paired form (tiles of 512 targets, see tc_pack_pairs_kernel)
+// TPC = targets per MMA column: 1, or 2 / 4 = the grouped forms (tiles of 256 TPC targets, see tc_pack_group_kernel).
+// The filter test, the exact pass and the remembered unit are QUARTERS of a warp's sub-tile: 32 columns = 32 TPC targets
+// (the running minimum costs the same split four ways; an exact pass then covers a quarter of the targets).
 template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC>
 __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const KTParams p)
 {
 	constexpr int TILE_T = TC_TN * TPC;                  // targets per tile
 	constexpr int TRK_T = TC_TRK * TPC;                  // targets per sub-tile (filter test / tracking unit)
-	constexpr int TILE_FLOATS = (TPC == 2) ? TC2_TILE_FLOATS : (TC_B_FLOATS + 3 * TC_TN);
+	constexpr int TILE_FLOATS = tcg_tile_floats(TPC);
+	constexpr int QT = 32 * TPC;                         // targets per quarter: the unit of the exact pass and of the key's index
+	constexpr int QPT = TILE_T / QT;                     // 8 quarters per tile
 	constexpr int TILE_BYTES = TILE_FLOATS * 4;
 	constexpr int SUBS = TC_TN / TC_TRK;                 // 2 sub-tiles per tile = per MMA unit
 	constexpr int UNIT_COLS = TC_TN;                     // one 256-column accumulator per (slab, tile) unit
@@ -771,7 +802,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					const float4* Z4 = Y4 + TILE_T / 4;
 					// paired form: ball {c_s, rho_s} around this warp's sub-tile midpoints and H_s = the largest pair half-width
 					float hcx = 0.f, hcy = 0.f, hcz = 0.f, hrho = 0.f, hH = 0.f;
-					if (TPC == 2) { const float* hdr = tile + TC_B_FLOATS + 3 * TILE_T + half * 8; hcx = hdr[0]; hcy = hdr[1]; hcz = hdr[2]; hrho = hdr[3]; hH = hdr[4]; }
+					if (TPC >= 2) { const float* hdr = tile + TC_B_FLOATS + 3 * TILE_T + half * 8; hcx = hdr[0]; hcy = hdr[1]; hcz = hdr[2]; hrho = hdr[3]; hH = hdr[4]; }
 #pragma unroll 1
 					for (int a = grp; a < SLABS; a += GROUPS) {
 						const int sidx = a * 128 + row;
@@ -781,45 +812,52 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						if (!mbar_wait_bounded(&tfull_bar[acc], (uint32_t)(j & 1))) { failed = true; break; }
 						asm volatile("tcgen05.fence::after_thread_sync;");
 						const uint32_t taddr = tmem_base + (uint32_t)(acc * UNIT_COLS + half * TC_TRK) + ((uint32_t)(quarter * 32) << 16);
-						const float em = subtile_min<LDW>(taddr);
+						float mq[4];
+						subtile_min4(taddr, mq);
 						// the accumulator is in registers: hand it back to the MMA warp before the (rare) exact pass
 						asm volatile("tcgen05.fence::before_thread_sync;");
 						__syncwarp();
 						if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-						const float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));
-						float tau = __fadd_ru(__fmul_ru(th, one8u), kk_s[sidx]);            // -inf for dead rows
-						if (TPC == 2) {
-							// + 2 H x_up, x_up >= |p - m| for every midpoint of the sub-tile, every operation rounded up
+						float slack = 0.0f;
+						if (TPC >= 2) {
+							// + 2 H x_up, x_up >= |p - m| for every group centre of the sub-tile, every operation rounded up
 							const float ex = ox_s[sidx] - hcx, ey = oy_s[sidx] - hcy, ez = oz_s[sidx] - hcz;
 							const float xup = __fadd_ru(__fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey)))), 1.0f + 16.0f * TC_U), hrho);
-							tau = __fmaf_ru(__fmul_ru(2.0f + 32.0f * TC_U, hH), xup, tau);
+							slack = __fmul_ru(__fmul_ru(2.0f + 32.0f * TC_U, hH), xup);
 						}
-						const unsigned need = __ballot_sync(0xffffffffu, em <= tau);
-						n_tests += 1;
-						if (need) {                                       // warp-uniform
-							n_exact += 1;
-							const int j0 = half * (TRK_T / 4), j1 = j0 + TRK_T / 4;
-							const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
-							const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
-							float mm = inf;                               // the sub-tile's true minimum (see the tie rule above)
+						const float kk = kk_s[sidx];                                    // -inf for dead rows
+#pragma unroll
+						for (int qq = 0; qq < 4; qq++) {
+							const float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));     // re-read: an exact pass may just have lowered it
+							const float tau = __fadd_ru(__fadd_ru(__fmul_ru(th, one8u), kk), slack);
+							const unsigned need = __ballot_sync(0xffffffffu, mq[qq] <= tau);
+							n_tests += 1;
+							if (need) {                                       // warp-uniform
+								n_exact += 1;
+								const int q_in_tile = half * 4 + qq;          // quarter of the tile: targets [QT q, QT q + QT)
+								const int j0 = q_in_tile * (QT / 4), j1 = j0 + QT / 4;
+								const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
+								const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
+								float mm = inf;                               // the quarter's true minimum (see the tie rule above)
 #pragma unroll 4
-							for (int jq = j0; jq < j1; jq++) {
-								const float4 Xo = X4[jq], Yo = Y4[jq], Zo = Z4[jq];
-								u64 dx = sub2(PX, pack2(Xo.x, Xo.y)), dy = sub2(PY, pack2(Yo.x, Yo.y)), dz = sub2(PZ, pack2(Zo.x, Zo.y));
-								u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-								float aa, bb;
-								unpack2(d, aa, bb);
-								mm = min3(mm, aa, bb);
-								dx = sub2(PX, pack2(Xo.z, Xo.w)); dy = sub2(PY, pack2(Yo.z, Yo.w)); dz = sub2(PZ, pack2(Zo.z, Zo.w));
-								d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-								unpack2(d, aa, bb);
-								mm = min3(mm, aa, bb);
-							}
-							// offered whenever its threshold is <= the one read above — compared AFTER lower_threshold: in sqrt mode a
-							// distance of the current class above the class floor still ties with it (NaN / inf never pass)
-							const float nt_ = (mm < inf) ? lower_threshold<MODE>(mm) : inf;
-							if (nt_ <= th && kk_s[sidx] > -inf) {
-								atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * SUBS + half));
+								for (int jq = j0; jq < j1; jq++) {
+									const float4 Xo = X4[jq], Yo = Y4[jq], Zo = Z4[jq];
+									u64 dx = sub2(PX, pack2(Xo.x, Xo.y)), dy = sub2(PY, pack2(Yo.x, Yo.y)), dz = sub2(PZ, pack2(Zo.x, Zo.y));
+									u64 d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+									float aa, bb;
+									unpack2(d, aa, bb);
+									mm = min3(mm, aa, bb);
+									dx = sub2(PX, pack2(Xo.z, Xo.w)); dy = sub2(PY, pack2(Yo.z, Yo.w)); dz = sub2(PZ, pack2(Zo.z, Zo.w));
+									d  = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+									unpack2(d, aa, bb);
+									mm = min3(mm, aa, bb);
+								}
+								// offered whenever its threshold is <= the one read above — compared AFTER lower_threshold: in sqrt mode a
+								// distance of the current class above the class floor still ties with it (NaN / inf never pass)
+								const float nt_ = (mm < inf) ? lower_threshold<MODE>(mm) : inf;
+								if (nt_ <= th && kk > -inf) {
+									atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * QPT + q_in_tile));
+								}
 							}
 						}
 					}
@@ -844,13 +882,13 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					if (i < p.n && bs >= 0) {
 						const float th = __uint_as_float((unsigned)(kv >> 32));
 						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
-						const float* gx = p.tiles + (size_t)(bs / SUBS) * TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % SUBS) * TRK_T;
+						const float* gx = p.tiles + (size_t)(bs / QPT) * TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % QPT) * QT;
 						const float4* GX = reinterpret_cast<const float4*>(gx);
 						const float4* GY = reinterpret_cast<const float4*>(gx + TILE_T);
 						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TILE_T);
 						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
 						int found = -1;
-						for (int jq = 0; jq < TRK_T / 4 && found < 0; jq++) {
+						for (int jq = 0; jq < QT / 4 && found < 0; jq++) {
 							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
 							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
 							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
@@ -863,7 +901,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 							else if (d3 <= target) found = 4 * jq + 3;
 						}
 						if (found >= 0) {
-							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * TRK_T + found);
+							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * QT + found);
 							atomicMin(p.keys + i, key);
 						}
 					}
@@ -874,7 +912,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 	}
 	__syncthreads();
 	if (s_fail && tid == 0) *p.fail = 1;
-	if (p.stats != nullptr && is_epi) {      // one test = one (warp, slab, sub-tile), as in K1F
+	if (p.stats != nullptr && is_epi) {      // one test = one (warp, slab, quarter of a sub-tile)
 		for (int o = 16; o > 0; o >>= 1) { n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o); n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o); }
 		if (lane == 0) { atomicAdd(p.stats, n_tests / 32); atomicAdd(p.stats + 1, n_exact / 32); }
 	}
@@ -888,13 +926,13 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 // ------------------------------------------------------------------------------------------------
 
 // Operand tiles of the current target (needs the centre chosen by build_filter_data); kept across targets of one size.
-// pairs = true: the paired form (one column per two consecutive targets, 512 targets per tile).
+// kt_tpc = 2 / 4: the grouped forms (one column per two / four consecutive targets).
 int build_filter_tc_data(Ctx* c)
 {
 	const int m = c->m;
-	const bool pairs = c->kt_pairs;
-	const int tile_t = pairs ? TC2_TT : TC_TN;
-	const int tile_f = pairs ? TC2_TILE_FLOATS : TC_TILE_FLOATS;
+	const int tpc = c->kt_tpc;
+	const int tile_t = tcg_tile_targets(tpc);
+	const int tile_f = tcg_tile_floats(tpc);
 	const int nt = (m + tile_t - 1) / tile_t;
 	const size_t need = (size_t)nt * tile_f;
 	if (need > c->kt_tiles_cap) {
@@ -903,12 +941,15 @@ int build_filter_tc_data(Ctx* c)
 		c->kt_tiles_cap = need;
 	}
 	if (!c->kt_fail) { ICPB_CUDA(c, cudaMalloc((void**)&c->kt_fail, sizeof(int))); ICPB_CUDA(c, cudaMemsetAsync(c->kt_fail, 0, sizeof(int), c->stream)); }
-	if (pairs) tc_pack_pairs_kernel<<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	if (tpc == 16) tc_pack_group_kernel<16><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	else if (tpc == 8) tc_pack_group_kernel<8><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	else if (tpc == 4) tc_pack_group_kernel<4><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	else if (tpc == 2) tc_pack_group_kernel<2><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
 	else tc_pack_kernel<<<(nt * TC_TN + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * TC_TN, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	c->kt_nt = nt;
-	c->kt_built_pairs = pairs;
+	c->kt_built_tpc = tpc;
 	c->kt_ready = true;
 	return ICPB_OK;
 }
@@ -955,11 +996,11 @@ template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC>
 static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 {
 	constexpr int SBN = 128 * SLABS;
-	constexpr size_t TILE_BYTES = (TPC == 2) ? TC2_TILE_BYTES : TC_TILE_BYTES;
+	constexpr size_t TILE_BYTES = (size_t)tcg_tile_floats(TPC) * 4;
 	constexpr size_t SMEM = (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TILE_BYTES + (size_t)6 * SBN * 4 + 1024;
 	const int nb = (c->n + SBN - 1) / SBN;
 	p.total_units = (long long)nb * p.nt;
-	p.min_chunk = 8 / TPC; p.max_chunk = 128 / TPC; p.gss_div = 4;
+	p.min_chunk = (8 / TPC) > 0 ? 8 / TPC : 1; p.max_chunk = (128 / TPC) > 1 ? 128 / TPC : 2; p.gss_div = 4;      // same number of targets per grab whatever TPC
 	if (c->kf_gss[0] > 0) { p.min_chunk = c->kf_gss[0]; p.max_chunk = c->kf_gss[1]; p.gss_div = c->kf_gss[2]; }
 	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
 	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
@@ -982,9 +1023,11 @@ static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 {
 	int rc;
-	// variants 8+ are the paired form: its tiles have another layout, rebuilt when the form changes
-	c->kt_pairs = c->kt_variant >= 8;
-	if (!c->kt_ready || c->kt_built_pairs != c->kt_pairs) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
+	// targets per MMA column: forced by ICPB_KT_VAR (experiments), else chosen by the exact-pass-rate policy (kf_policy_update):
+	// it starts at kt_tpc_auto and halves whenever more than a fifth of the quarter tests end in the exact pass
+	const bool forced = c->kt_variant >= 0;
+	c->kt_tpc = !forced ? c->kt_tpc_auto : (c->kt_variant == 12) ? 16 : (c->kt_variant == 11) ? 8 : (c->kt_variant >= 10) ? 4 : (c->kt_variant >= 8 ? 2 : 1);
+	if (!c->kt_ready || c->kt_built_tpc != c->kt_tpc) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
 	KTParams p;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
 	p.tiles = c->kt_tiles; p.q4 = c->q4; p.seed_idx = c->kf_use_seed ? c->seed : nullptr; p.keys = c->keys;
@@ -1006,7 +1049,15 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	//   3: as 2 with 16-column TMEM loads (fewer registers); 4: as 0 with 16-column loads
 	//   5 / 6: split form, one group of 8 warps on two accumulators (per-source state merged with atomicMin), 32- / 16-column loads
 	//   7: split form, two groups of 8 warps (16 epilogue warps), 16-column loads
-	//   8 / 9: as 7 / 6 in the PAIRED form: one column per two consecutive targets (tc_pack_pairs_kernel)
+	//   8 / 9: as 7 / 6 in the PAIRED form: one column per two consecutive targets (tc_pack_group_kernel); 10: as 7 with QUADS
+	if (!forced) {
+		switch (c->kt_tpc) {
+		case 8:  return launch_tc_split<2, 8, 3, 16, 8>(c, dist_mode, p, 11);
+		case 4:  return launch_tc_split<2, 8, 3, 16, 4>(c, dist_mode, p, 10);
+		case 2:  return launch_tc_split<2, 8, 3, 16, 2>(c, dist_mode, p, 8);
+		default: return launch_tc_split<2, 8, 3, 16, 1>(c, dist_mode, p, 7);
+		}
+	}
 	switch (c->kt_variant) {
 	case 1:  return launch_tc_variant<1, 2, 8, 3, 1, 32>(c, dist_mode, p, 1);
 	case 2:  return launch_tc_variant<1, 1, 4, 2, 2, 32>(c, dist_mode, p, 2);
@@ -1017,6 +1068,9 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	case 7:  return launch_tc_split<2, 8, 3, 16, 1>(c, dist_mode, p, 7);
 	case 8:  return launch_tc_split<2, 8, 3, 16, 2>(c, dist_mode, p, 8);
 	case 9:  return launch_tc_split<1, 8, 3, 16, 2>(c, dist_mode, p, 9);
+	case 10: return launch_tc_split<2, 8, 3, 16, 4>(c, dist_mode, p, 10);
+	case 11: return launch_tc_split<2, 8, 3, 16, 8>(c, dist_mode, p, 11);
+	case 12: return launch_tc_split<2, 8, 2, 16, 16>(c, dist_mode, p, 12);
 	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
 	}
 }

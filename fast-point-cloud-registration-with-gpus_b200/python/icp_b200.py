@@ -72,6 +72,7 @@ def _load():
         "icpb_get_grid_stats": (C.c_int, [vp, dp, ip, ip, fp]),
         "icpb_get_filter_stats": (C.c_int, [vp, dp, dp]),
         "icpb_get_filter_config": (C.c_int, [vp, ip, ip, ip, dp]),
+        "icpb_get_filter_tc_config": (C.c_int, [vp, ip, ip]),
         "icpb_launch_count": (C.c_longlong, [vp]),
         "icpb_host_alloc": (C.c_int, [C.POINTER(vp), C.c_ulonglong]),
         "icpb_host_free": (C.c_int, [vp]),
@@ -316,6 +317,11 @@ class Context:
         a, b, d, f = C.c_int(), C.c_int(), C.c_int(), C.c_double()
         self._ck(lib.icpb_get_filter_config(self.h, C.byref(a), C.byref(b), C.byref(d), C.byref(f)), "get_filter_config")
         return {"dims_next": a.value, "dims_last": b.value, "drop_axis": d.value, "last_exact_fraction": f.value}
+
+    def filter_tc_config(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(lib.icpb_get_filter_tc_config(self.h, C.byref(a), C.byref(b)), "get_filter_tc_config")
+        return {"enabled": bool(a.value), "targets_per_column": b.value}
 
     def dist_info(self):
         r, w, p = C.c_int(), C.c_int(), C.c_int()

@@ -43,9 +43,10 @@ extern "C" {
 #define ICPB_POINT_TO_POINT 0   /* centroids, 3x3 cross-covariance, SVD, R = U*V^T   src/ICP_point_to_point.cu:313-398 */
 #define ICPB_POINT_TO_PLANE 1   /* 6x6 normal equations, Cholesky, Euler -> R        src/ICP_point_to_plane.cu:537-601 */
 
-#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method): a rigorous 2- or 3-FMA lower
-                                   bound is evaluated for every pair and the reference's chain wherever the bound cannot
-                                   exclude the pair's 128-target sub-tile; identical indices (icpb_get_filter_config) */
+#define ICPB_NN_BRUTE 0         /* exact brute force over every target (the reference's method): a rigorous lower bound is
+                                   evaluated for every pair — on the tensor cores (tcgen05.mma kind::tf32, K1T) or with 2-3 FMAs
+                                   (K1F) — and the reference's chain wherever the bound cannot exclude the pair's sub-tile;
+                                   identical indices (icpb_get_filter_config, icpb_get_filter_tc_config) */
 #define ICPB_NN_GRID  1         /* exact uniform-grid search, identical indices */
 #define ICPB_NN_BRUTE_DIRECT 2  /* exact brute force, the reference's chain evaluated for every pair (no pruning) */
 
@@ -257,6 +258,10 @@ int  icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile
  * bound leaves out for the current target (-1 before the first launch); last_exact_fraction: share of sub-tile tests
  * that needed the exact chain, as last sampled. Results never depend on any of this. */
 int  icpb_get_filter_config(icpb_ctx* ctx, int* dims_next, int* dims_last, int* drop_axis, double* last_exact_fraction);
+/* ICPB_NN_BRUTE on the tensor cores (K1T, the default; ICPB_K1_TC=0 selects the FP32 filter): `enabled`, and how many
+ * consecutive targets share one MMA column in the launches to come (1, 2, 4 or 8; chosen from the measured exact-pass rate).
+ * icpb_get_filter_config reports dims_last == 4 after a K1T launch. Results never depend on any of this. */
+int  icpb_get_filter_tc_config(icpb_ctx* ctx, int* enabled, int* targets_per_column);
 /* Number of kernels this context has launched since creation. */
 long long icpb_launch_count(const icpb_ctx* ctx);
 

@@ -23,17 +23,19 @@ def _context(ib, **env):
 
 # every test runs with the bound chosen automatically (full on cold passes, planar on warm ones, switched by the
 # measured exact-pass rate), with the planar bound forced for each choice of the dropped axis, and with the full one
-@pytest.fixture(scope="module", params=["auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2", "tc-pair", "tc-pair1"])
+@pytest.fixture(scope="module", params=["tc-auto", "auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2", "tc-pair", "tc-pair1", "tc-quad", "tc-oct", "tc-hex"])
 def ctx(ib, request):
     """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
     use the direct kernel, which would make most of these small cases vacuous)."""
-    env = {"ICPB_K1_FILTER_MIN_PAIRS": 0}
-    if request.param.startswith("planar"):
+    env = {"ICPB_K1_FILTER_MIN_PAIRS": 0, "ICPB_K1_TC": 0}       # K1F variants: the FP32 filter kernel
+    if request.param == "tc-auto":                 # the default: K1T, group size chosen by the exact-pass-rate policy
+        env.update(ICPB_K1_TC=1)
+    elif request.param.startswith("planar"):
         env.update(ICPB_KF_DIMS=2, ICPB_KF_DROP="xyz".index(request.param[-1]))
     elif request.param == "full":
         env.update(ICPB_KF_DIMS=3)
     elif request.param.startswith("tc"):           # K1T: the 3-D bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
-        env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7, "tc-pair": 8, "tc-pair1": 9}[request.param])
+        env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc-auto": -1, "tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7, "tc-pair": 8, "tc-pair1": 9, "tc-quad": 10, "tc-oct": 11, "tc-hex": 12}[request.param])
     c = _context(ib, **env)
     c.variant = request.param
     yield c
@@ -50,6 +52,8 @@ def _check(ctx, ib, orc, P, Q, modes=(0, 1), sentinel=100000.0, oracle=True, exp
             if expect_filter:
                 cfg = ctx.filter_config()
                 want = {"planar": 2, "full": 3, "tc": 4}.get(ctx.variant.split("-")[0])
+                if ctx.variant == "auto":
+                    assert cfg["dims_last"] in (2, 3)
                 assert want is None or cfg["dims_last"] == want, (ctx.variant, cfg)
                 if ctx.variant.startswith("planar"):
                     assert cfg["drop_axis"] == "xyz".index(ctx.variant[-1])
@@ -149,7 +153,7 @@ def test_planar_bound_policy(ib, orc):
     """Automatic choice: on the 1M-point saddle the planar bound stays in use once the pass is warm (few sub-tiles
     reach the exact chain); on a small volumetric cloud whose thresholds are of the order of the point spacing its
     exact-pass rate is high and the engine goes back to the full bound. Same indices either way."""
-    c = _context(ib, ICPB_K1_FILTER_MIN_PAIRS=0)
+    c = _context(ib, ICPB_K1_FILTER_MIN_PAIRS=0, ICPB_K1_TC=0)
     try:
         D, M = orc.synth_p2p(1000)
         c.set_target(M); c.set_source(D)

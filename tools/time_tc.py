@@ -16,7 +16,7 @@ D, M = icp_synth.p2p_clouds(W)
 out = {}
 ref_idx = None
 variants = [int(v) for v in os.environ.get("TC_VARIANTS", "0,1,2,3,4").split(",")]
-cases = [("k1t_var%d" % v, {"ICPB_K1_TC": "1", "ICPB_KT_VAR": str(v)}) for v in variants] + [("k1f_fp32", {})]
+cases = [("k1t_var%d" % v, {"ICPB_K1_TC": "1", "ICPB_KT_VAR": str(v)}) for v in variants if v >= 0] + [("k1t_auto", {"ICPB_K1_TC": "1"}), ("k1f_fp32", {"ICPB_K1_TC": "0"})]
 for name, env in cases:
     os.environ.pop("ICPB_K1_TC", None); os.environ.pop("ICPB_KT_VAR", None)
     os.environ.update(env)
@@ -29,7 +29,8 @@ for name, env in cases:
         st = ctx.filter_stats()
         idx = ctx.correspondences()
         out[name] = {"match_ms_per_iteration": per_it, "pairs_per_sec_last": float(D.shape[0]) * M.shape[0] / (per_it[-1] * 1e-3),
-                     "exact_fraction_overall": st["subtile_exact"] / max(st["subtile_tests"], 1), "final_rms": float(e[1])}
+                     "exact_fraction_overall": st["subtile_exact"] / max(st["subtile_tests"], 1), "final_rms": float(e[1]),
+                     "tc_config": ctx.filter_tc_config()}
         if ref_idx is None:
             ref_idx = idx
         else:
