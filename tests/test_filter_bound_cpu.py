@@ -117,3 +117,106 @@ def test_bound_holds_on_lattices_and_flat_clouds():
     check_cloud(P, Q)
     Q[:, 1] = Q[:, 0]                                                          # collinear
     check_cloud(P, Q)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K1T (csrc/nn_filter_tc.cu): the same bound with the bracket evaluated by tcgen05.mma kind::tf32 — operands as round-to-
+# nearest TF32 hi + lo pairs, products hi*hi + hi*lo + lo*hi per coordinate, w as hi + lo — and eps multiplied by 16; and
+# the grouped form, where one column stands for TPC consecutive targets through their centroid m:
+#       e~_m  <=  tau(d_chain_k) + 2 H x_up         for every member k of the group
+# The tensor core's own accumulation rounding is not specified; the kernel budgets 60 u of sum |terms| for it (measured
+# on B200: 2.2 u, tools/ubench_tc_filter check). Here the products are summed exactly and the WORST case of that budget is
+# added to e~ before the comparison, so the test covers any accumulation order within the budget.
+# ---------------------------------------------------------------------------------------------------------------------
+def tf32_rn(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0xfff + ((u >> 13) & 1)) & 0xffffe000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def tf32_split(x):
+    hi = tf32_rn(x)
+    lo = tf32_rn((np.asarray(x, np.float32) - hi).astype(np.float32))
+    return hi, lo
+
+
+def tc_bracket(pc, mc, w):
+    """e~ for sources pc [n,3] against columns mc [g,3], w [g]: exact sum of the 11 TF32 products + the accumulation budget."""
+    a = (F(-2.0) * pc).astype(np.float32)
+    e = np.zeros((pc.shape[0], mc.shape[0]), np.float64); mag = np.zeros_like(e)
+    for c in range(3):
+        ah, al = tf32_split(a[:, c]); qh, ql = tf32_split(mc[:, c])
+        for x, y in ((ah, qh), (ah, ql), (al, qh)):
+            t = x.astype(np.float64)[:, None] * y.astype(np.float64)[None, :]
+            e += t; mag += np.abs(t)
+    wh, wl = tf32_split(w)
+    for y in (wh, wl):
+        e += y.astype(np.float64)[None, :]; mag += np.abs(y.astype(np.float64))[None, :]
+    return e + 60.0 * float(U) * mag                      # worst case of the accumulation budget (makes skipping harder to justify)
+
+
+def check_cloud_tc(P, Q, tpc):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    m = Q.shape[0] - Q.shape[0] % tpc
+    Q = Q[:m]
+    ctr = (F(0.5) * Q.min(axis=0) + F(0.5) * Q.max(axis=0)).astype(np.float32)
+    qc_all = (Q - ctr).astype(np.float32)
+    rq = np.nextafter(F(np.sqrt(F(chain(qc_all[:, 0], qc_all[:, 1], qc_all[:, 2]).max())) * ONE8U), F(np.inf))       # kf_rq over the TARGETS
+    G = Q.reshape(-1, tpc, 3)
+    if tpc == 1:
+        M = G[:, 0, :].copy(); H = np.zeros(M.shape[0], np.float32)
+    else:
+        M = np.zeros((G.shape[0], 3), np.float32)
+        for k in range(tpc):
+            M = (M + G[:, k, :] * F(1.0 / tpc)).astype(np.float32)            # the kernel's centroid, same operation order
+        dd = np.zeros(G.shape[0], np.float32)
+        for k in range(tpc):
+            ex = (G[:, k, :] - M).astype(np.float32)
+            dk = fma_ru(ex[:, 2], ex[:, 2], fma_ru(ex[:, 0], ex[:, 0], mul_ru(ex[:, 1], ex[:, 1])))
+            dd = np.maximum(dd, dk)
+        H = mul_ru(sqrt_ru(dd), F(1.0) + F(16.0) * U)
+    mc = (M - ctr).astype(np.float32)
+    w = chain(mc[:, 0], mc[:, 1], mc[:, 2])
+    pc = (P - ctr).astype(np.float32)
+    p2 = chain(pc[:, 0], pc[:, 1], pc[:, 2])
+    p2lo = mul_rd(p2, F(1.0) - F(8.0) * U)
+    rp = mul_ru(sqrt_ru(p2), ONE8U)
+    eps = mul_ru(F(8.0) * rq, rq) * np.ones_like(rp)
+    eps = fma_ru(F(10.0) * rp, rq * np.ones_like(rp), eps)
+    eps = fma_ru(F(2.0) * rp, rp, eps)
+    eps = mul_ru(eps, F(1.05) * F(16.0) * U)                                  # TC_EPS_SCALE = 16
+    kk = sub_ru(eps, p2lo)
+    e = tc_bracket(pc, mc, w)
+    # the slack of the grouped form with the ball of ALL group centres as the "sub-tile" (the kernel uses 128 columns: a subset, so
+    # its c_s / rho_s / H_s are no larger than these)
+    cs = (F(0.5) * M.min(axis=0) + F(0.5) * M.max(axis=0)).astype(np.float32)
+    em = (M - cs).astype(np.float32)
+    rho = float(mul_ru(sqrt_ru(fma_ru(em[:, 2], em[:, 2], fma_ru(em[:, 0], em[:, 0], mul_ru(em[:, 1], em[:, 1])))), F(1.0) + F(16.0) * U).max())
+    ep = (P - cs).astype(np.float32)
+    xup = add_ru(mul_ru(sqrt_ru(fma_ru(ep[:, 2], ep[:, 2], fma_ru(ep[:, 0], ep[:, 0], mul_ru(ep[:, 1], ep[:, 1])))), F(1.0) + F(16.0) * U), F(rho))
+    slack = mul_ru(mul_ru(F(2.0) + F(32.0) * U, F(H.max())), xup) if tpc > 1 else np.zeros(P.shape[0], np.float32)
+    for k in range(tpc):
+        Qk = G[:, k, :]
+        d = chain((P[:, None, 0] - Qk[None, :, 0]).astype(np.float32), (P[:, None, 1] - Qk[None, :, 1]).astype(np.float32),
+                  (P[:, None, 2] - Qk[None, :, 2]).astype(np.float32))
+        tau = add_ru(add_ru(mul_ru(d, ONE8U), np.broadcast_to(kk[:, None], d.shape)), np.broadcast_to(slack[:, None], d.shape))
+        ok = e <= tau.astype(np.float64)
+        assert ok.all(), "K1T bound violated (tpc %d, member %d) at %d pairs" % (tpc, k, (~ok).sum())
+
+
+@pytest.mark.parametrize("tpc", [1, 2, 4, 8])
+def test_tensor_core_bound_single_and_grouped_columns(orc, tpc):
+    rng = np.random.default_rng(40 + tpc)
+    base_q = rng.normal(size=(640, 3)); base_p = rng.normal(size=(300, 3))
+    for shift, scale in ((0.0, 1.0), (1000.0, 1.0), (-5e4, 30.0), (0.0, 1e-4), (123456.0, 0.5)):
+        Q = (base_q * scale + shift).astype(np.float32)
+        P = (base_p * scale + shift).astype(np.float32)
+        P[:10] += np.float32(50 * scale)
+        check_cloud_tc(P, Q, tpc)
+    D, M = orc.synth_p2p(40)                                                   # raster order: consecutive targets are neighbours
+    check_cloud_tc(M[:400], M, tpc)                                            # exact coincidence
+    check_cloud_tc(np.nextafter(M[:400], np.float32(np.inf)), M, tpc)
+    check_cloud_tc(orc.icp_p2p(D, M, max_iter=30)["P"][:500], M, tpc)
+    check_cloud_tc(D[:500], M, tpc)
+    L = (rng.integers(-8, 9, size=(640, 3)) * 0.25).astype(np.float32)         # lattice with duplicates: groups of identical points
+    check_cloud_tc((rng.integers(-16, 17, size=(300, 3)) * 0.125).astype(np.float32), L, tpc)
