@@ -218,6 +218,7 @@ struct Ctx {
 	bool    kf_ready = false;
 	float*  kf_tiles7 = nullptr;        // [nt][X Y Z | Xc Yc Zc | W3 W2][512]
 	int     kf_tiles_cap = 0;           // tiles allocated (kept across targets of the same size)
+	bool    kf_tiles_built = false;     // kf_tiles7 holds the current target (false when only centre + radius were computed for K1T)
 	unsigned long long* kf_scratch = nullptr;   // bbox / radius / axis-score scratch of build_filter_data
 	float   kf_center[3] = {0, 0, 0};
 	float   kf_rq = 0.f;                // >= max |q - centre|
@@ -238,12 +239,14 @@ struct Ctx {
 	unsigned long long kf_stats_seen[2] = {0, 0};
 	double  kf_last_frac = 0.0;
 	bool    kf_use_seed = true;         // warm start from the previous correspondences
-	double  kf_min_pairs = 1e9;         // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS)
+	double  kf_min_pairs = 2.5e8;       // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS); K1T pays off
+	                                    // from 16 384 x 16 384 (62 us against 85 us per pass), K1F (ICPB_K1_TC=0) from ~3e4 x 3e4
 	bool    k1_use_filter = true;       // ICPB_NN_BRUTE goes through the filter kernel (ICPB_K1_FILTER=0 disables)
 	// K1T: the filter on the tensor cores (nn_filter_tc.cu)
 	bool    k1_use_tc = true;           // ICPB_NN_BRUTE goes through K1T (ICPB_K1_TC=0: the FP32 filter kernel K1F)
 	int     kt_variant = -1;            // ICPB_KT_VAR: forces a pipeline shape of K1T (nn_filter_tc.cu); -1 = automatic
 	int     kt_tpc_start = 4;           // ICPB_KT_TPC: where the policy starts for a new target (1, 2, 4, 8)
+	int     kt_policy_m = -1;           // target size the policy state belongs to
 	int     kt_tpc_auto = 4;            // targets per MMA column the policy currently uses (4 -> 2 -> 1 when exact passes pile up)
 	bool    kt_ready = false;
 	float*  kt_tiles = nullptr;         // [nt][B operand block 16 KB | X Y Z originals 3 KB], 256 targets per tile

@@ -179,6 +179,7 @@ int create_context(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_FILTER")) c->k1_use_filter = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_SEED")) c->kf_use_seed = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_K1_TC")) c->k1_use_tc = atoi(e) != 0;
+	if (!c->k1_use_tc && !getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = 1e9;      // the FP32 filter's own crossover
 	if (const char* e = getenv("ICPB_KT_VAR")) c->kt_variant = atoi(e);
 	if (const char* e = getenv("ICPB_KT_TPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) { c->kt_tpc_start = v; c->kt_tpc_auto = v; } }
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);

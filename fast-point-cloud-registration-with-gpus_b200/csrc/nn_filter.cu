@@ -94,6 +94,7 @@ __global__ void kf_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, 
 		w2 = __fmaf_rn(a, a, __fmul_rn(b, b));
 		atomicMax(r2max, __float_as_uint(w));        // w >= 0: uint order = float order
 	}
+	if (tiles7 == nullptr) return;                 // K1T only needs the radius bound (its own tiles: nn_filter_tc.cu)
 	float* t = tiles7 + (size_t)(j / KF_TT) * KF_TILE_FLOATS + (j % KF_TT);
 	t[0] = x; t[KF_TT] = y; t[2 * KF_TT] = z; t[3 * KF_TT] = xc; t[4 * KF_TT] = yc; t[5 * KF_TT] = zc; t[6 * KF_TT] = w; t[7 * KF_TT] = w2;
 }
@@ -417,9 +418,14 @@ static int build_filter_data(Ctx* c)
 	ICPB_CUDA(c, cudaMemsetAsync(score, 0, 3 * sizeof(unsigned long long), c->stream));
 	kf_bbox_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->q4, m, scratch);
 	c->launches++;
+	// K1T (the default) needs the centre and the radius bound only; the planar axis score and K1F's 32-byte-per-target tiles
+	// are built when the FP32 filter kernel is the one in use
+	const bool fp32_tiles = !c->k1_use_tc;
 	// the axis the planar bound leaves out: the projection that keeps the sub-tiles best separated
-	kf_score_kernel<<<(m + KF_TRK - 1) / KF_TRK, KF_TRK, 0, c->stream>>>(c->q4, m, score);
-	c->launches++;
+	if (fp32_tiles) {
+		kf_score_kernel<<<(m + KF_TRK - 1) / KF_TRK, KF_TRK, 0, c->stream>>>(c->q4, m, score);
+		c->launches++;
+	}
 	unsigned h[8];
 	unsigned long long hs[3] = { 0, 0, 0 };
 	ICPB_CUDA(c, cudaMemcpyAsync(h, scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -438,12 +444,14 @@ static int build_filter_data(Ctx* c)
 	if (c->kf_drop_forced >= 0 && c->kf_drop_forced <= 2) drop = c->kf_drop_forced;
 	c->kf_drop = drop;
 	for (int k = 0; k < 3; k++) c->kf_score[k] = (double)hs[k];
-	if (nt > c->kf_tiles_cap) {
+	if (fp32_tiles && nt > c->kf_tiles_cap) {
 		cudaFree(c->kf_tiles7); c->kf_tiles7 = nullptr; c->kf_tiles_cap = 0;
 		ICPB_CUDA(c, cudaMalloc((void**)&c->kf_tiles7, sizeof(float) * (size_t)nt * KF_TILE_FLOATS));
 		c->kf_tiles_cap = nt;
 	}
-	kf_pack_kernel<<<(nt * KF_TT + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * KF_TT, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_drop, c->kf_tiles7, scratch + 6);
+	kf_pack_kernel<<<(nt * KF_TT + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * KF_TT, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_drop,
+	                                                                 fp32_tiles ? c->kf_tiles7 : nullptr, scratch + 6);
+	c->kf_tiles_built = fp32_tiles;
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	ICPB_CUDA(c, cudaMemcpyAsync(h, scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -453,7 +461,9 @@ static int build_filter_data(Ctx* c)
 	c->kf_rq = nextafterf(sqrtf(r2) * (1.0f + 8.0f * KF_U), INFINITY);
 	c->kf_nt = nt;
 	c->kf_dims = 2; c->kf_bounces = 0; c->kf_hold = 0;     // a new target: optimistic again
-	c->kt_tpc_auto = c->kt_tpc_start;
+	// K1T's group size starts over only for a target of another size: a same-size upload is, as a rule, the same cloud again
+	// (a host-driven loop re-uploads the target at every step) and keeps what the exact-pass rate has taught
+	if (c->m != c->kt_policy_m) { c->kt_tpc_auto = c->kt_tpc_start; c->kt_policy_m = c->m; }
 	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 2 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 2 * sizeof(unsigned long long), c->stream)); }
 	c->kf_ready = true;
 	return ICPB_OK;
@@ -543,6 +553,7 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 	// the direct kernel.
 	if (!std::isfinite(c->kf_rq) || c->kf_rq > 1e15f || c->kf_rq < 1e-15f) return launch_match_brute(c, dist_mode, sentinel);
 	if (c->k1_use_tc) return launch_match_filter_tc(c, dist_mode, sentinel);      // K1T: the same bound on the tensor cores (nn_filter_tc.cu)
+	if (!c->kf_tiles_built) { if ((rc = build_filter_data(c)) != ICPB_OK) return rc; }
 	return (c->kf_s == 16) ? launch_filter_cfg<16, 1>(c, dist_mode, sentinel) : launch_filter_cfg<8, 2>(c, dist_mode, sentinel);
 }
 

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(RB) transform_kernel(const ReduceParams p)
 // ------------------------------------------------------------------------------------------------
 // Layout kernels: AoS xyz <-> SoA, and the target re-tiling done once per registration
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_source_kernel(const float* __restrict__ xyz, int n, int n_cap, float* px, float* py, float* pz, u64* keys, int* idx, int* seed, int reset_seed)
+__global__ void pack_source_kernel(const float* __restrict__ xyz, int n, int n_cap, float* px, float* py, float* pz, u64* keys, int* idx, int* seed, int reset_seed, int m)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_cap) return;
@@ -330,7 +330,10 @@ __global__ void pack_source_kernel(const float* __restrict__ xyz, int n, int n_c
 	if (i < n) { x = xyz[3 * (size_t)i]; y = xyz[3 * (size_t)i + 1]; z = xyz[3 * (size_t)i + 2]; }
 	px[i] = x; py[i] = y; pz[i] = z;
 	keys[i] = KEY_UNMATCHED; idx[i] = 0;
-	if (reset_seed) seed[i] = 0;
+	// a fresh warm-start seed: ANY target index is a valid upper bound of the minimum, so this only affects the speed of the
+	// first (cold) matching pass. The target at the same relative position in index order is a far better guess than
+	// target 0 for scans of the same sensor / moved copies of one cloud, and as good as any other otherwise.
+	if (reset_seed) seed[i] = (m > 0 && n > 0 && i < n) ? (int)(((long long)i * m) / n) : 0;
 }
 __global__ void unpack_source_kernel(const float* px, const float* py, const float* pz, int n, float* __restrict__ xyz)
 {
@@ -441,7 +444,7 @@ int launch_resolve(Ctx* c, float sentinel)
 }
 int launch_pack_source(Ctx* c, const float* d_xyz, int n, bool reset_seed)
 {
-	pack_source_kernel<<<(c->n_cap + 255) / 256, 256, 0, c->stream>>>(d_xyz, n, c->n_cap, c->px, c->py, c->pz, c->keys, c->idx, c->seed, reset_seed ? 1 : 0);
+	pack_source_kernel<<<(c->n_cap + 255) / 256, 256, 0, c->stream>>>(d_xyz, n, c->n_cap, c->px, c->py, c->pz, c->keys, c->idx, c->seed, reset_seed ? 1 : 0, c->m);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	return ICPB_OK;
