@@ -485,9 +485,10 @@ def run_stream_config(args, env, emit):
         except Exception as exc:      # noqa: BLE001
             floor_extra = {"error": str(exc)[:200]}
     traffic = None
+    tc_tpc = ctx.filter_tc_config()["targets_per_column"] if used_tc else 0
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
-        traffic = tj.get("k1_filter", {}).get(str(args.width or cfg["width"]))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k1_traffic.json")))
+        traffic = tj.get("k1_filter_tc" if used_tc else "k1_filter", {}).get(str(args.width or cfg["width"]))
     except Exception:      # noqa: BLE001
         pass
     if rank == 0:
@@ -532,11 +533,13 @@ def run_stream_config(args, env, emit):
                                    if used_filter else ("k1_filter_tc (brute-force NN: the 3-D lower bound of every pair by tcgen05.mma kind::tf32 into TMEM, tcgen05.ld + FMNMX3 "
                                                         "minimum per sub-tile, the reference's chain on the sub-tiles it cannot exclude)" if used_tc
                                                         else "k1_match (the reference's chain on every pair)"),
-                         "tensor": ({"tf32_tflops": achieved / 8.0 * 32.0, "what": "K = 16 TF32 MACs per (source, MMA column) = 32 FLOP; dense TF32 nominal 1100 TFLOP/s; "
-                                     "the kernel is bound by the TMEM read-out + minimum and the accumulator hand-shake, not by the MMA (profiles/r02_k1t_*)"} if used_tc else None),
+                         "tensor": ({"tf32_tflops": achieved / 8.0 * 32.0 / max(1, tc_tpc), "targets_per_column": tc_tpc,
+                                     "what": "one MMA column stands for targets_per_column consecutive targets (their centroid + a slack term); K = 16 TF32 MACs per "
+                                     "(source, column) = 32 FLOP; dense TF32 nominal 1100 TFLOP/s; the kernel is bound by the TMEM read-out + minimum and the accumulator "
+                                     "hand-shake, not by the MMA (profiles/r02_k1t_*)"} if used_tc else None),
                          "flop_per_pair": 8, "filter": fcfg,
                          "traffic": traffic,
-                         "traffic_source": "profiles/r01_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"},
+                         "traffic_source": "profiles/r02_k1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"},
             "roofline_direct_kernel": {"kernel": "k1_match (reference chain on every pair)", "ms_per_launch": direct_ms,
                                        "achieved": 8.0 * float(n_rank) * m / (direct_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
                                        "frac": 8.0 * float(n_rank) * m / (direct_ms * 1e-3) * 1e-12 / fp32_peak},

@@ -949,6 +949,7 @@ int build_filter_tc_data(Ctx* c)
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	c->kt_nt = nt;
+	if (c->kt_built_tpc != tpc) c->graph_gen++;      // a captured iteration graph holds the kernel of the old group size: its tiles are gone
 	c->kt_built_tpc = tpc;
 	c->kt_ready = true;
 	return ICPB_OK;
