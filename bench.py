@@ -441,6 +441,7 @@ def run_stream_config(args, env, emit):
     fcfg = ctx.filter_config()
     used_filter = fcfg["dims_last"] in (2, 3)
     used_tc = fcfg["dims_last"] == 4                 # K1T: the bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
+    tc_tpc = ctx.filter_tc_config()["targets_per_column"] if used_tc else 0
     # Extras, outside every timed region and never allowed to disturb the contract line (config 4, one GPU only):
     #  (1) the same registration from its initial pose to convergence with the exact uniform-grid variant (ICPB_NN_GRID:
     #      occupancy pyramid over the cells, identical correspondences), device time from the engine's events;
@@ -485,7 +486,6 @@ def run_stream_config(args, env, emit):
         except Exception as exc:      # noqa: BLE001
             floor_extra = {"error": str(exc)[:200]}
     traffic = None
-    tc_tpc = ctx.filter_tc_config()["targets_per_column"] if used_tc else 0
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k1_traffic.json")))
         traffic = tj.get("k1_filter_tc" if used_tc else "k1_filter", {}).get(str(args.width or cfg["width"]))

@@ -127,6 +127,7 @@ int  kf_policy_update(Ctx* c);
 int  prepare_match_filter(Ctx* c);
 int  prepare_match_grid(Ctx* c);
 int  build_filter_tc_data(Ctx* c);
+int  ensure_filter_tc_data(Ctx* c);
 int  launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel);
 int  filter_tc_check(Ctx* c);
 int  launch_moments(Ctx* c, int metric);
@@ -245,15 +246,26 @@ struct Ctx {
 	// K1T: the filter on the tensor cores (nn_filter_tc.cu)
 	bool    k1_use_tc = true;           // ICPB_NN_BRUTE goes through K1T (ICPB_K1_TC=0: the FP32 filter kernel K1F)
 	int     kt_variant = -1;            // ICPB_KT_VAR: forces a pipeline shape of K1T (nn_filter_tc.cu); -1 = automatic
-	int     kt_tpc_start = 4;           // ICPB_KT_TPC: where the policy starts for a new target (1, 2, 4, 8)
+	int     kt_tpc_start = 8;           // ICPB_KT_TPC: where the policy starts for a new target (1, 2, 4, 8, 16)
 	int     kt_policy_m = -1;           // target size the policy state belongs to
-	int     kt_tpc_auto = 4;            // targets per MMA column the policy currently uses (4 -> 2 -> 1 when exact passes pile up)
+	float   kt_policy_fp[4] = {0, 0, 0, -1};   // ... and its centre and radius: the same cloud uploaded again keeps the state
+	bool    kt_tpc_forced_start = false;       // ICPB_KT_TPC given: start there whatever the target size
+	int     kt_tpc_auto = 8;            // targets per MMA column the policy currently uses (halved when exact passes pile up)
 	bool    kt_ready = false;
 	float*  kt_tiles = nullptr;         // [nt][B operand block 16 KB | X Y Z originals 3 KB], 256 targets per tile
 	size_t  kt_tiles_cap = 0;           // floats allocated
 	int     kt_nt = 0;
 	int     kt_tpc = 1, kt_built_tpc = 0;   // targets per MMA column: 1, or 2 / 4 = the grouped forms (consecutive targets share a column)
 	int*    kt_fail = nullptr;          // device flag: a bounded mbarrier wait of the pipeline timed out
+	int*    kt_colstart = nullptr;      // grouped form: first target of every column; kt_scan_a / kt_scan_b: scan scratch (run starts, column ids)
+	int*    kt_scan_a = nullptr;
+	int*    kt_scan_b = nullptr;
+	size_t  kt_cols_cap = 0;
+	void*   kt_cub_tmp = nullptr;
+	size_t  kt_cub_cap = 0;
+	float*  kt_hmax_d = nullptr;        // device: [0] largest group radius (float), then the step sum (double at byte 8)
+	float   kt_hmax = 0.0f;
+	int     kt_ncols = 0;
 
 	// iteration state
 	IterState* st = nullptr;     // device

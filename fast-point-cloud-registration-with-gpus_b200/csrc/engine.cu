@@ -181,7 +181,7 @@ int create_context(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_TC")) c->k1_use_tc = atoi(e) != 0;
 	if (!c->k1_use_tc && !getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = 1e9;      // the FP32 filter's own crossover
 	if (const char* e = getenv("ICPB_KT_VAR")) c->kt_variant = atoi(e);
-	if (const char* e = getenv("ICPB_KT_TPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) { c->kt_tpc_start = v; c->kt_tpc_auto = v; } }
+	if (const char* e = getenv("ICPB_KT_TPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) { c->kt_tpc_start = v; c->kt_tpc_auto = v; c->kt_tpc_forced_start = true; } }
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
 	if (const char* e = getenv("ICPB_KF_CHUNK")) c->kf_chunk_override = atoi(e);
@@ -275,7 +275,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->kt_tiles); cudaFree(c->kt_fail);
+	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
 	cudaFree(c->grid_counts); cudaFree(c->grid_cell_of); cudaFree(c->grid_sums); cudaFree(c->grid_mm);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);
@@ -546,7 +546,7 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 	// per-target data of the matching method is built before the clock starts (as the reference's cudaMalloc block is)
 	if (p.nn_method == ICPB_NN_BRUTE && c->k1_use_filter && p.dist_mode != ICPB_DIST_STD && (double)c->n * (double)c->m >= c->kf_min_pairs) {
 		if ((rc = prepare_match_filter(c)) != ICPB_OK) return rc;
-		if (c->k1_use_tc && !c->kt_ready && (rc = build_filter_tc_data(c)) != ICPB_OK) return rc;
+		if (c->k1_use_tc && (rc = ensure_filter_tc_data(c)) != ICPB_OK) return rc;
 	}
 	if (p.nn_method == ICPB_NN_GRID && p.dist_mode != ICPB_DIST_STD) { if ((rc = prepare_match_grid(c)) != ICPB_OK) return rc; }
 	// Opt-in (ICPB_FLAG_GRAPH / ICPB_GRAPHS=1) for launch-latency-bound small problems: after a first plain iteration
@@ -566,6 +566,8 @@ int icpb_run(icpb_ctx* ctx, const icpb_params* params, float* errors, icpb_resul
 		enq = 1;
 		if ((rc = read_state(c)) != ICPB_OK) return rc;
 		if (!c->st_host->done) {
+			// the policy may just have changed K1T's group size: lay the tiles out again before the capture, not inside it
+			if (p.nn_method == ICPB_NN_BRUTE && c->k1_use_filter && c->k1_use_tc && c->kf_dims_last == 4 && (rc = ensure_filter_tc_data(c)) != ICPB_OK) return rc;
 			const bool valid = c->graph_exec != nullptr && c->graph_built_gen == c->graph_gen && c->graph_batch == p.sync_every &&
 			                   c->graph_key[0] == p.metric && c->graph_key[1] == p.dist_mode && c->graph_key[2] == p.nn_method &&
 			                   c->graph_key[3] == p.flags && c->graph_sentinel == p.sentinel;

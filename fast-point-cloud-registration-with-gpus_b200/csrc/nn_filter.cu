@@ -461,9 +461,17 @@ static int build_filter_data(Ctx* c)
 	c->kf_rq = nextafterf(sqrtf(r2) * (1.0f + 8.0f * KF_U), INFINITY);
 	c->kf_nt = nt;
 	c->kf_dims = 2; c->kf_bounces = 0; c->kf_hold = 0;     // a new target: optimistic again
-	// K1T's group size starts over only for a target of another size: a same-size upload is, as a rule, the same cloud again
-	// (a host-driven loop re-uploads the target at every step) and keeps what the exact-pass rate has taught
-	if (c->m != c->kt_policy_m) { c->kt_tpc_auto = c->kt_tpc_start; c->kt_policy_m = c->m; }
+	// K1T's group size starts over for a NEW target; the same cloud uploaded again (a host-driven loop re-uploads the target
+	// at every step: same size, bit-identical centre and radius) keeps what the exact-pass rate has taught. The start:
+	// the exact pass works on quarters of 32 TPC consecutive targets, which should stay a fraction of a scan line —
+	// measured best on the raster saddle: 2 at 128^2, 4 at 317^2, 8 at 1000^2 points, i.e. about sqrt(m) / 64
+	const float fp[4] = { c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_rq };
+	if (c->m != c->kt_policy_m || memcmp(fp, c->kt_policy_fp, sizeof fp) != 0) {
+		int t = 1;
+		while (t < c->kt_tpc_start && (double)(2 * t) * 64.0 <= sqrt((double)c->m)) t *= 2;
+		c->kt_tpc_auto = c->kt_tpc_forced_start ? c->kt_tpc_start : t;
+		c->kt_policy_m = c->m; memcpy(c->kt_policy_fp, fp, sizeof fp);
+	}
 	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 2 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 2 * sizeof(unsigned long long), c->stream)); }
 	c->kf_ready = true;
 	return ICPB_OK;
@@ -575,9 +583,10 @@ int kf_policy_update(Ctx* c)
 	const double frac = de / dt;
 	c->kf_last_frac = frac;
 	if (c->kf_dims_last == 4) {
-		// K1T: grouped columns (4 or 2 consecutive targets per MMA column) pay off while consecutive targets are neighbours in
-		// space; when more than a fifth of the quarter tests end in the exact pass the group size is halved for this target
-		if (c->kt_variant < 0 && frac > 0.20 && c->kt_tpc_auto > 1) c->kt_tpc_auto /= 2;
+		// K1T: grouped columns (up to 16 consecutive targets per MMA column) pay off while consecutive targets are neighbours
+		// in space. A quarter test costs the same whatever the group size, the exact pass it may ask for covers 32 x TPC
+		// targets: the group size is halved for this target once exact passes cost about as much as the tests (0.8 / TPC of them)
+		if (c->kt_variant < 0 && c->kt_tpc_auto > 1 && frac * (double)c->kt_tpc_auto > 0.8) c->kt_tpc_auto /= 2;
 		return ICPB_OK;
 	}
 	if (c->kf_dims_last == 2 && frac > 0.10) { c->kf_dims = 3; c->kf_bounces++; c->kf_hold = 8 << c->kf_bounces; }

@@ -40,6 +40,7 @@
 #include "common.cuh"
 #include "k1_device.cuh"
 #include <cmath>
+#include <cub/device/device_scan.cuh>
 
 namespace icpb {
 
@@ -74,6 +75,8 @@ struct KTParams {
 	const int*   done;
 	unsigned long long* stats;       // [0] sub-tile tests, [1] exact passes
 	int*         fail;               // set on a protocol time-out
+	const int*   colstart;           // grouped form: index of the first target of every column
+	float        hmax;               // grouped form: the largest group radius h
 };
 
 // element (row r, slot k) of an operand block in the canonical K-major no-swizzle layout: core matrices of 8 rows x 16 B,
@@ -116,64 +119,132 @@ __global__ void tc_pack_kernel(const float4* __restrict__ q4, int m, int m_pad, 
 	tile[TC_B_FLOATS + r] = x; tile[TC_B_FLOATS + TC_TN + r] = y; tile[TC_B_FLOATS + 2 * TC_TN + r] = z;
 }
 
-// ---- paired form: one MMA column per PAIR of consecutive targets -----------------------------------------------------
+// ---- grouped form: one MMA column per GROUP of consecutive targets --------------------------------------------------
 // K1T is bound by what the epilogue can read out of TMEM and min-reduce, and by the MMA hand-shake per accumulator —
-// both per COLUMN. A column can stand for two targets: for a virtual target m (the float midpoint of q1, q2) and
-// h >= max(|q1 - m|, |q2 - m|),   |p - q_k|^2 >= |p - m|^2 - 2 |p - m| h   (k = 1, 2; the dropped term |q_k - m|^2 >= 0),
-// so the bracket of m, e~_m = |m - c|^2 - 2 (p - c).(m - c), evaluated by the same MMA, excludes BOTH targets when
-//     e~_m > tau + 2 H x_up,        H = max h over the sub-tile, x_up >= |p - m| for every m of the sub-tile
-// (x_up = |p - c_s| + rho_s with c_s, rho_s a ball around the sub-tile's midpoints: one distance per source and sub-tile,
-// computed in the epilogue with upward rounding). Targets that are consecutive in index are neighbours in space for
-// scan-ordered clouds (the reference's raster saddle, LiDAR sweeps): H is half the point spacing and the extra slack is
-// small exactly where it matters (near the source x_up is small). For clouds in arbitrary order H is large, every
-// sub-tile goes to the exact pass, and the host's exact-pass-rate policy falls back to one target per column.
-// The same holds for a group of any size around any point m; quads (TPC = 4, m = the centroid of four consecutive targets)
-// halve the columns again at the price of a larger H.
-// Tile (256 TPC targets): B block of the 256 group centres | X Y Z originals | per sub-tile {c_s, rho_s, H_s}.
-// grouped tiles: TPC targets per column (2 = pairs, 4 = quads of consecutive targets; m = their float centroid)
+// both per COLUMN. A column can stand for several targets: for a point g (the float centroid of the group) and
+// h >= max_k |q_k - g|, the triangle inequality gives |p - g| <= |p - q_k| + h. A member can only matter while its
+// distance is within the source's current threshold, |p - q_k|^2 <= tau <= s0^2 (s0 = the square root of the threshold the
+// source starts the sweep with), so for such a member
+//     |p - g|^2 <= tau + 2 sqrt(tau) h + h^2 <= tau + 2 s0 h + h^2,
+// i.e. the whole group is excluded when
+//     |p - g|^2 - 2 s0 h - h^2 > tau.
+// The left side is still ONE inner product per (source, column): the bracket of g with |g - c|^2 - h^2 in the constant
+// slots and one more K slot holding s0 (source row, rounded UP to TF32) against -2 h (column, h rounded UP to TF32; the
+// product of two TF32 values is exact). No per-sub-tile slack is left for the epilogue to add, and the slack that is paid
+// is of the order (s0 + h)^2 - s0^2: the exact pass is asked for only where a group really reaches into the ball of
+// radius s0 around the source. (Round 2's first grouped form bounded 2 |p - g| h by its largest value over a sub-tile,
+// which grows with the distance to the sub-tile's far end: 6 % of the quarters went to the exact pass on the 1M raster
+// at 4 targets per column and one group straddling a row end spoilt its whole sub-tile; now 8-16 targets per column work.)
+//   A row (source):  ax_hi ax_hi ax_lo | ay.. | az.. | 1    1    | s0   | 0 ...
+//   B row (column):  gx_hi gx_lo gx_hi | gy.. | gz.. | w_hi w_lo | -2 h | 0 ...          w = |g - c|^2 - h^2, rounded down
+// Groups never span a JUMP of the scan: consecutive targets are neighbours in space for scan-ordered clouds (the
+// reference's raster saddle, LiDAR sweeps) except where a row or a sweep ends; a step longer than TCG_JUMP times the mean
+// step closes the column early (its unused slots hold +inf originals and are never attained), so columns cover a variable
+// number (1 .. TPC) of targets and `colstart` maps a column back to the index of its first target. For clouds in arbitrary
+// order every h is of the order of the cloud, every quarter goes to the exact pass, and the host's exact-pass-rate policy
+// (kf_policy_update) halves TPC down to one target per column.
+// Tile = 256 columns: B block | X Y Z originals in slot order (slot = column * TPC + member).
 __host__ __device__ constexpr int tcg_tile_targets(int tpc) { return TC_TN * tpc; }
-__host__ __device__ constexpr int tcg_tile_floats(int tpc) { return tpc == 1 ? TC_TILE_FLOATS : TC_B_FLOATS + 3 * TC_TN * tpc + 16; }   // + 2 x {cx, cy, cz, rho, H, 0, 0, 0}
+__host__ __device__ constexpr int tcg_tile_floats(int tpc) { return tpc == 1 ? TC_TILE_FLOATS : TC_B_FLOATS + 3 * TC_TN * tpc; }
+constexpr float TCG_JUMP = 8.0f;
 
-// one block of 128 threads per sub-tile (128 columns = 128 TPC targets)
+__device__ __forceinline__ float tf32_ru_pos(float x)      // smallest TF32 value >= x, x >= 0 and finite
+{
+	return __uint_as_float((__float_as_uint(x) + 0x1fffu) & 0xffffe000u);
+}
+
+// sum of the steps |q_i - q_(i-1)| of the scan (double; the order of the atomic adds only moves the jump threshold by rounding)
+__global__ void tcg_step_sum_kernel(const float4* __restrict__ q4, int m, double* sum)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	float d = 0.0f;
+	if (i > 0 && i < m) {
+		const float4 a = q4[i - 1], b = q4[i];
+		const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
+		d = sqrtf(ex * ex + ey * ey + ez * ez);
+		if (!(d == d) || d == __int_as_float(0x7f800000)) d = 0.0f;
+	}
+	double v = d;
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	__shared__ double s[8];
+	if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s[w]; atomicAdd(sum, t); }
+}
+// mark[i] = i where a column must start because the scan jumps (or i == 0), else 0: an inclusive max-scan gives every
+// target the start of its run
+__global__ void tcg_break_kernel(const float4* __restrict__ q4, int m, const double* sum, int* mark)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	int v = 0;
+	if (i > 0) {
+		const float jump = TCG_JUMP * (float)(*sum / (double)(m > 1 ? m - 1 : 1));
+		const float4 a = q4[i - 1], b = q4[i];
+		const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
+		const float d = sqrtf(ex * ex + ey * ey + ez * ez);
+		if (!(d <= jump)) v = i;
+	}
+	mark[i] = v;
+}
+// flag[i] = 1 where a column starts: every TPC-th target of a run
+__global__ void tcg_colflag_kernel(const int* __restrict__ runstart, int m, int tpc, int* flag)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < m) flag[i] = ((i - runstart[i]) % tpc == 0) ? 1 : 0;
+}
+__global__ void tcg_colstart_kernel(const int* __restrict__ runstart, const int* __restrict__ colid, int m, int tpc, int* colstart)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < m && (i - runstart[i]) % tpc == 0) colstart[colid[i] - 1] = i;
+}
+struct TcgMax { __host__ __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
+
+// one block of 128 threads per sub-tile (128 columns)
 template <int TPC>
-__global__ void __launch_bounds__(128) tc_pack_group_kernel(const float4* __restrict__ q4, int m, float cx, float cy, float cz, float* __restrict__ tiles)
+__global__ void __launch_bounds__(128) tc_pack_group_kernel(const float4* __restrict__ q4, int m, const int* __restrict__ colstart, int ncols,
+                                                            float cx, float cy, float cz, float* __restrict__ tiles, float* hmax)
 {
 	constexpr int TT = TC_TN * TPC;
 	const int sub = blockIdx.x;                      // global sub-tile
 	const int col = threadIdx.x;                     // column inside the sub-tile
 	float* tile = tiles + (size_t)(sub >> 1) * tcg_tile_floats(TPC);
 	const int r = (sub & 1) * 128 + col;             // B row inside the tile
-	const int j0 = (sub * 128 + col) * TPC;
+	const int gc = sub * 128 + col;                  // global column
 	const float inf = __int_as_float(0x7f800000);
+	int j0 = m, len = 0;
+	if (gc < ncols) { j0 = colstart[gc]; len = ((gc + 1 < ncols) ? colstart[gc + 1] : m) - j0; }      // 1 .. TPC members
 	float v[TC_K];
 #pragma unroll
 	for (int k = 0; k < TC_K; k++) v[k] = 0.0f;
-	float mx = 0.f, my = 0.f, mz = 0.f, h = 0.f;
-	const bool have = j0 < m;
 	float4 q[TPC];
 #pragma unroll
-	for (int k = 0; k < TPC; k++) q[k] = (j0 + k < m) ? q4[j0 + k] : make_float4(inf, inf, inf, 0.f);
-	if (have) {
-		// m: any float point works; the centroid of the group's real members (missing ones repeat the first)
+	for (int k = 0; k < TPC; k++) q[k] = (k < len) ? q4[j0 + k] : make_float4(inf, inf, inf, 0.f);
+	if (len > 0) {
+		// g: any float point works; the centroid of the members
+		float gx = 0.f, gy = 0.f, gz = 0.f;
+		const float inv = 1.0f / (float)len;
 #pragma unroll
-		for (int k = 0; k < TPC; k++) { const float4 t = (j0 + k < m) ? q[k] : q[0]; mx += t.x * (1.0f / TPC); my += t.y * (1.0f / TPC); mz += t.z * (1.0f / TPC); }
-		// h >= max |q_k - m|: differences rounded (relative u), squares and sums rounded up, then a safety factor
+		for (int k = 0; k < TPC; k++) if (k < len) { gx += q[k].x * inv; gy += q[k].y * inv; gz += q[k].z * inv; }
+		// h >= max |q_k - g|: differences rounded (relative u), squares and sums rounded up, a safety factor, then up to TF32
 		float d = 0.f;
 #pragma unroll
 		for (int k = 0; k < TPC; k++) {
-			if (j0 + k < m) {
-				const float ex = q[k].x - mx, ey = q[k].y - my, ez = q[k].z - mz;
+			if (k < len) {
+				const float ex = q[k].x - gx, ey = q[k].y - gy, ez = q[k].z - gz;
 				d = fmaxf(d, __fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey))));
 			}
 		}
-		h = __fmul_ru(__fsqrt_ru(d), 1.0f + 16.0f * TC_U);
-		const float xc = __fsub_rn(mx, cx), yc = __fsub_rn(my, cy), zc = __fsub_rn(mz, cz);
-		const float w = __fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc)));
+		const float h = tf32_ru_pos(__fmul_ru(__fsqrt_ru(d), 1.0f + 16.0f * TC_U));
+		const float xc = __fsub_rn(gx, cx), yc = __fsub_rn(gy, cy), zc = __fsub_rn(gz, cz);
+		const float w = __fsub_rd(__fmaf_rn(zc, zc, __fmaf_rn(xc, xc, __fmul_rn(yc, yc))), __fmul_ru(h, h));
 		float hi, lo;
 		tf32_split(xc, hi, lo); v[0] = hi; v[1] = lo; v[2] = hi;
 		tf32_split(yc, hi, lo); v[3] = hi; v[4] = lo; v[5] = hi;
 		tf32_split(zc, hi, lo); v[6] = hi; v[7] = lo; v[8] = hi;
 		tf32_split(w, hi, lo);  v[9] = hi; v[10] = lo;
+		v[11] = -2.0f * h;
+		atomicMax(reinterpret_cast<int*>(hmax), __float_as_int(h));          // h >= 0: the bit patterns order like the values
 	} else {
 		v[9] = 3.0e38f;                              // padding column: never below any tau
 	}
@@ -182,37 +253,6 @@ __global__ void __launch_bounds__(128) tc_pack_group_kernel(const float4* __rest
 	float* X = tile + TC_B_FLOATS + (sub & 1) * 128 * TPC + col * TPC;
 #pragma unroll
 	for (int k = 0; k < TPC; k++) { X[k] = q[k].x; X[TT + k] = q[k].y; X[2 * TT + k] = q[k].z; }
-	// ball around the sub-tile's centroids (bounding-box centre, largest distance to it) and the largest h
-	__shared__ float s_lo[4][3], s_hi[4][3], s_r[4], s_h[4], s_c[3];
-	float lo3[3] = { have ? mx : inf, have ? my : inf, have ? mz : inf }, hi3[3] = { have ? mx : -inf, have ? my : -inf, have ? mz : -inf };
-	for (int k = 0; k < 3; k++)
-		for (int o = 16; o > 0; o >>= 1) { lo3[k] = fminf(lo3[k], __shfl_xor_sync(0xffffffffu, lo3[k], o)); hi3[k] = fmaxf(hi3[k], __shfl_xor_sync(0xffffffffu, hi3[k], o)); }
-	if ((col & 31) == 0) for (int k = 0; k < 3; k++) { s_lo[col >> 5][k] = lo3[k]; s_hi[col >> 5][k] = hi3[k]; }
-	__syncthreads();
-	if (col < 3) {
-		float l = inf, u = -inf;
-		for (int w = 0; w < 4; w++) { l = fminf(l, s_lo[w][col]); u = fmaxf(u, s_hi[w][col]); }
-		float ctr = 0.5f * l + 0.5f * u;
-		if (!(ctr == ctr) || fabsf(ctr) == inf) ctr = 0.0f;
-		s_c[col] = ctr;
-	}
-	__syncthreads();
-	float rr = 0.f;
-	if (have) {
-		const float ex = mx - s_c[0], ey = my - s_c[1], ez = mz - s_c[2];
-		rr = __fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey)))), 1.0f + 16.0f * TC_U);
-	}
-	float hh = h;
-	for (int o = 16; o > 0; o >>= 1) { rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o)); hh = fmaxf(hh, __shfl_xor_sync(0xffffffffu, hh, o)); }
-	if ((col & 31) == 0) { s_r[col >> 5] = rr; s_h[col >> 5] = hh; }
-	__syncthreads();
-	if (col == 0) {
-		float* hdr = tile + TC_B_FLOATS + 3 * TT + (sub & 1) * 8;
-		hdr[0] = s_c[0]; hdr[1] = s_c[1]; hdr[2] = s_c[2];
-		hdr[3] = fmaxf(fmaxf(s_r[0], s_r[1]), fmaxf(s_r[2], s_r[3]));
-		hdr[4] = fmaxf(fmaxf(s_h[0], s_h[1]), fmaxf(s_h[2], s_h[3]));
-		hdr[5] = 0.f; hdr[6] = 0.f; hdr[7] = 0.f;
-	}
 }
 
 // ---- small PTX wrappers ---------------------------------------------------------------------------------------------
@@ -285,19 +325,37 @@ template <int LDW> __device__ __forceinline__ float subtile_min(uint32_t taddr)
 	return fminf(m0, m1);
 }
 
-// four partial minima of the 128 columns starting at taddr: columns [32 q, 32 q + 32), 16-column loads double-buffered
-__device__ __forceinline__ void subtile_min4(uint32_t taddr, float (&mq)[4])
+// 128 / QC partial minima of the 128 columns starting at taddr: columns [QC q, QC q + QC), 16-column loads double-buffered
+template <int QC> __device__ __forceinline__ void subtile_mins(uint32_t taddr, float (&mq)[128 / QC])
 {
+	static_assert(QC == 32 || QC == 16 || QC == 8, "columns per exact-pass unit");
 	const float inf = __int_as_float(0x7f800000);
 	float va[16], vb[16];
 	tmem_ld16(taddr, va);
 #pragma unroll
 	for (int q = 0; q < 4; q++) {
-		float m0 = inf, m1 = inf;
-		tmem_wait_ld(); tmem_ld16(taddr + 32 * q + 16, vb); min16(va, m0, m1);
-		tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
-		min16(vb, m0, m1);
-		mq[q] = fminf(m0, m1);
+		tmem_wait_ld(); tmem_ld16(taddr + 32 * q + 16, vb);
+		if constexpr (QC == 32) {
+			float m0 = inf, m1 = inf;
+			min16(va, m0, m1);
+			tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+			min16(vb, m0, m1);
+			mq[q] = fminf(m0, m1);
+		} else if constexpr (QC == 16) {
+			float m0 = inf, m1 = inf;
+			min16(va, m0, m1);
+			mq[2 * q] = fminf(m0, m1);
+			tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+			m0 = inf; m1 = inf;
+			min16(vb, m0, m1);
+			mq[2 * q + 1] = fminf(m0, m1);
+		} else {
+			mq[4 * q]     = fminf(min3(va[0], va[1], va[2]), min3(va[3], va[4], va[5])); mq[4 * q] = min3(mq[4 * q], va[6], va[7]);
+			mq[4 * q + 1] = fminf(min3(va[8], va[9], va[10]), min3(va[11], va[12], va[13])); mq[4 * q + 1] = min3(mq[4 * q + 1], va[14], va[15]);
+			tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+			mq[4 * q + 2] = fminf(min3(vb[0], vb[1], vb[2]), min3(vb[3], vb[4], vb[5])); mq[4 * q + 2] = min3(mq[4 * q + 2], vb[6], vb[7]);
+			mq[4 * q + 3] = fminf(min3(vb[8], vb[9], vb[10]), min3(vb[11], vb[12], vb[13])); mq[4 * q + 3] = min3(mq[4 * q + 3], vb[14], vb[15]);
+		}
 	}
 }
 
@@ -618,14 +676,15 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams 
 // TPC = targets per MMA column: 1, or 2 / 4 = the grouped forms (tiles of 256 TPC targets, see tc_pack_group_kernel).
 // The filter test, the exact pass and the remembered unit are QUARTERS of a warp's sub-tile: 32 columns = 32 TPC targets
 // (the running minimum costs the same split four ways; an exact pass then covers a quarter of the targets).
-template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC>
+template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC>
 __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const KTParams p)
 {
 	constexpr int TILE_T = TC_TN * TPC;                  // targets per tile
 	constexpr int TRK_T = TC_TRK * TPC;                  // targets per sub-tile (filter test / tracking unit)
 	constexpr int TILE_FLOATS = tcg_tile_floats(TPC);
-	constexpr int QT = 32 * TPC;                         // targets per quarter: the unit of the exact pass and of the key's index
-	constexpr int QPT = TILE_T / QT;                     // 8 quarters per tile
+	constexpr int QT = QC * TPC;                         // targets per "quarter" (QC columns): the unit of the exact pass and of the key's index
+	constexpr int QPT = TILE_T / QT;                     // quarters per tile: 256 / QC
+	constexpr int QPS = TC_TRK / QC;                     // quarters per sub-tile
 	constexpr int TILE_BYTES = TILE_FLOATS * 4;
 	constexpr int SUBS = TC_TN / TC_TRK;                 // 2 sub-tiles per tile = per MMA unit
 	constexpr int UNIT_COLS = TC_TN;                     // one 256-column accumulator per (slab, tile) unit
@@ -722,13 +781,8 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					const float p2 = __fmaf_rn(pcz, pcz, __fmaf_rn(pcx, pcx, __fmul_rn(pcy, pcy)));
 					const float p2lo = __fmul_rd(p2, 1.0f - 8.0f * TC_U);
 					const float rp = __fmul_ru(__fsqrt_ru(p2), 1.0f + 8.0f * TC_U);
-					float e = __fmul_ru(8.0f * p.rq, p.rq);
-					e = __fmaf_ru(10.0f * rp, p.rq, e);
-					e = __fmaf_ru(2.0f * rp, rp, e);
-					e = __fmul_ru(e, 1.05f * TC_EPS_SCALE * TC_U);
 					// sources past the end of the cloud, and non-finite ones, never ask for an exact pass: kk = -inf makes tau = -inf
 					const bool live = (i < p.n) && (p2 == p2) && (p2 < inf);
-					kk_s[sidx] = live ? __fsub_ru(e, p2lo) : -inf;
 					float th = thr_start;
 					if (p.seed_idx != nullptr && i < p.n) {
 						const int j0 = p.seed_idx[i];
@@ -740,6 +794,19 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						}
 					}
 					key_s[sidx] = ((u64)__float_as_uint(th) << 32) | 0xffffffffull;
+					// grouped form: s0 >= sqrt of everything the threshold can be compared at during this sweep (it only falls), up to TF32
+					float s0 = 0.0f;
+					bool wide = false;                       // no usable starting threshold: every quarter goes to the exact pass
+					if (TPC >= 2) {
+						if (th > 0.0f && th < 1.0e30f) s0 = tf32_ru_pos(__fmul_ru(__fsqrt_ru(__fmul_ru(th, one8u)), 1.0f + 4.0f * TC_U));
+						else if (!(th <= 0.0f)) wide = true;
+					}
+					float e = __fmul_ru(8.0f * p.rq, p.rq);
+					e = __fmaf_ru(10.0f * rp, p.rq, e);
+					e = __fmaf_ru(2.0f * rp, rp, e);
+					if (TPC >= 2) { e = __fmaf_ru(8.0f * p.hmax, p.hmax, e); e = __fmaf_ru(4.0f * s0, p.hmax, e); }
+					e = __fmul_ru(e, 1.05f * TC_EPS_SCALE * TC_U);
+					kk_s[sidx] = live ? (wide ? inf : __fsub_ru(e, p2lo)) : -inf;
 					// A row: a = -2 (p - c) as hi + lo; slots ax_hi ax_hi ax_lo | ay.. | az.. | 1 1 | 0...
 					float* A = a_slabs + (size_t)a * (TC_A_BYTES / 4);
 					float h, l;
@@ -748,8 +815,9 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					tf32_split(ay, h, l); A[tc_elem(row, 3)] = h; A[tc_elem(row, 4)] = h; A[tc_elem(row, 5)] = l;
 					tf32_split(az, h, l); A[tc_elem(row, 6)] = h; A[tc_elem(row, 7)] = h; A[tc_elem(row, 8)] = l;
 					A[tc_elem(row, 9)] = 1.0f; A[tc_elem(row, 10)] = 1.0f;
+					A[tc_elem(row, 11)] = live ? s0 : 0.0f;              // against -2 h of the column (0 for one target per column)
 #pragma unroll
-					for (int k = 11; k < TC_K; k++) A[tc_elem(row, k)] = 0.0f;
+					for (int k = 12; k < TC_K; k++) A[tc_elem(row, k)] = 0.0f;
 				}
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of A -> visible to the tensor core
 			}
@@ -800,9 +868,6 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					const float4* X4 = reinterpret_cast<const float4*>(tile + TC_B_FLOATS);
 					const float4* Y4 = X4 + TILE_T / 4;
 					const float4* Z4 = Y4 + TILE_T / 4;
-					// paired form: ball {c_s, rho_s} around this warp's sub-tile midpoints and H_s = the largest pair half-width
-					float hcx = 0.f, hcy = 0.f, hcz = 0.f, hrho = 0.f, hH = 0.f;
-					if (TPC >= 2) { const float* hdr = tile + TC_B_FLOATS + 3 * TILE_T + half * 8; hcx = hdr[0]; hcy = hdr[1]; hcz = hdr[2]; hrho = hdr[3]; hH = hdr[4]; }
 #pragma unroll 1
 					for (int a = grp; a < SLABS; a += GROUPS) {
 						const int sidx = a * 128 + row;
@@ -812,29 +877,22 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						if (!mbar_wait_bounded(&tfull_bar[acc], (uint32_t)(j & 1))) { failed = true; break; }
 						asm volatile("tcgen05.fence::after_thread_sync;");
 						const uint32_t taddr = tmem_base + (uint32_t)(acc * UNIT_COLS + half * TC_TRK) + ((uint32_t)(quarter * 32) << 16);
-						float mq[4];
-						subtile_min4(taddr, mq);
+						float mq[QPS];
+						subtile_mins<QC>(taddr, mq);
 						// the accumulator is in registers: hand it back to the MMA warp before the (rare) exact pass
 						asm volatile("tcgen05.fence::before_thread_sync;");
 						__syncwarp();
 						if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-						float slack = 0.0f;
-						if (TPC >= 2) {
-							// + 2 H x_up, x_up >= |p - m| for every group centre of the sub-tile, every operation rounded up
-							const float ex = ox_s[sidx] - hcx, ey = oy_s[sidx] - hcy, ez = oz_s[sidx] - hcz;
-							const float xup = __fadd_ru(__fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ex, ex, __fmul_ru(ey, ey)))), 1.0f + 16.0f * TC_U), hrho);
-							slack = __fmul_ru(__fmul_ru(2.0f + 32.0f * TC_U, hH), xup);
-						}
 						const float kk = kk_s[sidx];                                    // -inf for dead rows
 #pragma unroll
-						for (int qq = 0; qq < 4; qq++) {
+						for (int qq = 0; qq < QPS; qq++) {
 							const float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));     // re-read: an exact pass may just have lowered it
-							const float tau = __fadd_ru(__fadd_ru(__fmul_ru(th, one8u), kk), slack);
+							const float tau = __fadd_ru(__fmul_ru(th, one8u), kk);
 							const unsigned need = __ballot_sync(0xffffffffu, mq[qq] <= tau);
 							n_tests += 1;
 							if (need) {                                       // warp-uniform
 								n_exact += 1;
-								const int q_in_tile = half * 4 + qq;          // quarter of the tile: targets [QT q, QT q + QT)
+								const int q_in_tile = half * QPS + qq;        // quarter of the tile: slots [QT q, QT q + QT)
 								const int j0 = q_in_tile * (QT / 4), j1 = j0 + QT / 4;
 								const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
 								const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
@@ -856,7 +914,24 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 								// distance of the current class above the class floor still ties with it (NaN / inf never pass)
 								const float nt_ = (mm < inf) ? lower_threshold<MODE>(mm) : inf;
 								if (nt_ <= th && kk > -inf) {
-									atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * QPT + q_in_tile));
+									// rare (a source improves or ties its best a few times per sweep): find the FIRST slot of the quarter that
+									// attains the minimum while its originals are still in shared memory, and offer (threshold, slot)
+									const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(nt_) : nt_;
+									int found = -1;
+									for (int jq = j0; jq < j1 && found < 0; jq++) {
+										const float4 X = X4[jq], Y = Y4[jq], Z = Z4[jq];
+										float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
+										float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
+										float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
+										float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
+										if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+										if (d0 <= target) found = 4 * jq;
+										else if (d1 <= target) found = 4 * jq + 1;
+										else if (d2 <= target) found = 4 * jq + 2;
+										else if (d3 <= target) found = 4 * jq + 3;
+									}
+									if (found >= 0)
+										atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * TILE_T + found));
 								}
 							}
 						}
@@ -870,40 +945,21 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 			it += t1 - t0;
 			__syncthreads();
 			if (s_fail) break;
-			// ---- index recovery: the first target of the remembered sub-tile that attains the exact minimum ----
+			// ---- flush: (threshold, slot) of every source that found something below its starting threshold ----
 			if (is_epi) {
-#pragma unroll 1
+#pragma unroll
 				for (int q = 0; q < SPT; q++) {
 					const int a = wq + 2 * GROUPS * q;
 					const int sidx = a * 128 + row;
 					const int i = sb * SBN + sidx;
 					const u64 kv = key_s[sidx];
-					const int bs = (int)(uint32_t)(kv & 0xffffffffull);          // -1: nothing below the starting threshold
-					if (i < p.n && bs >= 0) {
+					const int slot = (int)(uint32_t)(kv & 0xffffffffull);         // -1: nothing below the starting threshold
+					if (i < p.n && slot >= 0) {
 						const float th = __uint_as_float((unsigned)(kv >> 32));
-						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
-						const float* gx = p.tiles + (size_t)(bs / QPT) * TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % QPT) * QT;
-						const float4* GX = reinterpret_cast<const float4*>(gx);
-						const float4* GY = reinterpret_cast<const float4*>(gx + TILE_T);
-						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TILE_T);
 						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
-						int found = -1;
-						for (int jq = 0; jq < QT / 4 && found < 0; jq++) {
-							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
-							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
-							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
-							float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
-							float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
-							if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
-							if (d0 <= target) found = 4 * jq;
-							else if (d1 <= target) found = 4 * jq + 1;
-							else if (d2 <= target) found = 4 * jq + 2;
-							else if (d3 <= target) found = 4 * jq + 3;
-						}
-						if (found >= 0) {
-							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)(bs * QT + found);
-							atomicMin(p.keys + i, key);
-						}
+						// slot -> target index: one target per column, or column start + member (slots past a short column hold +inf)
+						const int jidx = (TPC == 1) ? slot : (__ldg(p.colstart + slot / TPC) + slot % TPC);
+						atomicMin(p.keys + i, ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)jidx);
 					}
 				}
 			}
@@ -925,34 +981,104 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 // host
 // ------------------------------------------------------------------------------------------------
 
-// Operand tiles of the current target (needs the centre chosen by build_filter_data); kept across targets of one size.
-// kt_tpc = 2 / 4: the grouped forms (one column per two / four consecutive targets).
+// Operand tiles of the current target (needs the centre chosen by build_filter_data); buffers kept across targets.
+// kt_tpc >= 2: the grouped form — columns of up to kt_tpc consecutive targets that never span a jump of the scan.
+template <int TPC> static void launch_pack_group(Ctx* c, int nt, int ncols)
+{
+	tc_pack_group_kernel<TPC><<<nt * 2, 128, 0, c->stream>>>(c->q4, c->m, c->kt_colstart, ncols, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles, c->kt_hmax_d);
+}
+// targets per MMA column: forced by ICPB_KT_VAR (experiments), else what the exact-pass-rate policy currently holds
+static int tc_current_tpc(const Ctx* c)
+{
+	if (c->kt_variant < 0) return c->kt_tpc_auto;
+	const int v = c->kt_variant;
+	return (v == 17) ? 4 : (v == 15 || v == 16) ? 8 : (v >= 12) ? 16 : (v == 11) ? 8 : (v >= 10) ? 4 : (v >= 8 ? 2 : 1);
+}
 int build_filter_tc_data(Ctx* c)
 {
 	const int m = c->m;
-	const int tpc = c->kt_tpc;
-	const int tile_t = tcg_tile_targets(tpc);
-	const int tile_f = tcg_tile_floats(tpc);
-	const int nt = (m + tile_t - 1) / tile_t;
-	const size_t need = (size_t)nt * tile_f;
+	const int tpc = c->kt_tpc = tc_current_tpc(c);
+	if (!c->kt_fail) { ICPB_CUDA(c, cudaMalloc((void**)&c->kt_fail, sizeof(int))); ICPB_CUDA(c, cudaMemsetAsync(c->kt_fail, 0, sizeof(int), c->stream)); }
+	int nt, ncols = 0;
+	if (tpc >= 2) {
+		// columns: runs of the scan between jumps, cut into groups of tpc
+		if ((size_t)m + 1 > c->kt_cols_cap) {
+			cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); c->kt_colstart = c->kt_scan_a = c->kt_scan_b = nullptr; c->kt_cols_cap = 0;
+			const size_t cap = (size_t)m + 1 + (size_t)m / 8;
+			ICPB_CUDA(c, cudaMalloc((void**)&c->kt_colstart, sizeof(int) * cap));
+			ICPB_CUDA(c, cudaMalloc((void**)&c->kt_scan_a, sizeof(int) * cap));
+			ICPB_CUDA(c, cudaMalloc((void**)&c->kt_scan_b, sizeof(int) * cap));
+			c->kt_cols_cap = cap;
+		}
+		if (!c->kt_hmax_d) ICPB_CUDA(c, cudaMalloc((void**)&c->kt_hmax_d, 2 * sizeof(double)));      // [0] float hmax (+ pad), [1] double step sum
+		double* step_sum = reinterpret_cast<double*>(c->kt_hmax_d) + 1;
+		ICPB_CUDA(c, cudaMemsetAsync(c->kt_hmax_d, 0, 2 * sizeof(double), c->stream));
+		size_t tmp_a = 0, tmp_b = 0;
+		cub::DeviceScan::InclusiveScan(nullptr, tmp_a, c->kt_scan_a, c->kt_scan_a, TcgMax(), m, c->stream);
+		cub::DeviceScan::InclusiveSum(nullptr, tmp_b, c->kt_scan_b, c->kt_scan_b, m, c->stream);
+		const size_t tmp = tmp_a > tmp_b ? tmp_a : tmp_b;
+		if (tmp > c->kt_cub_cap) {
+			cudaFree(c->kt_cub_tmp); c->kt_cub_tmp = nullptr; c->kt_cub_cap = 0;
+			ICPB_CUDA(c, cudaMalloc(&c->kt_cub_tmp, tmp + 256));
+			c->kt_cub_cap = tmp + 256;
+		}
+		const int g = (m + 255) / 256;
+		tcg_step_sum_kernel<<<g, 256, 0, c->stream>>>(c->q4, m, step_sum);
+		tcg_break_kernel<<<g, 256, 0, c->stream>>>(c->q4, m, step_sum, c->kt_scan_a);
+		size_t t1 = c->kt_cub_cap;
+		ICPB_CUDA(c, cub::DeviceScan::InclusiveScan(c->kt_cub_tmp, t1, c->kt_scan_a, c->kt_scan_a, TcgMax(), m, c->stream));      // run start of every target
+		tcg_colflag_kernel<<<g, 256, 0, c->stream>>>(c->kt_scan_a, m, tpc, c->kt_scan_b);
+		t1 = c->kt_cub_cap;
+		ICPB_CUDA(c, cub::DeviceScan::InclusiveSum(c->kt_cub_tmp, t1, c->kt_scan_b, c->kt_scan_b, m, c->stream));                 // 1-based column of every target
+		tcg_colstart_kernel<<<g, 256, 0, c->stream>>>(c->kt_scan_a, c->kt_scan_b, m, tpc, c->kt_colstart);
+		c->launches += 6;
+		double step_total = 0.0;
+		ICPB_CUDA(c, cudaMemcpyAsync(&ncols, c->kt_scan_b + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaMemcpyAsync(&step_total, step_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+		// Consecutive targets that are not neighbours in space (a cloud in arbitrary order): every group is as wide as the cloud
+		// and grouping can only cost. The mean step of the scan against the spacing of m points spread over a surface of the
+		// cloud's radius tells: go to one target per column at once instead of letting the exact-pass rate find out.
+		if (c->kt_variant < 0 && m > 1 && step_total / (double)(m - 1) > 16.0 * (double)c->kf_rq * sqrt(3.14159265358979 / (double)m)) {
+			c->kt_tpc_auto = 1;
+			return build_filter_tc_data(c);
+		}
+		if (ncols < 1 || ncols > m) { snprintf(c->err, sizeof c->err, "k1_filter_tc: column scan returned %d columns for %d targets", ncols, m); return ICPB_ERR_CUDA; }
+		nt = (ncols + TC_TN - 1) / TC_TN;
+	} else {
+		nt = (m + TC_TN - 1) / TC_TN;
+	}
+	const size_t need = (size_t)nt * tcg_tile_floats(tpc);
 	if (need > c->kt_tiles_cap) {
 		cudaFree(c->kt_tiles); c->kt_tiles = nullptr; c->kt_tiles_cap = 0;
 		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_tiles, sizeof(float) * need));
 		c->kt_tiles_cap = need;
 	}
-	if (!c->kt_fail) { ICPB_CUDA(c, cudaMalloc((void**)&c->kt_fail, sizeof(int))); ICPB_CUDA(c, cudaMemsetAsync(c->kt_fail, 0, sizeof(int), c->stream)); }
-	if (tpc == 16) tc_pack_group_kernel<16><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
-	else if (tpc == 8) tc_pack_group_kernel<8><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
-	else if (tpc == 4) tc_pack_group_kernel<4><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
-	else if (tpc == 2) tc_pack_group_kernel<2><<<nt * 2, 128, 0, c->stream>>>(c->q4, m, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
+	c->kt_hmax = 0.0f;
+	if (tpc == 16) launch_pack_group<16>(c, nt, ncols);
+	else if (tpc == 8) launch_pack_group<8>(c, nt, ncols);
+	else if (tpc == 4) launch_pack_group<4>(c, nt, ncols);
+	else if (tpc == 2) launch_pack_group<2>(c, nt, ncols);
 	else tc_pack_kernel<<<(nt * TC_TN + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * TC_TN, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
+	if (tpc >= 2) {
+		ICPB_CUDA(c, cudaMemcpyAsync(&c->kt_hmax, c->kt_hmax_d, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
 	c->kt_nt = nt;
-	if (c->kt_built_tpc != tpc) c->graph_gen++;      // a captured iteration graph holds the kernel of the old group size: its tiles are gone
+	c->kt_ncols = ncols;
+	c->graph_gen++;              // a captured iteration graph holds the tile count, hmax and (when the group size changed) the kernel of the old tiles
 	c->kt_built_tpc = tpc;
 	c->kt_ready = true;
 	return ICPB_OK;
+}
+
+// tiles present and laid out for the group size the next launch will use (called before the clock and before a capture)
+int ensure_filter_tc_data(Ctx* c)
+{
+	if (c->kt_ready && c->kt_built_tpc == tc_current_tpc(c)) return ICPB_OK;
+	return build_filter_tc_data(c);
 }
 
 static float sqrt_domain_threshold_tc(float sentinel)
@@ -993,7 +1119,7 @@ static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
 	return ICPB_OK;
 }
 
-template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC>
+template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC = 32>
 static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 {
 	constexpr int SBN = 128 * SLABS;
@@ -1006,9 +1132,9 @@ static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
 	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
 	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
-	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC>;
-	static bool attr_set[2][16][64] = {};
-	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 15][c->device & 63];
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC, QC> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC, QC>;
+	static bool attr_set[2][32][64] = {};
+	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 31][c->device & 63];
 	if (!done) { ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); done = true; }
 	long long grid = c->sm_count;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
@@ -1027,7 +1153,7 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	// targets per MMA column: forced by ICPB_KT_VAR (experiments), else chosen by the exact-pass-rate policy (kf_policy_update):
 	// it starts at kt_tpc_auto and halves whenever more than a fifth of the quarter tests end in the exact pass
 	const bool forced = c->kt_variant >= 0;
-	c->kt_tpc = !forced ? c->kt_tpc_auto : (c->kt_variant == 12) ? 16 : (c->kt_variant == 11) ? 8 : (c->kt_variant >= 10) ? 4 : (c->kt_variant >= 8 ? 2 : 1);
+	c->kt_tpc = tc_current_tpc(c);
 	if (!c->kt_ready || c->kt_built_tpc != c->kt_tpc) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
 	KTParams p;
 	p.px = c->px; p.py = c->py; p.pz = c->pz;
@@ -1038,6 +1164,7 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	p.done = &c->st->done;
 	p.stats = c->kf_stats;
 	p.fail = c->kt_fail;
+	p.colstart = c->kt_colstart; p.hmax = c->kt_hmax;
 	c->kf_dims_last = 4;                       // reported as "4" = the 3-D bound on the tensor cores
 	c->kf_seeded = true;
 	c->pairs_acc += (double)c->n * (double)c->m;
@@ -1053,6 +1180,7 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	//   8 / 9: as 7 / 6 in the PAIRED form: one column per two consecutive targets (tc_pack_group_kernel); 10: as 7 with QUADS
 	if (!forced) {
 		switch (c->kt_tpc) {
+		case 16: return launch_tc_split<2, 8, 2, 16, 16>(c, dist_mode, p, 12);
 		case 8:  return launch_tc_split<2, 8, 3, 16, 8>(c, dist_mode, p, 11);
 		case 4:  return launch_tc_split<2, 8, 3, 16, 4>(c, dist_mode, p, 10);
 		case 2:  return launch_tc_split<2, 8, 3, 16, 2>(c, dist_mode, p, 8);
@@ -1072,6 +1200,11 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	case 10: return launch_tc_split<2, 8, 3, 16, 4>(c, dist_mode, p, 10);
 	case 11: return launch_tc_split<2, 8, 3, 16, 8>(c, dist_mode, p, 11);
 	case 12: return launch_tc_split<2, 8, 2, 16, 16>(c, dist_mode, p, 12);
+	case 13: return launch_tc_split<2, 8, 2, 16, 16, 16>(c, dist_mode, p, 13);      // 13-16: finer exact-pass units (16 / 8 columns)
+	case 14: return launch_tc_split<2, 8, 2, 16, 16, 8>(c, dist_mode, p, 14);
+	case 15: return launch_tc_split<2, 8, 3, 16, 8, 16>(c, dist_mode, p, 15);
+	case 16: return launch_tc_split<2, 8, 3, 16, 8, 8>(c, dist_mode, p, 16);
+	case 17: return launch_tc_split<2, 8, 3, 16, 4, 16>(c, dist_mode, p, 17);
 	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
 	}
 }

@@ -15,35 +15,41 @@ __device__ inline void polar_rotation(const double W[9] /*col-major*/, double R[
 	for (int i = 0; i < 3; i++)
 #pragma unroll
 		for (int j = 0; j < 3; j++) { a[i][j] = W[i + 3 * j]; v[i][j] = (i == j) ? 1.0 : 0.0; }
+	// One thread, so the latency of every FP64 square root and division is paid in full: a rotation costs one sqrt, one
+	// division and one rsqrt (t from the half-angle form with the division by gamma folded in, the convergence test on
+	// gamma^2 against alpha beta instead of their quotient's root).
 	for (int sweep = 0; sweep < 60; sweep++) {
-		double off = 0.0;
+		bool moved = false;
 #pragma unroll
 		for (int pq = 0; pq < 3; pq++) {
 			const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
 			double alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
 			for (int i = 0; i < 3; i++) { alpha += a[i][p] * a[i][p]; beta += a[i][q] * a[i][q]; gamma += a[i][p] * a[i][q]; }
-			if (gamma == 0.0) continue;
-			const double lim = fabs(gamma) / sqrt(alpha * beta);
-			if (lim > off) off = lim;
-			if (lim < 1e-17) continue;
-			const double zeta = (beta - alpha) / (2.0 * gamma);
-			const double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-			const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+			const double g2 = gamma * gamma, ab = alpha * beta;
+			if (gamma == 0.0 || g2 < 1e-34 * ab) continue;           // |gamma| / sqrt(alpha beta) < 1e-17: columns orthogonal to working precision
+			if (g2 >= 1e-32 * ab) moved = true;                      // ... >= 1e-16: another sweep is needed
+			// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma), numerator and denominator times 2 |gamma|
+			const double d = beta - alpha;
+			const double sgn = (d == 0.0 || ((d > 0.0) == (gamma > 0.0))) ? 1.0 : -1.0;
+			const double t = sgn * 2.0 * fabs(gamma) / (fabs(d) + sqrt(d * d + 4.0 * g2));
+			const double c = rsqrt(1.0 + t * t), s = c * t;
 #pragma unroll
 			for (int i = 0; i < 3; i++) {
 				double x = a[i][p], y = a[i][q]; a[i][p] = c * x - s * y; a[i][q] = s * x + c * y;
 				x = v[i][p]; y = v[i][q]; v[i][p] = c * x - s * y; v[i][q] = s * x + c * y;
 			}
 		}
-		if (off < 1e-16) break;
+		if (!moved) break;
 	}
 	double u[3][3], sv[3];
 #pragma unroll
 	for (int j = 0; j < 3; j++) {
-		sv[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
+		const double n2 = a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j];
+		sv[j] = sqrt(n2);
+		const double inv = (n2 > 0) ? 1.0 / sv[j] : 0.0;
 #pragma unroll
-		for (int i = 0; i < 3; i++) u[i][j] = (sv[j] > 0) ? a[i][j] / sv[j] : 0.0;
+		for (int i = 0; i < 3; i++) u[i][j] = a[i][j] * inv;
 	}
 	int small = 0;
 	if (sv[1] < sv[small]) small = 1;
@@ -88,7 +94,8 @@ __device__ inline void solve_p2p(IterState* st)
 	const double* mom = st->moments;
 	const double N = mom[15];
 	double pb[3], qb[3], W[9], R[9];
-	for (int c = 0; c < 3; c++) { pb[c] = mom[c] / N; qb[c] = mom[3 + c] / N; }
+	const double invN = 1.0 / N;
+	for (int c = 0; c < 3; c++) { pb[c] = mom[c] * invN; qb[c] = mom[3 + c] * invN; }
 	for (int c = 0; c < 3; c++)
 		for (int r = 0; r < 3; r++) W[r + 3 * c] = mom[6 + r + 3 * c] - N * qb[r] * pb[c];
 	polar_rotation(W, R, (st->flags & ICPB_FLAG_FIX_REFLECTION) != 0);

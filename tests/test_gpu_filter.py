@@ -176,3 +176,46 @@ def test_planar_bound_policy(ib, orc):
         assert np.array_equal(c.match(0, ib.NN_BRUTE), orc.match(P, Q, 0))
     finally:
         c.close()
+
+
+def test_grouped_columns_on_rasters_no_group_size_divides(ctx, ib, orc):
+    """K1T's grouped columns never span a jump of the scan (a row end, a gap in a sweep): rasters whose row length no group
+    size divides, a cloud whose scan is cut by gaps of random length, and a raster followed by scattered points."""
+    for w in (37, 61):
+        D, M = orc.synth_p2p(w)
+        _check(ctx, ib, orc, D, M)
+        _check(ctx, ib, orc, orc.icp_p2p(D, M, max_iter=12, stop_early=False)["P"], M, oracle=False)
+    rng = np.random.default_rng(77)
+    t = np.cumsum(np.where(rng.random(6000) < 0.02, rng.uniform(0.5, 3.0, 6000), 0.01)).astype(np.float32)      # a sweep with gaps
+    Q = np.stack([np.cos(t) * (1 + 0.05 * t), np.sin(t) * (1 + 0.05 * t), 0.1 * np.sin(7 * t)], axis=1).astype(np.float32)
+    P = (Q[rng.permutation(6000)[:3000]] + rng.normal(scale=0.004, size=(3000, 3))).astype(np.float32)
+    _check(ctx, ib, orc, P, Q)
+    D, M = orc.synth_p2p(50)
+    Q2 = np.concatenate([M, rng.normal(size=(777, 3)).astype(np.float32) * 3.0, M[:333] + np.float32(0.001)]).astype(np.float32)
+    _check(ctx, ib, orc, D, Q2)
+
+
+def test_tc_group_size_policy(ib, orc):
+    """Automatic choice of K1T's targets per column: about sqrt(m) / 64 on a scan-ordered cloud, one at once for a cloud in
+    arbitrary order (mean step of the scan far above the point spacing), and again from the start for the next target."""
+    c = _context(ib, ICPB_K1_FILTER_MIN_PAIRS=0)
+    try:
+        for w, want in ((128, 2), (317, 4)):
+            D, M = orc.synth_p2p(w)
+            c.set_target(M); c.set_source(D)
+            a = c.match(0, ib.NN_BRUTE)
+            # (the exact-pass rate of this cold first pass may already have halved it once)
+            assert c.filter_config()["dims_last"] == 4 and c.filter_tc_config()["targets_per_column"] in (want, want // 2), c.filter_tc_config()
+            assert np.array_equal(a, c.match(0, ib.NN_BRUTE_DIRECT))
+        rng = np.random.default_rng(3)
+        Q = rng.random((20000, 3)).astype(np.float32); P = rng.random((5000, 3)).astype(np.float32)
+        c.set_target(Q); c.set_source(P)
+        a = c.match(0, ib.NN_BRUTE)
+        assert c.filter_tc_config()["targets_per_column"] == 1, c.filter_tc_config()
+        assert np.array_equal(a, orc.match(P, Q, 0))
+        D, M = orc.synth_p2p(317)
+        c.set_target(M); c.set_source(D)
+        c.match(0, ib.NN_BRUTE)
+        assert c.filter_tc_config()["targets_per_column"] in (4, 2)
+    finally:
+        c.close()
