@@ -237,7 +237,7 @@ struct Ctx {
 	int     kf_dims_forced = 0;         // ICPB_KF_DIMS=2|3
 	int     kf_bounces = 0, kf_hold = 0; // planar -> full switches so far; full-bound launches left before planar is retried
 	bool    kf_seeded = false;          // the seeds hold real correspondences (not the reset value)
-	unsigned long long kf_stats_seen[2] = {0, 0};
+	unsigned long long kf_stats_seen[4] = {0, 0, 0, 0};   // tests, exact passes; K1T: source sweeps, of which with s0 < the largest group radius
 	double  kf_last_frac = 0.0;
 	bool    kf_use_seed = true;         // warm start from the previous correspondences
 	double  kf_min_pairs = 2.5e8;       // below this many pairs per pass the direct kernel is used (ICPB_K1_FILTER_MIN_PAIRS); K1T pays off
@@ -246,17 +246,18 @@ struct Ctx {
 	// K1T: the filter on the tensor cores (nn_filter_tc.cu)
 	bool    k1_use_tc = true;           // ICPB_NN_BRUTE goes through K1T (ICPB_K1_TC=0: the FP32 filter kernel K1F)
 	int     kt_variant = -1;            // ICPB_KT_VAR: forces a pipeline shape of K1T (nn_filter_tc.cu); -1 = automatic
-	int     kt_tpc_start = 8;           // ICPB_KT_TPC: where the policy starts for a new target (1, 2, 4, 8, 16)
+	int     kt_tpc_start = 16;          // ICPB_KT_TPC: where the policy starts for a new target (1, 2, 4, 8, 16)
 	int     kt_policy_m = -1;           // target size the policy state belongs to
 	float   kt_policy_fp[4] = {0, 0, 0, -1};   // ... and its centre and radius: the same cloud uploaded again keeps the state
 	bool    kt_tpc_forced_start = false;       // ICPB_KT_TPC given: start there whatever the target size
-	int     kt_tpc_auto = 8;            // targets per MMA column the policy currently uses (halved when exact passes pile up)
+	int     kt_tpc_auto = 16;           // targets per MMA column the policy currently uses (halved when exact passes pile up)
 	bool    kt_ready = false;
 	float*  kt_tiles = nullptr;         // [nt][B operand block 16 KB | X Y Z originals 3 KB], 256 targets per tile
 	size_t  kt_tiles_cap = 0;           // floats allocated
 	int     kt_nt = 0;
 	int     kt_tpc = 1, kt_built_tpc = 0;   // targets per MMA column: 1, or 2 / 4 = the grouped forms (consecutive targets share a column)
 	int*    kt_fail = nullptr;          // device flag: a bounded mbarrier wait of the pipeline timed out
+	unsigned long long* kt_work = nullptr;   // [0] work counter of the K1T pass, [1] CTAs through (the last one re-arms both)
 	int*    kt_colstart = nullptr;      // grouped form: first target of every column; kt_scan_a / kt_scan_b: scan scratch (run starts, column ids)
 	int*    kt_scan_a = nullptr;
 	int*    kt_scan_b = nullptr;

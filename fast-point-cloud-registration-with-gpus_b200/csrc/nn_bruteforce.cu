@@ -235,6 +235,44 @@ __global__ void __launch_bounds__(128) k1_match_std(const K1Params p)
 	if (valid && best >= 0) p.keys[i] = ((u64)__float_as_uint(mn) << 32) | (u64)(uint32_t)best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small problems. k1_match works in units of (1024..2048 sources) x (1024 targets) and recovers indices with a scan of the
+// winning sub-tile from L2 at the end: at the reference's own sizes (1 024 points = ONE unit = one SM busy, 56 us per pass
+// measured, most of it the serial index scan) that is all latency. Here: one source per thread, a slice of the targets
+// per block staged in shared memory, distance and index tracked together, one atomicMin on the (distance, index) key per
+// thread — the keys give the lowest index among equal distances whatever order the slices finish in.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k1_match_small(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
+                                                      const float4* __restrict__ q4, u64* keys, int n, int m, int ts, float sentinel, const int* done)
+{
+	if (done != nullptr && *done) return;
+	extern __shared__ float4 k1s_q[];
+	const int t0 = blockIdx.y * ts;
+	const int cnt = min(m - t0, ts);
+	for (int k = threadIdx.x; k < cnt; k += 128) k1s_q[k] = q4[t0 + k];
+	__syncthreads();
+	const int i = blockIdx.x * 128 + threadIdx.x;
+	if (i >= n) return;
+	const float x = px[i], y = py[i], z = pz[i];
+	float best = sentinel;
+	int bj = -1;
+#pragma unroll 4
+	for (int k = 0; k < cnt; k++) {
+		const float4 q = k1s_q[k];
+		float d;
+		if (MODE == ICPB_DIST_STD) {                     // ICP_standard's formula (src/ICP_standard.cu:31), as k1_match_std evaluates it
+			const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
+			d = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)), __dmul_rn((double)dz, (double)dz)));
+		} else {
+			d = dist_chain(x, y, z, q.x, q.y, q.z);
+			if (MODE == ICPB_DIST_SQRT) d = __fsqrt_rn(d);
+		}
+		if (d < best) { best = d; bj = t0 + k; }        // strict: the first of equal distances stays (src/ICP_point_to_point.cu:47-55)
+	}
+	if (bj >= 0) atomicMin(keys + i, ((u64)__float_as_uint(best) << 32) | (u64)(uint32_t)bj);
+}
+
 __global__ void key_reset_kernel(u64* keys, int n, const int* done)
 {
 	if (done != nullptr && *done) return;
@@ -326,8 +364,26 @@ static int launch_match_brute_impl(Ctx* c, int dist_mode, float sentinel, const 
 	p.thr0 = (dist_mode == ICPB_DIST_SQRT) ? sqrt_domain_threshold(sentinel) : sentinel;
 	p.done = &c->st->done;
 	if (remap == nullptr) c->pairs_acc += (double)c->n * (double)c->m;
-	if (dist_mode == ICPB_DIST_STD) {
+	// too few (source block, tile) units to fill the GPU: the small-problem kernel
+	const bool small = remap == nullptr && !c->k1_cfg_forced && (long long)((c->n + 1023) / 1024) * c->nt < 2LL * c->sm_count;
+	if (dist_mode == ICPB_DIST_STD && !small) {
 		k1_match_std<<<(c->n + 127) / 128, 128, 0, c->stream>>>(p);
+		c->launches++;
+		ICPB_CUDA(c, cudaGetLastError());
+		return ICPB_OK;
+	}
+	if (small) {
+		const int gx = (c->n + 127) / 128;
+		int gy = (4 * c->sm_count + gx - 1) / gx;
+		if (gy > (c->m + 63) / 64) gy = (c->m + 63) / 64;
+		if (gy < 1) gy = 1;
+		int ts = ((c->m + gy - 1) / gy + 63) / 64 * 64;
+		if (ts > 3072) ts = 3072;                             // 48 KB of shared memory
+		gy = (c->m + ts - 1) / ts;
+		const dim3 grid((unsigned)gx, (unsigned)gy);
+		if (dist_mode == ICPB_DIST_STD) k1_match_small<ICPB_DIST_STD><<<grid, 128, (size_t)ts * sizeof(float4), c->stream>>>(c->px, c->py, c->pz, c->q4, c->keys, c->n, c->m, ts, sentinel, &c->st->done);
+		else if (dist_mode == ICPB_DIST_SQRT) k1_match_small<ICPB_DIST_SQRT><<<grid, 128, (size_t)ts * sizeof(float4), c->stream>>>(c->px, c->py, c->pz, c->q4, c->keys, c->n, c->m, ts, sentinel, &c->st->done);
+		else k1_match_small<ICPB_DIST_SQ><<<grid, 128, (size_t)ts * sizeof(float4), c->stream>>>(c->px, c->py, c->pz, c->q4, c->keys, c->n, c->m, ts, sentinel, &c->st->done);
 		c->launches++;
 		ICPB_CUDA(c, cudaGetLastError());
 		return ICPB_OK;

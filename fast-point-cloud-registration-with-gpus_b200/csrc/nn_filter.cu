@@ -464,15 +464,16 @@ static int build_filter_data(Ctx* c)
 	// K1T's group size starts over for a NEW target; the same cloud uploaded again (a host-driven loop re-uploads the target
 	// at every step: same size, bit-identical centre and radius) keeps what the exact-pass rate has taught. The start:
 	// the exact pass works on quarters of 32 TPC consecutive targets, which should stay a fraction of a scan line —
-	// measured best on the raster saddle: 2 at 128^2, 4 at 317^2, 8 at 1000^2 points, i.e. about sqrt(m) / 64
+	// measured best on the raster saddle with exact-pass units of 8 columns: 2 at 128^2, 8 at 317^2, 16 at 1000^2 points, i.e.
+	// the power of two at or above sqrt(m) / 64
 	const float fp[4] = { c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kf_rq };
 	if (c->m != c->kt_policy_m || memcmp(fp, c->kt_policy_fp, sizeof fp) != 0) {
 		int t = 1;
-		while (t < c->kt_tpc_start && (double)(2 * t) * 64.0 <= sqrt((double)c->m)) t *= 2;
+		while (t < c->kt_tpc_start && (double)t * 64.0 < sqrt((double)c->m)) t *= 2;
 		c->kt_tpc_auto = c->kt_tpc_forced_start ? c->kt_tpc_start : t;
 		c->kt_policy_m = c->m; memcpy(c->kt_policy_fp, fp, sizeof fp);
 	}
-	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 2 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 2 * sizeof(unsigned long long), c->stream)); }
+	if (!c->kf_stats) { ICPB_CUDA(c, cudaMalloc((void**)&c->kf_stats, 4 * sizeof(unsigned long long))); ICPB_CUDA(c, cudaMemsetAsync(c->kf_stats, 0, 4 * sizeof(unsigned long long), c->stream)); }
 	c->kf_ready = true;
 	return ICPB_OK;
 }
@@ -573,12 +574,13 @@ int launch_match_filter(Ctx* c, int dist_mode, float sentinel)
 int kf_policy_update(Ctx* c)
 {
 	if (!c->kf_ready || !c->kf_stats) return ICPB_OK;
-	unsigned long long h[2] = { 0, 0 };
+	unsigned long long h[4] = { 0, 0, 0, 0 };
 	ICPB_CUDA(c, cudaMemcpyAsync(h, c->kf_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (c->k1_use_tc) { const int rc = filter_tc_check(c); if (rc != ICPB_OK) return rc; }
 	const double dt = (double)(h[0] - c->kf_stats_seen[0]), de = (double)(h[1] - c->kf_stats_seen[1]);
-	c->kf_stats_seen[0] = h[0]; c->kf_stats_seen[1] = h[1];
+	const double dn = (double)(h[2] - c->kf_stats_seen[2]), ds = (double)(h[3] - c->kf_stats_seen[3]);
+	c->kf_stats_seen[0] = h[0]; c->kf_stats_seen[1] = h[1]; c->kf_stats_seen[2] = h[2]; c->kf_stats_seen[3] = h[3];
 	if (dt <= 0.0) return ICPB_OK;
 	const double frac = de / dt;
 	c->kf_last_frac = frac;
@@ -586,7 +588,12 @@ int kf_policy_update(Ctx* c)
 		// K1T: grouped columns (up to 16 consecutive targets per MMA column) pay off while consecutive targets are neighbours
 		// in space. A quarter test costs the same whatever the group size, the exact pass it may ask for covers 32 x TPC
 		// targets: the group size is halved for this target once exact passes cost about as much as the tests (0.8 / TPC of them)
-		if (c->kt_variant < 0 && c->kt_tpc_auto > 1 && frac * (double)c->kt_tpc_auto > 0.8) c->kt_tpc_auto /= 2;
+		// — but only when the groups are what asks for them: the exact pass is wanted wherever a group reaches into the ball of
+		// radius s0 around a source, and while the registration is far from converged (or on a cold pass) s0 is much larger
+		// than any group; smaller groups would not help then. The kernel counts the sources whose s0 is below the largest
+		// group radius: the groups drive the exact-pass rate when that is most of them.
+		const bool groups_matter = dn > 0.0 && ds > 0.5 * dn;
+		if (c->kt_variant < 0 && c->kt_tpc_auto > 1 && groups_matter && frac * (double)c->kt_tpc_auto > 0.8) c->kt_tpc_auto /= 2;
 		return ICPB_OK;
 	}
 	if (c->kf_dims_last == 2 && frac > 0.10) { c->kf_dims = 3; c->kf_bounces++; c->kf_hold = 8 << c->kf_bounces; }

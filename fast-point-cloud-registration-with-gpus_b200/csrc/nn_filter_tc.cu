@@ -70,6 +70,7 @@ struct KTParams {
 	long long    total_units;        // source blocks x nt
 	int          min_chunk, max_chunk, gss_div;
 	unsigned long long* work_counter;
+	unsigned long long* exit_counter;   // split form: CTAs that are through; the last one re-arms both counters (no memset launch per pass)
 	float        thr0;
 	float        cx, cy, cz, rq;
 	const int*   done;
@@ -741,6 +742,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 
 	int it = 0;                   // tiles this CTA has streamed so far: ring stage and parities follow it across segments
 	unsigned long long n_tests = 0, n_exact = 0;
+	unsigned n_sweeps = 0, n_small_s0 = 0;      // grouped form: source sweeps started, of which with s0 below the largest group radius
 	const float inf = __int_as_float(0x7f800000);
 	const float one8u = 1.0f + 8.0f * TC_U;
 	// largest float below the starting threshold: with it, "threshold <= current" is the reference's strict d < sentinel
@@ -805,6 +807,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					e = __fmaf_ru(10.0f * rp, p.rq, e);
 					e = __fmaf_ru(2.0f * rp, rp, e);
 					if (TPC >= 2) { e = __fmaf_ru(8.0f * p.hmax, p.hmax, e); e = __fmaf_ru(4.0f * s0, p.hmax, e); }
+					if (TPC >= 2 && live && !wide) { n_sweeps += 1; n_small_s0 += (s0 < p.hmax) ? 1u : 0u; }
 					e = __fmul_ru(e, 1.05f * TC_EPS_SCALE * TC_U);
 					kk_s[sidx] = live ? (wide ? inf : __fsub_ru(e, p2lo)) : -inf;
 					// A row: a = -2 (p - c) as hi + lo; slots ax_hi ax_hi ax_lo | ay.. | az.. | 1 1 | 0...
@@ -884,12 +887,19 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						__syncwarp();
 						if (lane == 0) mbar_arrive(&tempty_bar[acc]);
 						const float kk = kk_s[sidx];                                    // -inf for dead rows
+						float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));
+						float tau = __fadd_ru(__fmul_ru(th, one8u), kk);
+						// most sub-tiles have nothing below tau: one vote on the minimum of the partial minima settles them
+						// (a threshold that another warp lowers meanwhile only costs an unnecessary exact pass)
+						float mall = mq[0];
+#pragma unroll
+						for (int qq = 1; qq + 1 < QPS; qq += 2) mall = min3(mall, mq[qq], mq[qq + 1]);
+						mall = fminf(mall, mq[QPS - 1]);
+						n_tests += QPS;
+						if (__ballot_sync(0xffffffffu, mall <= tau) == 0u) continue;
 #pragma unroll
 						for (int qq = 0; qq < QPS; qq++) {
-							const float th = __uint_as_float((unsigned)(key_s[sidx] >> 32));     // re-read: an exact pass may just have lowered it
-							const float tau = __fadd_ru(__fmul_ru(th, one8u), kk);
 							const unsigned need = __ballot_sync(0xffffffffu, mq[qq] <= tau);
-							n_tests += 1;
 							if (need) {                                       // warp-uniform
 								n_exact += 1;
 								const int q_in_tile = half * QPS + qq;        // quarter of the tile: slots [QT q, QT q + QT)
@@ -914,25 +924,10 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 								// distance of the current class above the class floor still ties with it (NaN / inf never pass)
 								const float nt_ = (mm < inf) ? lower_threshold<MODE>(mm) : inf;
 								if (nt_ <= th && kk > -inf) {
-									// rare (a source improves or ties its best a few times per sweep): find the FIRST slot of the quarter that
-									// attains the minimum while its originals are still in shared memory, and offer (threshold, slot)
-									const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(nt_) : nt_;
-									int found = -1;
-									for (int jq = j0; jq < j1 && found < 0; jq++) {
-										const float4 X = X4[jq], Y = Y4[jq], Z = Z4[jq];
-										float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
-										float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
-										float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
-										float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
-										if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
-										if (d0 <= target) found = 4 * jq;
-										else if (d1 <= target) found = 4 * jq + 1;
-										else if (d2 <= target) found = 4 * jq + 2;
-										else if (d3 <= target) found = 4 * jq + 3;
-									}
-									if (found >= 0)
-										atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * TILE_T + found));
+									atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * QPT + q_in_tile));
 								}
+								th = __uint_as_float((unsigned)(key_s[sidx] >> 32));     // re-read: this pass (or the warp on the other half) may have lowered it
+								tau = __fadd_ru(__fmul_ru(th, one8u), kk);
 							}
 						}
 					}
@@ -945,21 +940,44 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 			it += t1 - t0;
 			__syncthreads();
 			if (s_fail) break;
-			// ---- flush: (threshold, slot) of every source that found something below its starting threshold ----
+			// ---- index recovery: the first target of the remembered quarter that attains the exact minimum ----
+			// (done once per source and sweep here; finding the slot whenever the exact pass offers a quarter was measured
+			// 15-60 % slower: it stalls the warp inside the pipeline, several times per source on cold passes)
 			if (is_epi) {
-#pragma unroll
+#pragma unroll 1
 				for (int q = 0; q < SPT; q++) {
 					const int a = wq + 2 * GROUPS * q;
 					const int sidx = a * 128 + row;
 					const int i = sb * SBN + sidx;
 					const u64 kv = key_s[sidx];
-					const int slot = (int)(uint32_t)(kv & 0xffffffffull);         // -1: nothing below the starting threshold
-					if (i < p.n && slot >= 0) {
+					const int bs = (int)(uint32_t)(kv & 0xffffffffull);          // -1: nothing below the starting threshold
+					if (i < p.n && bs >= 0) {
 						const float th = __uint_as_float((unsigned)(kv >> 32));
+						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
+						const float* gx = p.tiles + (size_t)(bs / QPT) * TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % QPT) * QT;
+						const float4* GX = reinterpret_cast<const float4*>(gx);
+						const float4* GY = reinterpret_cast<const float4*>(gx + TILE_T);
+						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TILE_T);
 						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
-						// slot -> target index: one target per column, or column start + member (slots past a short column hold +inf)
-						const int jidx = (TPC == 1) ? slot : (__ldg(p.colstart + slot / TPC) + slot % TPC);
-						atomicMin(p.keys + i, ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)jidx);
+						int found = -1;
+						for (int jq = 0; jq < QT / 4 && found < 0; jq++) {
+							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
+							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
+							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
+							float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
+							float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
+							if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+							if (d0 <= target) found = 4 * jq;
+							else if (d1 <= target) found = 4 * jq + 1;
+							else if (d2 <= target) found = 4 * jq + 2;
+							else if (d3 <= target) found = 4 * jq + 3;
+						}
+						if (found >= 0) {
+							// slot -> target index: one target per column, or column start + member (slots past a short column hold +inf)
+							const int jidx = (TPC == 1) ? (bs * QT + found) : (__ldg(p.colstart + (size_t)bs * QC + found / TPC) + found % TPC);
+							const u64 key = ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)jidx;
+							atomicMin(p.keys + i, key);
+						}
 					}
 				}
 			}
@@ -968,9 +986,18 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 	}
 	__syncthreads();
 	if (s_fail && tid == 0) *p.fail = 1;
+	if (tid == 0) {
+		// every CTA has taken its last grab before it gets here: the last one through re-arms the counters for the next pass
+		__threadfence();
+		if (atomicAdd(p.exit_counter, 1ull) == (unsigned long long)gridDim.x - 1ull) { *p.work_counter = 0ull; *p.exit_counter = 0ull; __threadfence(); }
+	}
 	if (p.stats != nullptr && is_epi) {      // one test = one (warp, slab, quarter of a sub-tile)
 		for (int o = 16; o > 0; o >>= 1) { n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o); n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o); }
 		if (lane == 0) { atomicAdd(p.stats, n_tests / 32); atomicAdd(p.stats + 1, n_exact / 32); }
+		if (TPC >= 2) {
+			for (int o = 16; o > 0; o >>= 1) { n_sweeps += __shfl_xor_sync(0xffffffffu, n_sweeps, o); n_small_s0 += __shfl_xor_sync(0xffffffffu, n_small_s0, o); }
+			if (lane == 0) { atomicAdd(p.stats + 2, (unsigned long long)n_sweeps); atomicAdd(p.stats + 3, (unsigned long long)n_small_s0); }
+		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
@@ -992,7 +1019,7 @@ static int tc_current_tpc(const Ctx* c)
 {
 	if (c->kt_variant < 0) return c->kt_tpc_auto;
 	const int v = c->kt_variant;
-	return (v == 17) ? 4 : (v == 15 || v == 16) ? 8 : (v >= 12) ? 16 : (v == 11) ? 8 : (v >= 10) ? 4 : (v >= 8 ? 2 : 1);
+	return (v == 19 || v == 20) ? 2 : (v == 17 || v == 18) ? 4 : (v == 15 || v == 16) ? 8 : (v >= 12) ? 16 : (v == 11) ? 8 : (v >= 10) ? 4 : (v >= 8 ? 2 : 1);
 }
 int build_filter_tc_data(Ctx* c)
 {
@@ -1112,7 +1139,7 @@ static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
 	const long long max_ctas = (p.total_units + p.min_chunk - 1) / p.min_chunk;
 	if (grid > max_ctas) grid = max_ctas;
-	ICPB_CUDA(c, cudaMemsetAsync(c->kf_work_counter, 0, sizeof(unsigned long long), c->stream));
+	ICPB_CUDA(c, cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), c->stream));
 	kern<<<(unsigned)grid, TC_THREADS, SMEM, c->stream>>>(p);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
@@ -1140,8 +1167,7 @@ static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
 	const long long max_ctas = (p.total_units + p.min_chunk - 1) / p.min_chunk;
 	if (grid > max_ctas) grid = max_ctas;
-	ICPB_CUDA(c, cudaMemsetAsync(c->kf_work_counter, 0, sizeof(unsigned long long), c->stream));
-	kern<<<(unsigned)grid, 64 + 256 * GROUPS, SMEM, c->stream>>>(p);
+	kern<<<(unsigned)grid, 64 + 256 * GROUPS, SMEM, c->stream>>>(p);      // the counters re-arm themselves (exit_counter)
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	return ICPB_OK;
@@ -1168,8 +1194,11 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	c->kf_dims_last = 4;                       // reported as "4" = the 3-D bound on the tensor cores
 	c->kf_seeded = true;
 	c->pairs_acc += (double)c->n * (double)c->m;
-	if (!c->kf_work_counter) ICPB_CUDA(c, cudaMalloc((void**)&c->kf_work_counter, sizeof(unsigned long long)));
-	p.work_counter = c->kf_work_counter;
+	if (!c->kt_work) {
+		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_work, 2 * sizeof(unsigned long long)));
+		ICPB_CUDA(c, cudaMemsetAsync(c->kt_work, 0, 2 * sizeof(unsigned long long), c->stream));
+	}
+	p.work_counter = c->kt_work; p.exit_counter = c->kt_work + 1;
 	// ICPB_KT_VAR selects the pipeline shape (experiments; results are identical):
 	//   0: one 256-column MMA per (slab, tile), one accumulator per epilogue group, 8 slabs, 1 CTA/SM
 	//   1: two 128-column MMAs per (slab, tile), two accumulators per group (MMA of the next unit overlaps the read of this one)
@@ -1180,10 +1209,10 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	//   8 / 9: as 7 / 6 in the PAIRED form: one column per two consecutive targets (tc_pack_group_kernel); 10: as 7 with QUADS
 	if (!forced) {
 		switch (c->kt_tpc) {
-		case 16: return launch_tc_split<2, 8, 2, 16, 16>(c, dist_mode, p, 12);
-		case 8:  return launch_tc_split<2, 8, 3, 16, 8>(c, dist_mode, p, 11);
-		case 4:  return launch_tc_split<2, 8, 3, 16, 4>(c, dist_mode, p, 10);
-		case 2:  return launch_tc_split<2, 8, 3, 16, 2>(c, dist_mode, p, 8);
+		case 16: return launch_tc_split<2, 8, 2, 16, 16, 8>(c, dist_mode, p, 14);
+		case 8:  return launch_tc_split<2, 8, 3, 16, 8, 8>(c, dist_mode, p, 16);
+		case 4:  return launch_tc_split<2, 8, 3, 16, 4, 8>(c, dist_mode, p, 18);
+		case 2:  return launch_tc_split<2, 8, 3, 16, 2, 8>(c, dist_mode, p, 20);
 		default: return launch_tc_split<2, 8, 3, 16, 1>(c, dist_mode, p, 7);
 		}
 	}
@@ -1205,6 +1234,9 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	case 15: return launch_tc_split<2, 8, 3, 16, 8, 16>(c, dist_mode, p, 15);
 	case 16: return launch_tc_split<2, 8, 3, 16, 8, 8>(c, dist_mode, p, 16);
 	case 17: return launch_tc_split<2, 8, 3, 16, 4, 16>(c, dist_mode, p, 17);
+	case 18: return launch_tc_split<2, 8, 3, 16, 4, 8>(c, dist_mode, p, 18);
+	case 19: return launch_tc_split<2, 8, 3, 16, 2, 16>(c, dist_mode, p, 19);
+	case 20: return launch_tc_split<2, 8, 3, 16, 2, 8>(c, dist_mode, p, 20);
 	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
 	}
 }

@@ -61,6 +61,11 @@ template <int NV> __device__ __forceinline__ bool last_block_sum(double* partial
 	static_assert(NV <= 32, "one lane per value");
 	__shared__ int is_last;
 	__shared__ double gsum[GROUPS * NVP];
+	if (gridDim.x == 1) {             // small clouds: the block's row is the sum — no ticket, no fences, no second trip to L2
+		if (threadIdx.x < NV) dst[threadIdx.x] = partials[threadIdx.x];      // written by this same thread in block_reduce
+		__syncthreads();
+		return true;
+	}
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {

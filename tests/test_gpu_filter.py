@@ -196,11 +196,11 @@ def test_grouped_columns_on_rasters_no_group_size_divides(ctx, ib, orc):
 
 
 def test_tc_group_size_policy(ib, orc):
-    """Automatic choice of K1T's targets per column: about sqrt(m) / 64 on a scan-ordered cloud, one at once for a cloud in
+    """Automatic choice of K1T's targets per column: the power of two at or above sqrt(m) / 64 on a scan-ordered cloud, one at once for a cloud in
     arbitrary order (mean step of the scan far above the point spacing), and again from the start for the next target."""
     c = _context(ib, ICPB_K1_FILTER_MIN_PAIRS=0)
     try:
-        for w, want in ((128, 2), (317, 4)):
+        for w, want in ((128, 2), (317, 8)):
             D, M = orc.synth_p2p(w)
             c.set_target(M); c.set_source(D)
             a = c.match(0, ib.NN_BRUTE)
@@ -216,6 +216,6 @@ def test_tc_group_size_policy(ib, orc):
         D, M = orc.synth_p2p(317)
         c.set_target(M); c.set_source(D)
         c.match(0, ib.NN_BRUTE)
-        assert c.filter_tc_config()["targets_per_column"] in (4, 2)
+        assert c.filter_tc_config()["targets_per_column"] in (8, 4)
     finally:
         c.close()

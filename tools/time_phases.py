@@ -32,6 +32,10 @@ with ib.Context(0) as ctx:
                 ctx.set_source(D)
                 e, r = ctx.run(ib.default_params(max_iter=64, nn_method=nn))
                 out["p2p_%s_%s" % (tag, name)] = {"iterations_run": r.iterations_run, "elapsed_ms": r.elapsed_ms, "us_per_iteration": 1e3 * r.elapsed_ms / r.iterations_run}
+                ctx.set_source(D)
+                e, r = ctx.run(ib.default_params(max_iter=64, nn_method=nn, sync_every=1, flags=ib.FLAG_PROFILE))
+                out["p2p_%s_%s" % (tag, name)].update({"match_us_per_it": 1e3 * r.match_ms / r.iterations_run, "minimize_us_per_it": 1e3 * r.minimize_ms / r.iterations_run,
+                                                       "transform_us_per_it": 1e3 * r.transform_ms / r.iterations_run, "elapsed_ms_profiled": r.elapsed_ms})
     D, M = icp_synth.p2p_clouds(317, 100000)
     ctx.set_target(M); ctx.set_source(D)
     ms = [ctx.estimate_normals(4) for _ in range(3)]
