@@ -50,7 +50,7 @@ def clocks_start(device_index):
                               "--query-gpu=timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
                               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                              "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+                              "--format=csv,noheader,nounits", "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
         return p, f
     except Exception:
         return None, None

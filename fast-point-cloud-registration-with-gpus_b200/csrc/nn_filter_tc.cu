@@ -22,21 +22,19 @@
 // sum |terms| <= Rq^2 + 2 Rp Rq. The price of the larger eps is a few more exact passes (the test fails for sub-tiles
 // within sqrt(thr + eps) instead of sqrt(thr)); measured exact-pass rate in bench.py's line.
 //
-// Kernel: one CTA per SM, 10 warps.
-//   warp 0   : TMA producer — streams target tiles (B operand block in the canonical K-major no-swizzle UMMA layout +
-//              the original coordinates for the exact pass, one 19 KB cp.async.bulk per 256 targets) through a 3-stage ring
-//   warp 1   : MMA issuer — for every tile, every one of the 8 source slabs (128 sources each, A operand built in shared
-//              memory by the CTA) and both 128-target sub-tiles: two tcgen05.mma (K = 2 x 8) into one of four 128-column
-//              TMEM accumulators, tcgen05.commit
-//   warps 2-9: two epilogue groups of 4 warps (one warp per TMEM lane quarter); group g owns the slabs a = g, g+2, g+4,
-//              g+6 and the accumulators g and g+2, which its (slab, sub-tile) units use alternately — the MMA of the next
-//              unit runs while this one is read: tcgen05.ld 32 columns at a time, running minimum over the sub-tile,
-//              ballot against tau, exact pass (K1's packed chain from the original coordinates in the ring) where needed.
-//              (First version: one 256-column accumulator per group; the group then sat idle for the ~300 cycles of every
-//              MMA: 1.52e13 pairs/s. Measured numbers in DESIGN.md.)
-// A source's state (threshold, remembered sub-tile, tau) is touched by exactly one thread, sub-tiles are visited in
-// ascending order: the tie rule is K1's. Every mbarrier wait is bounded: a protocol error ends the kernel with a flag
-// instead of hanging the GPU.
+// Kernels. k1_filter_tc_split (the default): one CTA per SM, 18 warps.
+//   warps 0-15: epilogue — two groups of 8 (two warps per TMEM lane quarter, each reading one 128-column half of an
+//               accumulator): tcgen05.ld 16 columns at a time, partial minima per unit of QC columns, one vote per half on
+//               their minimum, K1's exact packed chain over the units that cannot be excluded (originals from the ring)
+//   warp 16   : TMA producer — streams target tiles (B operand block in the canonical K-major no-swizzle UMMA layout +
+//               the original coordinates of the tile's 256 x TPC target slots, one cp.async.bulk each) through a 2-3 stage ring
+//   warp 17   : MMA issuer — for every tile and every one of the 8 source slabs (128 sources each, A operand built in
+//               shared memory by the CTA): two tcgen05.mma (K = 2 x 8) into one of two 256-column TMEM accumulators,
+//               tcgen05.commit to an mbarrier
+// A source's state is one 64-bit word (threshold bits << 32 | unit) updated with atomicMin in shared memory: the tie rule
+// is K1's whatever order the warps get there in. Every mbarrier wait is bounded: a protocol error ends the kernel with a
+// flag instead of hanging the GPU. k1_filter_tc (ICPB_KT_VAR 0-4) is the first pipeline shape (10 warps, one target per
+// column), kept for the comparison in DESIGN.md.
 #include "common.cuh"
 #include "k1_device.cuh"
 #include <cmath>
@@ -960,17 +958,24 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						const float4* GZ = reinterpret_cast<const float4*>(gx + 2 * TILE_T);
 						const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
 						int found = -1;
-						for (int jq = 0; jq < QT / 4 && found < 0; jq++) {
-							const float4 X = __ldg(GX + jq), Y = __ldg(GY + jq), Z = __ldg(GZ + jq);
-							float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
-							float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
-							float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
-							float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
-							if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
-							if (d0 <= target) found = 4 * jq;
-							else if (d1 <= target) found = 4 * jq + 1;
-							else if (d2 <= target) found = 4 * jq + 2;
-							else if (d3 <= target) found = 4 * jq + 3;
+						// the unit comes from L2: four float4 triples (16 slots) are requested together, one round trip per 16 slots
+						static_assert((QT / 4) % 4 == 0, "whole groups of four float4 per unit");
+						for (int jq = 0; jq < QT / 4 && found < 0; jq += 4) {
+							float4 X[4], Y[4], Z[4];
+#pragma unroll
+							for (int u = 0; u < 4; u++) { X[u] = __ldg(GX + jq + u); Y[u] = __ldg(GY + jq + u); Z[u] = __ldg(GZ + jq + u); }
+#pragma unroll
+							for (int u = 3; u >= 0; u--) {               // descending, so that the lowest slot is what remains
+								float d0 = dist_chain(sx, sy, sz, X[u].x, Y[u].x, Z[u].x);
+								float d1 = dist_chain(sx, sy, sz, X[u].y, Y[u].y, Z[u].y);
+								float d2 = dist_chain(sx, sy, sz, X[u].z, Y[u].z, Z[u].z);
+								float d3 = dist_chain(sx, sy, sz, X[u].w, Y[u].w, Z[u].w);
+								if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+								if (d3 <= target) found = 4 * (jq + u) + 3;
+								if (d2 <= target) found = 4 * (jq + u) + 2;
+								if (d1 <= target) found = 4 * (jq + u) + 1;
+								if (d0 <= target) found = 4 * (jq + u);
+							}
 						}
 						if (found >= 0) {
 							// slot -> target index: one target per column, or column start + member (slots past a short column hold +inf)

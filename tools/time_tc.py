@@ -16,7 +16,7 @@ D, M = icp_synth.p2p_clouds(W)
 out = {}
 ref_idx = None
 variants = [int(v) for v in os.environ.get("TC_VARIANTS", "0,1,2,3,4").split(",")]
-cases = [("k1t_var%d" % v, {"ICPB_K1_TC": "1", "ICPB_KT_VAR": str(v)}) for v in variants if v >= 0] + [("k1t_auto", {"ICPB_K1_TC": "1"}), ("k1f_fp32", {"ICPB_K1_TC": "0"})]
+cases = [("k1t_var%d" % v, {"ICPB_K1_TC": "1", "ICPB_KT_VAR": str(v)}) for v in variants if v >= 0] + [("k1t_auto", {"ICPB_K1_TC": "1"})] + ([] if os.environ.get("SKIP_K1F") else [("k1f_fp32", {"ICPB_K1_TC": "0"})])
 for name, env in cases:
     os.environ.pop("ICPB_K1_TC", None); os.environ.pop("ICPB_KT_VAR", None)
     os.environ.update(env)
