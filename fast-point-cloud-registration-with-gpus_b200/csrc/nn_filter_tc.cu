@@ -325,33 +325,35 @@ template <int LDW> __device__ __forceinline__ float subtile_min(uint32_t taddr)
 }
 
 // 128 / QC partial minima of the 128 columns starting at taddr: columns [QC q, QC q + QC), 16-column loads double-buffered
-template <int QC> __device__ __forceinline__ void subtile_mins(uint32_t taddr, float (&mq)[128 / QC])
+template <int QC, int NCOL> __device__ __forceinline__ void subtile_mins(uint32_t taddr, float (&mq)[NCOL / QC])
 {
 	static_assert(QC == 32 || QC == 16 || QC == 8, "columns per exact-pass unit");
+	static_assert(NCOL == 128 || NCOL == 64, "columns a warp reads per unit");
+	constexpr int NQ = NCOL / 32;
 	const float inf = __int_as_float(0x7f800000);
 	float va[16], vb[16];
 	tmem_ld16(taddr, va);
 #pragma unroll
-	for (int q = 0; q < 4; q++) {
+	for (int q = 0; q < NQ; q++) {
 		tmem_wait_ld(); tmem_ld16(taddr + 32 * q + 16, vb);
 		if constexpr (QC == 32) {
 			float m0 = inf, m1 = inf;
 			min16(va, m0, m1);
-			tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+			tmem_wait_ld(); if (q < NQ - 1) tmem_ld16(taddr + 32 * q + 32, va);
 			min16(vb, m0, m1);
 			mq[q] = fminf(m0, m1);
 		} else if constexpr (QC == 16) {
 			float m0 = inf, m1 = inf;
 			min16(va, m0, m1);
 			mq[2 * q] = fminf(m0, m1);
-			tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+			tmem_wait_ld(); if (q < NQ - 1) tmem_ld16(taddr + 32 * q + 32, va);
 			m0 = inf; m1 = inf;
 			min16(vb, m0, m1);
 			mq[2 * q + 1] = fminf(m0, m1);
 		} else {
 			mq[4 * q]     = fminf(min3(va[0], va[1], va[2]), min3(va[3], va[4], va[5])); mq[4 * q] = min3(mq[4 * q], va[6], va[7]);
 			mq[4 * q + 1] = fminf(min3(va[8], va[9], va[10]), min3(va[11], va[12], va[13])); mq[4 * q + 1] = min3(mq[4 * q + 1], va[14], va[15]);
-			tmem_wait_ld(); if (q < 3) tmem_ld16(taddr + 32 * q + 32, va);
+			tmem_wait_ld(); if (q < NQ - 1) tmem_ld16(taddr + 32 * q + 32, va);
 			mq[4 * q + 2] = fminf(min3(vb[0], vb[1], vb[2]), min3(vb[3], vb[4], vb[5])); mq[4 * q + 2] = min3(mq[4 * q + 2], vb[6], vb[7]);
 			mq[4 * q + 3] = fminf(min3(vb[8], vb[9], vb[10]), min3(vb[11], vb[12], vb[13])); mq[4 * q + 3] = min3(mq[4 * q + 3], vb[14], vb[15]);
 		}
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams 
 // TPC = targets per MMA column: 1, or 2 / 4 = the grouped forms (tiles of 256 TPC targets, see tc_pack_group_kernel).
 // The filter test, the exact pass and the remembered unit are QUARTERS of a warp's sub-tile: 32 columns = 32 TPC targets
 // (the running minimum costs the same split four ways; an exact pass then covers a quarter of the targets).
-template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC>
+template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC, int NACC>
 __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const KTParams p)
 {
 	constexpr int TILE_T = TC_TN * TPC;                  // targets per tile
@@ -683,11 +685,15 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 	constexpr int TILE_FLOATS = tcg_tile_floats(TPC);
 	constexpr int QT = QC * TPC;                         // targets per "quarter" (QC columns): the unit of the exact pass and of the key's index
 	constexpr int QPT = TILE_T / QT;                     // quarters per tile: 256 / QC
-	constexpr int QPS = TC_TRK / QC;                     // quarters per sub-tile
 	constexpr int TILE_BYTES = TILE_FLOATS * 4;
-	constexpr int SUBS = TC_TN / TC_TRK;                 // 2 sub-tiles per tile = per MMA unit
-	constexpr int UNIT_COLS = TC_TN;                     // one 256-column accumulator per (slab, tile) unit
-	constexpr int TMEM_COLS = 2 * UNIT_COLS;
+	// NACC = 1: one 256-column accumulator per group, a unit = (slab, tile). NACC = 2: two 128-column accumulators per group,
+	// a unit = (slab, half tile): the MMA of the next half runs while the group reads this one.
+	constexpr int UNIT_COLS = TC_TN / NACC;
+	constexpr int WCOLS = UNIT_COLS / 2;                 // columns a warp reads per unit (two warps per TMEM lane quarter)
+	constexpr int QPS = WCOLS / QC;                      // exact-pass units per warp and MMA unit
+	constexpr int NBAR = (GROUPS == 2) ? 2 * NACC : 2;   // accumulators
+	constexpr int TMEM_COLS = 512;
+	static_assert(NACC == 1 || (NACC == 2 && GROUPS == 2), "double-buffered accumulators need the two-group form");
 	constexpr int SBN = 128 * SLABS;                     // sources per source block
 	constexpr int NEPI = 8 * GROUPS;                     // epilogue warps
 	constexpr int SPT = SBN / (32 * NEPI);               // sources each epilogue thread sets up and flushes
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 	if (p.done != nullptr && *p.done) return;
 	extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
 	unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);      // 1 KB alignment by hand
-	__shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+	__shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[NBAR], tempty_bar[NBAR];
 	__shared__ uint32_t tmem_base_s;
 	__shared__ unsigned long long s_u0;
 	__shared__ int s_len, s_fail;
@@ -723,7 +729,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 
 	if (tid == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NEPI); }
-		for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+		for (int a = 0; a < NBAR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
 		s_fail = 0;
 		fence_mbar_init();
 	}
@@ -842,21 +848,25 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 						if (!mbar_wait_bounded(&full_bar[st], (uint32_t)(use & 1))) { failed = true; break; }
 						const uint32_t sB = smem_u32(ring + (size_t)st * TILE_FLOATS);
 #pragma unroll 1
-						for (int a = 0; a < SLABS; a++) {
-							// GROUPS = 2: slab a belongs to group a & 1 and goes to accumulator a & 1; GROUPS = 1: the units alternate
+						for (int a = 0; a < SLABS && !failed; a++) {
+							// GROUPS = 2: slab a belongs to group a & 1; its NACC unit(s) go to the group's accumulator(s). GROUPS = 1: the units alternate
 							const int v = (GROUPS == 2) ? (k * (SLABS / 2) + (a >> 1)) : (k * SLABS + a);
-							const int acc = (GROUPS == 2) ? (a & 1) : (v & 1);
-							const int j = (GROUPS == 2) ? v : (v >> 1);                       // use counter of accumulator `acc`
-							if (j >= 1 && !mbar_wait_bounded(&tempty_bar[acc], (uint32_t)((j - 1) & 1))) { failed = true; break; }
-							asm volatile("tcgen05.fence::after_thread_sync;");
 							const uint32_t sA = smem_u32(a_slabs + (size_t)a * (TC_A_BYTES / 4));
+#pragma unroll 1
+							for (int hs = 0; hs < NACC; hs++) {
+								const int acc = (GROUPS == 2) ? ((a & 1) * NACC + hs) : (v & 1);
+								const int j = (GROUPS == 2) ? v : (v >> 1);                       // use counter of accumulator `acc`
+								if (j >= 1 && !mbar_wait_bounded(&tempty_bar[acc], (uint32_t)((j - 1) & 1))) { failed = true; break; }
+								asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-							for (int kk2 = 0; kk2 < 2; kk2++) {
-								const uint64_t dA = umma_desc(sA + kk2 * 256), dB = umma_desc(sB + kk2 * 256);   // K advances by two 128 B core matrices
-								asm volatile("{\n.reg .pred pacc;\nsetp.ne.b32 pacc, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pacc;\n}\n"
-								             :: "r"(tmem_base + (uint32_t)(acc * UNIT_COLS)), "l"(dA), "l"(dB), "r"(idesc), "r"((uint32_t)kk2));
+								for (int kk2 = 0; kk2 < 2; kk2++) {
+									// K advances by two 128 B core matrices; half hs starts at row hs * UNIT_COLS of the B block (row groups of 8 rows, 512 B apart)
+									const uint64_t dA = umma_desc(sA + kk2 * 256), dB = umma_desc(sB + hs * (UNIT_COLS / 8) * 512 + kk2 * 256);
+									asm volatile("{\n.reg .pred pacc;\nsetp.ne.b32 pacc, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pacc;\n}\n"
+									             :: "r"(tmem_base + (uint32_t)(acc * UNIT_COLS)), "l"(dA), "l"(dB), "r"(idesc), "r"((uint32_t)kk2));
+								}
+								asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&tfull_bar[acc])) : "memory");
 							}
-							asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&tfull_bar[acc])) : "memory");
 						}
 					}
 				}
@@ -870,16 +880,18 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					const float4* Y4 = X4 + TILE_T / 4;
 					const float4* Z4 = Y4 + TILE_T / 4;
 #pragma unroll 1
-					for (int a = grp; a < SLABS; a += GROUPS) {
+					for (int un = 0; un < (SLABS / GROUPS) * NACC && !failed; un++) {
+						// (a, hs): the group's slabs in ascending order, each slab's NACC units one after the other
+						const int a = grp + GROUPS * (un / NACC), hs = un % NACC;
 						const int sidx = a * 128 + row;
 						const int v = (GROUPS == 2) ? (k * (SLABS / 2) + (a >> 1)) : (k * SLABS + a);
-						const int acc = (GROUPS == 2) ? grp : (v & 1);
+						const int acc = (GROUPS == 2) ? (grp * NACC + hs) : (v & 1);
 						const int j = (GROUPS == 2) ? v : (v >> 1);
 						if (!mbar_wait_bounded(&tfull_bar[acc], (uint32_t)(j & 1))) { failed = true; break; }
 						asm volatile("tcgen05.fence::after_thread_sync;");
-						const uint32_t taddr = tmem_base + (uint32_t)(acc * UNIT_COLS + half * TC_TRK) + ((uint32_t)(quarter * 32) << 16);
+						const uint32_t taddr = tmem_base + (uint32_t)(acc * UNIT_COLS + half * WCOLS) + ((uint32_t)(quarter * 32) << 16);
 						float mq[QPS];
-						subtile_mins<QC>(taddr, mq);
+						subtile_mins<QC, WCOLS>(taddr, mq);
 						// the accumulator is in registers: hand it back to the MMA warp before the (rare) exact pass
 						asm volatile("tcgen05.fence::before_thread_sync;");
 						__syncwarp();
@@ -900,7 +912,7 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 							const unsigned need = __ballot_sync(0xffffffffu, mq[qq] <= tau);
 							if (need) {                                       // warp-uniform
 								n_exact += 1;
-								const int q_in_tile = half * QPS + qq;        // quarter of the tile: slots [QT q, QT q + QT)
+								const int q_in_tile = (hs * UNIT_COLS + half * WCOLS) / QC + qq;      // exact-pass unit of the tile: slots [QT q, QT q + QT)
 								const int j0 = q_in_tile * (QT / 4), j1 = j0 + QT / 4;
 								const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
 								const u64 PX = pack2(sx, sx), PY = pack2(sy, sy), PZ = pack2(sz, sz);
@@ -1024,6 +1036,7 @@ static int tc_current_tpc(const Ctx* c)
 {
 	if (c->kt_variant < 0) return c->kt_tpc_auto;
 	const int v = c->kt_variant;
+	if (v >= 21 && v <= 24) return 16 >> (v - 21);
 	return (v == 19 || v == 20) ? 2 : (v == 17 || v == 18) ? 4 : (v == 15 || v == 16) ? 8 : (v >= 12) ? 16 : (v == 11) ? 8 : (v >= 10) ? 4 : (v >= 8 ? 2 : 1);
 }
 int build_filter_tc_data(Ctx* c)
@@ -1151,7 +1164,7 @@ static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
 	return ICPB_OK;
 }
 
-template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC = 32>
+template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC = 32, int NACC = 1>
 static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 {
 	constexpr int SBN = 128 * SLABS;
@@ -1159,12 +1172,14 @@ static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 	constexpr size_t SMEM = (size_t)SLABS * TC_A_BYTES + (size_t)STAGES * TILE_BYTES + (size_t)6 * SBN * 4 + 1024;
 	const int nb = (c->n + SBN - 1) / SBN;
 	p.total_units = (long long)nb * p.nt;
-	p.min_chunk = (8 / TPC) > 0 ? 8 / TPC : 1; p.max_chunk = (128 / TPC) > 1 ? 128 / TPC : 2; p.gss_div = 4;      // same number of targets per grab whatever TPC
+	// same number of targets per grab whatever TPC; up to 128k targets per segment: every segment costs a source set-up, three
+	// block-wide barriers and an index recovery (measured at 1M x 1M: 8-tile segments 9.25 ms, 32-tile 8.35 ms per pass)
+	p.min_chunk = (8 / TPC) > 0 ? 8 / TPC : 1; p.max_chunk = (512 / TPC) > 1 ? 512 / TPC : 2; p.gss_div = 4;
 	if (c->kf_gss[0] > 0) { p.min_chunk = c->kf_gss[0]; p.max_chunk = c->kf_gss[1]; p.gss_div = c->kf_gss[2]; }
 	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
 	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
 	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
-	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC, QC> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC, QC>;
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC, QC, NACC> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC, QC, NACC>;
 	static bool attr_set[2][32][64] = {};
 	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 31][c->device & 63];
 	if (!done) { ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); done = true; }
@@ -1242,6 +1257,10 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	case 18: return launch_tc_split<2, 8, 3, 16, 4, 8>(c, dist_mode, p, 18);
 	case 19: return launch_tc_split<2, 8, 3, 16, 2, 16>(c, dist_mode, p, 19);
 	case 20: return launch_tc_split<2, 8, 3, 16, 2, 8>(c, dist_mode, p, 20);
+	case 21: return launch_tc_split<2, 8, 2, 16, 16, 8, 2>(c, dist_mode, p, 21);     // 21-24: two 128-column accumulators per group
+	case 22: return launch_tc_split<2, 8, 3, 16, 8, 8, 2>(c, dist_mode, p, 22);
+	case 23: return launch_tc_split<2, 8, 3, 16, 4, 8, 2>(c, dist_mode, p, 23);
+	case 24: return launch_tc_split<2, 8, 3, 16, 2, 8, 2>(c, dist_mode, p, 24);
 	default: return launch_tc_variant<2, 1, 8, 3, 1, 32>(c, dist_mode, p, 0);
 	}
 }

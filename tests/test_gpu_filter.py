@@ -23,7 +23,8 @@ def _context(ib, **env):
 
 # every test runs with the bound chosen automatically (full on cold passes, planar on warm ones, switched by the
 # measured exact-pass rate), with the planar bound forced for each choice of the dropped axis, and with the full one
-@pytest.fixture(scope="module", params=["tc-auto", "auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2", "tc-pair", "tc-pair1", "tc-quad", "tc-oct", "tc-hex"])
+@pytest.fixture(scope="module", params=["tc-auto", "auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2", "tc-pair", "tc-pair1", "tc-quad", "tc-oct", "tc-hex",
+                                        "tc-u8x16", "tc-u16x16", "tc-u8x8", "tc-u8x2", "tc-d16", "tc-d8", "tc-d4", "tc-d2"])
 def ctx(ib, request):
     """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
     use the direct kernel, which would make most of these small cases vacuous)."""
@@ -35,7 +36,9 @@ def ctx(ib, request):
     elif request.param == "full":
         env.update(ICPB_KF_DIMS=3)
     elif request.param.startswith("tc"):           # K1T: the 3-D bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
-        env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc-auto": -1, "tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7, "tc-pair": 8, "tc-pair1": 9, "tc-quad": 10, "tc-oct": 11, "tc-hex": 12}[request.param])
+        env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc-auto": -1, "tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7, "tc-pair": 8, "tc-pair1": 9, "tc-quad": 10, "tc-oct": 11, "tc-hex": 12,
+                                                  # exact-pass units of 8 / 16 columns at 16 / 8 / 2 targets per column; d*: two 128-column accumulators per group
+                                                  "tc-u16x16": 13, "tc-u8x16": 14, "tc-u8x8": 16, "tc-u8x2": 20, "tc-d16": 21, "tc-d8": 22, "tc-d4": 23, "tc-d2": 24}[request.param])
     c = _context(ib, **env)
     c.variant = request.param
     yield c
