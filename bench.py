@@ -479,8 +479,9 @@ def run_stream_config(args, env, emit):
                 fc = ctx.filter_config()
                 floor_extra[name] = {"points": "%dx%d" % (nf, nf), "nn_pairs_per_sec": float(nf) * nf * r_f.iterations_run / (r_f.match_ms * 1e-3),
                                      "match_ms_per_iteration": float(r_f.match_ms) / r_f.iterations_run, "bound_dims": fc["dims_last"],
-                                     "exact_fraction": fc["last_exact_fraction"]}
-            floor_extra["what"] = ("k1_filter on clouds that are not height fields (3 warm iterations each, device time of the matching kernel); "
+                                     "exact_fraction": fc["last_exact_fraction"], "tensor_core_filter": ctx.filter_tc_config()}
+            floor_extra["what"] = ("ICPB_NN_BRUTE on clouds that are neither height fields nor in scan order (3 warm iterations each, device time of the "
+                                   "matching kernel; the tensor-core filter groups such clouds along their Morton order); "
                                    "non-finite or denormal-range inputs fall to the direct kernel: roofline_direct_kernel below")
             ctx.set_target(M); ctx.set_source(shard)
         except Exception as exc:      # noqa: BLE001

@@ -267,6 +267,14 @@ struct Ctx {
 	float*  kt_hmax_d = nullptr;        // device: [0] largest group radius (float), then the step sum (double at byte 8)
 	float   kt_hmax = 0.0f;
 	int     kt_ncols = 0;
+	int     kt_sort_mode = -1;          // ICPB_KT_SORT: 1 = always build the tiles over the targets in Morton order, 0 = never, -1 = when the scan order is incoherent
+	bool    kt_sorted = false;          // what the current tiles are
+	unsigned long long* kt_mkeys = nullptr;   // [2][cap] Morton keys (in / out of the radix sort)
+	int*    kt_perm2 = nullptr;         // [2][cap] indices (in / out): the second half is the sorted order's original indices
+	float4* kt_q4s = nullptr;           // the targets in Morton order
+	size_t  kt_sort_cap = 0;
+	int*    kt_slot_index = nullptr;    // original index of the target in every slot of every tile
+	size_t  kt_slot_cap = 0;
 
 	// iteration state
 	IterState* st = nullptr;     // device

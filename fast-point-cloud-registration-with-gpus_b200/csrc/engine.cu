@@ -181,6 +181,7 @@ int create_context(Ctx** out, int device)
 	if (const char* e = getenv("ICPB_K1_TC")) c->k1_use_tc = atoi(e) != 0;
 	if (!c->k1_use_tc && !getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = 1e9;      // the FP32 filter's own crossover
 	if (const char* e = getenv("ICPB_KT_VAR")) c->kt_variant = atoi(e);
+	if (const char* e = getenv("ICPB_KT_SORT")) c->kt_sort_mode = atoi(e) != 0 ? 1 : 0;
 	if (const char* e = getenv("ICPB_KT_TPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) { c->kt_tpc_start = v; c->kt_tpc_auto = v; c->kt_tpc_forced_start = true; } }
 	if (const char* e = getenv("ICPB_K1_FILTER_MIN_PAIRS")) c->kf_min_pairs = atof(e);
 	if (const char* e = getenv("ICPB_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
@@ -275,7 +276,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_work); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
+	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_work); cudaFree(c->kt_mkeys); cudaFree(c->kt_perm2); cudaFree(c->kt_q4s); cudaFree(c->kt_slot_index); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
 	cudaFree(c->grid_counts); cudaFree(c->grid_cell_of); cudaFree(c->grid_sums); cudaFree(c->grid_mm);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);

@@ -625,6 +625,15 @@ extern "C" int icpb_get_filter_tc_config(icpb_ctx* ctx, int* enabled, int* targe
 	return ICPB_OK;
 }
 
+extern "C" int icpb_get_filter_tc_order(icpb_ctx* ctx, int* morton_order)
+{
+	using namespace icpb;
+	if (!ctx) return ICPB_ERR_BADARG;
+	Ctx* c = reinterpret_cast<Ctx*>(ctx);
+	if (morton_order) *morton_order = (c->kt_ready && c->kt_sorted) ? 1 : 0;
+	return ICPB_OK;
+}
+
 extern "C" int icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile_exact)
 {
 	using namespace icpb;

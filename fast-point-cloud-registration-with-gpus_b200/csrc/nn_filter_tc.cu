@@ -38,7 +38,9 @@
 #include "common.cuh"
 #include "k1_device.cuh"
 #include <cmath>
+#include <algorithm>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace icpb {
 
@@ -76,6 +78,7 @@ struct KTParams {
 	int*         fail;               // set on a protocol time-out
 	const int*   colstart;           // grouped form: index of the first target of every column
 	float        hmax;               // grouped form: the largest group radius h
+	const int*   slot_index;         // sorted form: original index of the target in every slot of every tile (-1: unused slot)
 };
 
 // element (row r, slot k) of an operand block in the canonical K-major no-swizzle layout: core matrices of 8 rows x 16 B,
@@ -199,10 +202,45 @@ __global__ void tcg_colstart_kernel(const int* __restrict__ runstart, const int*
 }
 struct TcgMax { __host__ __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 
+// ---- sorted form: clouds in arbitrary order ----------------------------------------------------------------------------
+// Grouping needs consecutive targets to be neighbours in space. Where the scan order does not give that (mean step far
+// above the point spacing: a shuffled cloud, a mesh's vertex list) the tiles are built over the targets in MORTON order
+// instead (21 bits per axis over the cube around the cloud, cub radix sort): consecutive positions are close again, the
+// jumps of the Z curve close the columns like row ends do. Slots are then no longer in index order, so the lowest-index
+// tie rule cannot come from the slot order: the exact pass, whenever it offers a unit, looks up the ORIGINAL index of
+// every slot that attains the unit's minimum (slot_index[], read from L2 for those slots only) and the per-source key
+// carries (threshold, smallest original index) — atomicMin keeps the reference's answer whatever the visiting order.
+__device__ __forceinline__ unsigned long long morton_spread21(unsigned v)
+{
+	unsigned long long x = v & 0x1fffffu;
+	x = (x | (x << 32)) & 0x1f00000000ffffull;
+	x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+	x = (x | (x << 8))  & 0x100f00f00f00f00full;
+	x = (x | (x << 4))  & 0x10c30c30c30c30c3ull;
+	x = (x | (x << 2))  & 0x1249249249249249ull;
+	return x;
+}
+__global__ void tcg_morton_kernel(const float4* __restrict__ q4, int m, float x0, float y0, float z0, float inv, unsigned long long* keys, int* vals)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	const float4 q = q4[i];
+	const float fx = fminf(fmaxf((q.x - x0) * inv, 0.0f), 1.0f), fy = fminf(fmaxf((q.y - y0) * inv, 0.0f), 1.0f), fz = fminf(fmaxf((q.z - z0) * inv, 0.0f), 1.0f);
+	const unsigned ux = min(2097151u, (unsigned)(fx * 2097152.0f)), uy = min(2097151u, (unsigned)(fy * 2097152.0f)), uz = min(2097151u, (unsigned)(fz * 2097152.0f));
+	keys[i] = morton_spread21(ux) | (morton_spread21(uy) << 1) | (morton_spread21(uz) << 2);
+	vals[i] = i;
+}
+__global__ void tcg_gather_kernel(const float4* __restrict__ q4, const int* __restrict__ perm, int m, float4* out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < m) out[i] = q4[perm[i]];
+}
+
 // one block of 128 threads per sub-tile (128 columns)
 template <int TPC>
 __global__ void __launch_bounds__(128) tc_pack_group_kernel(const float4* __restrict__ q4, int m, const int* __restrict__ colstart, int ncols,
-                                                            float cx, float cy, float cz, float* __restrict__ tiles, float* hmax)
+                                                            float cx, float cy, float cz, float* __restrict__ tiles, float* hmax,
+                                                            const int* __restrict__ perm, int* __restrict__ slot_index)
 {
 	constexpr int TT = TC_TN * TPC;
 	const int sub = blockIdx.x;                      // global sub-tile
@@ -252,6 +290,11 @@ __global__ void __launch_bounds__(128) tc_pack_group_kernel(const float4* __rest
 	float* X = tile + TC_B_FLOATS + (sub & 1) * 128 * TPC + col * TPC;
 #pragma unroll
 	for (int k = 0; k < TPC; k++) { X[k] = q[k].x; X[TT + k] = q[k].y; X[2 * TT + k] = q[k].z; }
+	if (slot_index != nullptr) {                     // sorted form: q4 is the cloud in Morton order, perm its original indices
+		int* S = slot_index + (size_t)(sub >> 1) * TT + (sub & 1) * 128 * TPC + col * TPC;
+#pragma unroll
+		for (int k = 0; k < TPC; k++) S[k] = (k < len) ? perm[j0 + k] : -1;
+	}
 }
 
 // ---- small PTX wrappers ---------------------------------------------------------------------------------------------
@@ -677,7 +720,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) k1_filter_tc(const KTParams 
 // TPC = targets per MMA column: 1, or 2 / 4 = the grouped forms (tiles of 256 TPC targets, see tc_pack_group_kernel).
 // The filter test, the exact pass and the remembered unit are QUARTERS of a warp's sub-tile: 32 columns = 32 TPC targets
 // (the running minimum costs the same split four ways; an exact pass then covers a quarter of the targets).
-template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC, int NACC>
+template <int MODE, int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC, int NACC, bool SORTED>
 __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const KTParams p)
 {
 	constexpr int TILE_T = TC_TN * TPC;                  // targets per tile
@@ -934,7 +977,28 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 								// distance of the current class above the class floor still ties with it (NaN / inf never pass)
 								const float nt_ = (mm < inf) ? lower_threshold<MODE>(mm) : inf;
 								if (nt_ <= th && kk > -inf) {
-									atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * QPT + q_in_tile));
+									if constexpr (SORTED) {
+										// slots are in Morton order: the smallest ORIGINAL index among the slots that attain the minimum goes into the key
+										const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(nt_) : nt_;
+										const int* so = p.slot_index + (size_t)t * TILE_T;
+										int bi = 0x7fffffff;
+										for (int jq = j0; jq < j1; jq++) {
+											const float4 X = X4[jq], Y = Y4[jq], Z = Z4[jq];
+											float d0 = dist_chain(sx, sy, sz, X.x, Y.x, Z.x);
+											float d1 = dist_chain(sx, sy, sz, X.y, Y.y, Z.y);
+											float d2 = dist_chain(sx, sy, sz, X.z, Y.z, Z.z);
+											float d3 = dist_chain(sx, sy, sz, X.w, Y.w, Z.w);
+											if (MODE == ICPB_DIST_SQRT) { d0 = __fsqrt_rn(d0); d1 = __fsqrt_rn(d1); d2 = __fsqrt_rn(d2); d3 = __fsqrt_rn(d3); }
+											if (d0 <= target) bi = min(bi, __ldg(so + 4 * jq));
+											if (d1 <= target) bi = min(bi, __ldg(so + 4 * jq + 1));
+											if (d2 <= target) bi = min(bi, __ldg(so + 4 * jq + 2));
+											if (d3 <= target) bi = min(bi, __ldg(so + 4 * jq + 3));
+										}
+										if (bi != 0x7fffffff)
+											atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)bi);
+									} else {
+										atomicMin(reinterpret_cast<unsigned long long*>(key_s + sidx), ((u64)__float_as_uint(nt_) << 32) | (u64)(uint32_t)(t * QPT + q_in_tile));
+									}
 								}
 								th = __uint_as_float((unsigned)(key_s[sidx] >> 32));     // re-read: this pass (or the warp on the other half) may have lowered it
 								tau = __fadd_ru(__fmul_ru(th, one8u), kk);
@@ -961,7 +1025,13 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 					const int i = sb * SBN + sidx;
 					const u64 kv = key_s[sidx];
 					const int bs = (int)(uint32_t)(kv & 0xffffffffull);          // -1: nothing below the starting threshold
-					if (i < p.n && bs >= 0) {
+					if (SORTED) {                                               // the key already holds the original index
+						if (i < p.n && bs >= 0) {
+							const float th = __uint_as_float((unsigned)(kv >> 32));
+							const float target = (MODE == ICPB_DIST_SQRT) ? __fsqrt_rn(th) : th;
+							atomicMin(p.keys + i, ((u64)__float_as_uint(target) << 32) | (u64)(uint32_t)bs);
+						}
+					} else if (i < p.n && bs >= 0) {
 						const float th = __uint_as_float((unsigned)(kv >> 32));
 						const float sx = ox_s[sidx], sy = oy_s[sidx], sz = oz_s[sidx];
 						const float* gx = p.tiles + (size_t)(bs / QPT) * TILE_FLOATS + TC_B_FLOATS + (size_t)(bs % QPT) * QT;
@@ -1027,9 +1097,9 @@ __global__ void __launch_bounds__(64 + 256 * GROUPS, 1) k1_filter_tc_split(const
 
 // Operand tiles of the current target (needs the centre chosen by build_filter_data); buffers kept across targets.
 // kt_tpc >= 2: the grouped form — columns of up to kt_tpc consecutive targets that never span a jump of the scan.
-template <int TPC> static void launch_pack_group(Ctx* c, int nt, int ncols)
+template <int TPC> static void launch_pack_group(Ctx* c, int nt, int ncols, const float4* src, const int* perm, int* slot_index)
 {
-	tc_pack_group_kernel<TPC><<<nt * 2, 128, 0, c->stream>>>(c->q4, c->m, c->kt_colstart, ncols, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles, c->kt_hmax_d);
+	tc_pack_group_kernel<TPC><<<nt * 2, 128, 0, c->stream>>>(src, c->m, c->kt_colstart, ncols, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles, c->kt_hmax_d, perm, slot_index);
 }
 // targets per MMA column: forced by ICPB_KT_VAR (experiments), else what the exact-pass-rate policy currently holds
 static int tc_current_tpc(const Ctx* c)
@@ -1045,8 +1115,10 @@ int build_filter_tc_data(Ctx* c)
 	const int tpc = c->kt_tpc = tc_current_tpc(c);
 	if (!c->kt_fail) { ICPB_CUDA(c, cudaMalloc((void**)&c->kt_fail, sizeof(int))); ICPB_CUDA(c, cudaMemsetAsync(c->kt_fail, 0, sizeof(int), c->stream)); }
 	int nt, ncols = 0;
+	bool sorted = false;
+	const float4* src = c->q4;           // the cloud the columns are cut from: the targets in index order, or in Morton order
+	const int* perm = nullptr;
 	if (tpc >= 2) {
-		// columns: runs of the scan between jumps, cut into groups of tpc
 		if ((size_t)m + 1 > c->kt_cols_cap) {
 			cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); c->kt_colstart = c->kt_scan_a = c->kt_scan_b = nullptr; c->kt_cols_cap = 0;
 			const size_t cap = (size_t)m + 1 + (size_t)m / 8;
@@ -1057,19 +1129,52 @@ int build_filter_tc_data(Ctx* c)
 		}
 		if (!c->kt_hmax_d) ICPB_CUDA(c, cudaMalloc((void**)&c->kt_hmax_d, 2 * sizeof(double)));      // [0] float hmax (+ pad), [1] double step sum
 		double* step_sum = reinterpret_cast<double*>(c->kt_hmax_d) + 1;
+		const int g = (m + 255) / 256;
+		// Is the scan order coherent? Consecutive targets that are not neighbours in space (a cloud in arbitrary order) make
+		// every group as wide as the cloud. The mean step of the scan against the spacing of m points spread over a surface
+		// of the cloud's radius tells.
+		double step_total = 0.0;
 		ICPB_CUDA(c, cudaMemsetAsync(c->kt_hmax_d, 0, 2 * sizeof(double), c->stream));
-		size_t tmp_a = 0, tmp_b = 0;
+		tcg_step_sum_kernel<<<g, 256, 0, c->stream>>>(c->q4, m, step_sum);
+		ICPB_CUDA(c, cudaMemcpyAsync(&step_total, step_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+		const bool scattered = m > 1 && step_total / (double)(m - 1) > 16.0 * (double)c->kf_rq * sqrt(3.14159265358979 / (double)m);
+		if (c->kt_sort_mode == 1 || (c->kt_sort_mode < 0 && scattered)) sorted = true;                 // ICPB_KT_SORT: 1 always, 0 never, default: when scattered
+		else if (scattered && c->kt_variant < 0) { c->kt_tpc_auto = 1; return build_filter_tc_data(c); }   // sorting switched off: one target per column
+		size_t tmp_a = 0, tmp_b = 0, tmp_c = 0;
 		cub::DeviceScan::InclusiveScan(nullptr, tmp_a, c->kt_scan_a, c->kt_scan_a, TcgMax(), m, c->stream);
 		cub::DeviceScan::InclusiveSum(nullptr, tmp_b, c->kt_scan_b, c->kt_scan_b, m, c->stream);
-		const size_t tmp = tmp_a > tmp_b ? tmp_a : tmp_b;
+		if (sorted) {
+			if ((size_t)m > c->kt_sort_cap) {
+				cudaFree(c->kt_mkeys); cudaFree(c->kt_perm2); cudaFree(c->kt_q4s); c->kt_mkeys = nullptr; c->kt_perm2 = nullptr; c->kt_q4s = nullptr; c->kt_sort_cap = 0;
+				const size_t cap = (size_t)m + (size_t)m / 8 + 1;
+				ICPB_CUDA(c, cudaMalloc((void**)&c->kt_mkeys, sizeof(unsigned long long) * 2 * cap));
+				ICPB_CUDA(c, cudaMalloc((void**)&c->kt_perm2, sizeof(int) * 2 * cap));
+				ICPB_CUDA(c, cudaMalloc((void**)&c->kt_q4s, sizeof(float4) * cap));
+				c->kt_sort_cap = cap;
+			}
+			cub::DeviceRadixSort::SortPairs(nullptr, tmp_c, c->kt_mkeys, c->kt_mkeys + c->kt_sort_cap, c->kt_perm2, c->kt_perm2 + c->kt_sort_cap, m, 0, 63, c->stream);
+		}
+		const size_t tmp = std::max(tmp_a, std::max(tmp_b, tmp_c));
 		if (tmp > c->kt_cub_cap) {
 			cudaFree(c->kt_cub_tmp); c->kt_cub_tmp = nullptr; c->kt_cub_cap = 0;
 			ICPB_CUDA(c, cudaMalloc(&c->kt_cub_tmp, tmp + 256));
 			c->kt_cub_cap = tmp + 256;
 		}
-		const int g = (m + 255) / 256;
-		tcg_step_sum_kernel<<<g, 256, 0, c->stream>>>(c->q4, m, step_sum);
-		tcg_break_kernel<<<g, 256, 0, c->stream>>>(c->q4, m, step_sum, c->kt_scan_a);
+		if (sorted) {
+			// Morton order over the cube [centre - Rq, centre + Rq]^3, then the same column pipeline over the sorted cloud
+			const float inv = 0.5f / c->kf_rq;
+			tcg_morton_kernel<<<g, 256, 0, c->stream>>>(c->q4, m, c->kf_center[0] - c->kf_rq, c->kf_center[1] - c->kf_rq, c->kf_center[2] - c->kf_rq, inv, c->kt_mkeys, c->kt_perm2);
+			size_t t0 = c->kt_cub_cap;
+			ICPB_CUDA(c, cub::DeviceRadixSort::SortPairs(c->kt_cub_tmp, t0, c->kt_mkeys, c->kt_mkeys + c->kt_sort_cap, c->kt_perm2, c->kt_perm2 + c->kt_sort_cap, m, 0, 63, c->stream));
+			perm = c->kt_perm2 + c->kt_sort_cap;
+			tcg_gather_kernel<<<g, 256, 0, c->stream>>>(c->q4, perm, m, c->kt_q4s);
+			src = c->kt_q4s;
+			ICPB_CUDA(c, cudaMemsetAsync(c->kt_hmax_d, 0, 2 * sizeof(double), c->stream));
+			tcg_step_sum_kernel<<<g, 256, 0, c->stream>>>(src, m, step_sum);           // the jump threshold of the sorted scan
+			c->launches += 4;
+		}
+		tcg_break_kernel<<<g, 256, 0, c->stream>>>(src, m, step_sum, c->kt_scan_a);
 		size_t t1 = c->kt_cub_cap;
 		ICPB_CUDA(c, cub::DeviceScan::InclusiveScan(c->kt_cub_tmp, t1, c->kt_scan_a, c->kt_scan_a, TcgMax(), m, c->stream));      // run start of every target
 		tcg_colflag_kernel<<<g, 256, 0, c->stream>>>(c->kt_scan_a, m, tpc, c->kt_scan_b);
@@ -1077,17 +1182,8 @@ int build_filter_tc_data(Ctx* c)
 		ICPB_CUDA(c, cub::DeviceScan::InclusiveSum(c->kt_cub_tmp, t1, c->kt_scan_b, c->kt_scan_b, m, c->stream));                 // 1-based column of every target
 		tcg_colstart_kernel<<<g, 256, 0, c->stream>>>(c->kt_scan_a, c->kt_scan_b, m, tpc, c->kt_colstart);
 		c->launches += 6;
-		double step_total = 0.0;
 		ICPB_CUDA(c, cudaMemcpyAsync(&ncols, c->kt_scan_b + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-		ICPB_CUDA(c, cudaMemcpyAsync(&step_total, step_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-		// Consecutive targets that are not neighbours in space (a cloud in arbitrary order): every group is as wide as the cloud
-		// and grouping can only cost. The mean step of the scan against the spacing of m points spread over a surface of the
-		// cloud's radius tells: go to one target per column at once instead of letting the exact-pass rate find out.
-		if (c->kt_variant < 0 && m > 1 && step_total / (double)(m - 1) > 16.0 * (double)c->kf_rq * sqrt(3.14159265358979 / (double)m)) {
-			c->kt_tpc_auto = 1;
-			return build_filter_tc_data(c);
-		}
 		if (ncols < 1 || ncols > m) { snprintf(c->err, sizeof c->err, "k1_filter_tc: column scan returned %d columns for %d targets", ncols, m); return ICPB_ERR_CUDA; }
 		nt = (ncols + TC_TN - 1) / TC_TN;
 	} else {
@@ -1099,11 +1195,22 @@ int build_filter_tc_data(Ctx* c)
 		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_tiles, sizeof(float) * need));
 		c->kt_tiles_cap = need;
 	}
+	int* slot_index = nullptr;
+	if (sorted) {
+		const size_t slots = (size_t)nt * TC_TN * tpc;
+		if (slots > c->kt_slot_cap) {
+			cudaFree(c->kt_slot_index); c->kt_slot_index = nullptr; c->kt_slot_cap = 0;
+			ICPB_CUDA(c, cudaMalloc((void**)&c->kt_slot_index, sizeof(int) * slots));
+			c->kt_slot_cap = slots;
+		}
+		slot_index = c->kt_slot_index;
+	}
 	c->kt_hmax = 0.0f;
-	if (tpc == 16) launch_pack_group<16>(c, nt, ncols);
-	else if (tpc == 8) launch_pack_group<8>(c, nt, ncols);
-	else if (tpc == 4) launch_pack_group<4>(c, nt, ncols);
-	else if (tpc == 2) launch_pack_group<2>(c, nt, ncols);
+	if (tpc >= 2) ICPB_CUDA(c, cudaMemsetAsync(c->kt_hmax_d, 0, sizeof(float), c->stream));
+	if (tpc == 16) launch_pack_group<16>(c, nt, ncols, src, perm, slot_index);
+	else if (tpc == 8) launch_pack_group<8>(c, nt, ncols, src, perm, slot_index);
+	else if (tpc == 4) launch_pack_group<4>(c, nt, ncols, src, perm, slot_index);
+	else if (tpc == 2) launch_pack_group<2>(c, nt, ncols, src, perm, slot_index);
 	else tc_pack_kernel<<<(nt * TC_TN + 255) / 256, 256, 0, c->stream>>>(c->q4, m, nt * TC_TN, c->kf_center[0], c->kf_center[1], c->kf_center[2], c->kt_tiles);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
@@ -1113,6 +1220,7 @@ int build_filter_tc_data(Ctx* c)
 	}
 	c->kt_nt = nt;
 	c->kt_ncols = ncols;
+	c->kt_sorted = sorted;
 	c->graph_gen++;              // a captured iteration graph holds the tile count, hmax and (when the group size changed) the kernel of the old tiles
 	c->kt_built_tpc = tpc;
 	c->kt_ready = true;
@@ -1164,7 +1272,7 @@ static int launch_tc_variant(Ctx* c, int dist_mode, KTParams& p, int variant)
 	return ICPB_OK;
 }
 
-template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC = 32, int NACC = 1>
+template <int GROUPS, int SLABS, int STAGES, int LDW, int TPC, int QC = 32, int NACC = 1, bool SORTED = false>
 static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 {
 	constexpr int SBN = 128 * SLABS;
@@ -1179,9 +1287,9 @@ static int launch_tc_split(Ctx* c, int dist_mode, KTParams& p, int variant)
 	if (c->kf_chunk_override > 0) p.min_chunk = p.max_chunk = c->kf_chunk_override;
 	if (p.max_chunk > p.nt) p.max_chunk = p.nt;
 	if (p.min_chunk > p.max_chunk) p.min_chunk = p.max_chunk;
-	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC, QC, NACC> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC, QC, NACC>;
-	static bool attr_set[2][32][64] = {};
-	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][variant & 31][c->device & 63];
+	auto kern = (dist_mode == ICPB_DIST_SQRT) ? k1_filter_tc_split<ICPB_DIST_SQRT, GROUPS, SLABS, STAGES, LDW, TPC, QC, NACC, SORTED> : k1_filter_tc_split<ICPB_DIST_SQ, GROUPS, SLABS, STAGES, LDW, TPC, QC, NACC, SORTED>;
+	static bool attr_set[2][64][64] = {};
+	bool& done = attr_set[dist_mode == ICPB_DIST_SQRT ? 1 : 0][(variant & 31) + (SORTED ? 32 : 0)][c->device & 63];
 	if (!done) { ICPB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); done = true; }
 	long long grid = c->sm_count;
 	if (c->k1_grid_override > 0) grid = c->k1_grid_override;
@@ -1227,6 +1335,15 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 	//   5 / 6: split form, one group of 8 warps on two accumulators (per-source state merged with atomicMin), 32- / 16-column loads
 	//   7: split form, two groups of 8 warps (16 epilogue warps), 16-column loads
 	//   8 / 9: as 7 / 6 in the PAIRED form: one column per two consecutive targets (tc_pack_group_kernel); 10: as 7 with QUADS
+	p.slot_index = c->kt_sorted ? c->kt_slot_index : nullptr;
+	if (c->kt_sorted) {            // tiles in Morton order (build_filter_tc_data decided, or ICPB_KT_SORT=1): the kernels that carry original indices
+		switch (c->kt_tpc) {
+		case 16: return launch_tc_split<2, 8, 2, 16, 16, 8, 1, true>(c, dist_mode, p, 14);
+		case 8:  return launch_tc_split<2, 8, 3, 16, 8, 8, 1, true>(c, dist_mode, p, 16);
+		case 4:  return launch_tc_split<2, 8, 3, 16, 4, 8, 1, true>(c, dist_mode, p, 18);
+		default: return launch_tc_split<2, 8, 3, 16, 2, 8, 1, true>(c, dist_mode, p, 20);
+		}
+	}
 	if (!forced) {
 		switch (c->kt_tpc) {
 		case 16: return launch_tc_split<2, 8, 2, 16, 16, 8>(c, dist_mode, p, 14);

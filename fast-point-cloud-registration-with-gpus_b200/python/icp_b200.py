@@ -73,6 +73,7 @@ def _load():
         "icpb_get_filter_stats": (C.c_int, [vp, dp, dp]),
         "icpb_get_filter_config": (C.c_int, [vp, ip, ip, ip, dp]),
         "icpb_get_filter_tc_config": (C.c_int, [vp, ip, ip]),
+        "icpb_get_filter_tc_order": (C.c_int, [vp, ip]),
         "icpb_launch_count": (C.c_longlong, [vp]),
         "icpb_host_alloc": (C.c_int, [C.POINTER(vp), C.c_ulonglong]),
         "icpb_host_free": (C.c_int, [vp]),
@@ -321,7 +322,9 @@ class Context:
     def filter_tc_config(self):
         a, b = C.c_int(), C.c_int()
         self._ck(lib.icpb_get_filter_tc_config(self.h, C.byref(a), C.byref(b)), "get_filter_tc_config")
-        return {"enabled": bool(a.value), "targets_per_column": b.value}
+        o = C.c_int()
+        self._ck(lib.icpb_get_filter_tc_order(self.h, C.byref(o)), "get_filter_tc_order")
+        return {"enabled": bool(a.value), "targets_per_column": b.value, "morton_order": bool(o.value)}
 
     def dist_info(self):
         r, w, p = C.c_int(), C.c_int(), C.c_int()

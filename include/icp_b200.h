@@ -259,9 +259,15 @@ int  icpb_get_filter_stats(icpb_ctx* ctx, double* subtile_tests, double* subtile
  * that needed the exact chain, as last sampled. Results never depend on any of this. */
 int  icpb_get_filter_config(icpb_ctx* ctx, int* dims_next, int* dims_last, int* drop_axis, double* last_exact_fraction);
 /* ICPB_NN_BRUTE on the tensor cores (K1T, the default; ICPB_K1_TC=0 selects the FP32 filter): `enabled`, and how many
- * consecutive targets share one MMA column in the launches to come (1, 2, 4 or 8; chosen from the measured exact-pass rate).
+ * consecutive targets share one MMA column in the launches to come (1 ... 16; chosen from the target size and the measured
+ * exact-pass rate).
  * icpb_get_filter_config reports dims_last == 4 after a K1T launch. Results never depend on any of this. */
 int  icpb_get_filter_tc_config(icpb_ctx* ctx, int* enabled, int* targets_per_column);
+/* Whether the tiles of the last K1T build hold the targets in Morton order (1) or in index order (0). Morton order is
+ * chosen when consecutive targets are not neighbours in space (a cloud in arbitrary order: mean step of the scan far
+ * above the point spacing), so that one MMA column can still stand for a group of targets; ICPB_KT_SORT=1 / 0 forces /
+ * forbids it. Indices returned are always the caller's, the lowest one among equal distances. */
+int  icpb_get_filter_tc_order(icpb_ctx* ctx, int* morton_order);
 /* Number of kernels this context has launched since creation. */
 long long icpb_launch_count(const icpb_ctx* ctx);
 

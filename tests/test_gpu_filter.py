@@ -24,7 +24,8 @@ def _context(ib, **env):
 # every test runs with the bound chosen automatically (full on cold passes, planar on warm ones, switched by the
 # measured exact-pass rate), with the planar bound forced for each choice of the dropped axis, and with the full one
 @pytest.fixture(scope="module", params=["tc-auto", "auto", "planar-x", "planar-y", "planar-z", "full", "tc", "tc-split", "tc-split16", "tc-split2", "tc-pair", "tc-pair1", "tc-quad", "tc-oct", "tc-hex",
-                                        "tc-u8x16", "tc-u16x16", "tc-u8x8", "tc-u8x2", "tc-d16", "tc-d8", "tc-d4", "tc-d2"])
+                                        "tc-u8x16", "tc-u16x16", "tc-u8x8", "tc-u8x2", "tc-d16", "tc-d8", "tc-d4", "tc-d2",
+                                        "tc-sorted", "tc-sorted16", "tc-sorted2"])
 def ctx(ib, request):
     """A context that sends EVERY brute-force pass through the filter kernel (by default passes below 1e9 pairs
     use the direct kernel, which would make most of these small cases vacuous)."""
@@ -35,6 +36,10 @@ def ctx(ib, request):
         env.update(ICPB_KF_DIMS=2, ICPB_KF_DROP="xyz".index(request.param[-1]))
     elif request.param == "full":
         env.update(ICPB_KF_DIMS=3)
+    elif request.param.startswith("tc-sorted"):    # K1T over the targets in Morton order, whatever their scan order (policy-chosen, 16 and 2 per column)
+        env.update(ICPB_K1_TC=1, ICPB_KT_SORT=1)
+        if request.param != "tc-sorted":
+            env.update(ICPB_KT_VAR={"tc-sorted16": 14, "tc-sorted2": 20}[request.param])
     elif request.param.startswith("tc"):           # K1T: the 3-D bound evaluated by tcgen05.mma kind::tf32 (csrc/nn_filter_tc.cu)
         env.update(ICPB_K1_TC=1, ICPB_KT_VAR={"tc-auto": -1, "tc": 0, "tc-split": 5, "tc-split16": 6, "tc-split2": 7, "tc-pair": 8, "tc-pair1": 9, "tc-quad": 10, "tc-oct": 11, "tc-hex": 12,
                                                   # exact-pass units of 8 / 16 columns at 16 / 8 / 2 targets per column; d*: two 128-column accumulators per group
@@ -200,7 +205,8 @@ def test_grouped_columns_on_rasters_no_group_size_divides(ctx, ib, orc):
 
 def test_tc_group_size_policy(ib, orc):
     """Automatic choice of K1T's targets per column: the power of two at or above sqrt(m) / 64 on a scan-ordered cloud, one at once for a cloud in
-    arbitrary order (mean step of the scan far above the point spacing), and again from the start for the next target."""
+    arbitrary order (mean step of the scan far above the point spacing) — which is then grouped along its Morton order —
+    and again from the start for the next target."""
     c = _context(ib, ICPB_K1_FILTER_MIN_PAIRS=0)
     try:
         for w, want in ((128, 2), (317, 8)):
@@ -214,11 +220,13 @@ def test_tc_group_size_policy(ib, orc):
         Q = rng.random((20000, 3)).astype(np.float32); P = rng.random((5000, 3)).astype(np.float32)
         c.set_target(Q); c.set_source(P)
         a = c.match(0, ib.NN_BRUTE)
-        assert c.filter_tc_config()["targets_per_column"] == 1, c.filter_tc_config()
+        cfg = c.filter_tc_config()
+        assert cfg["morton_order"] and cfg["targets_per_column"] >= 2, cfg      # groups over the Morton order instead of one target per column
         assert np.array_equal(a, orc.match(P, Q, 0))
+        assert np.array_equal(c.match(1, ib.NN_BRUTE), orc.match(P, Q, 1))
         D, M = orc.synth_p2p(317)
         c.set_target(M); c.set_source(D)
         c.match(0, ib.NN_BRUTE)
-        assert c.filter_tc_config()["targets_per_column"] in (8, 4)
+        assert c.filter_tc_config()["targets_per_column"] in (8, 4) and not c.filter_tc_config()["morton_order"]
     finally:
         c.close()
