@@ -128,6 +128,7 @@ int  prepare_match_filter(Ctx* c);
 int  prepare_match_grid(Ctx* c);
 int  build_filter_tc_data(Ctx* c);
 int  ensure_filter_tc_data(Ctx* c);
+int  ensure_source_order(Ctx* c);
 int  launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel);
 int  filter_tc_check(Ctx* c);
 int  launch_moments(Ctx* c, int metric);
@@ -274,6 +275,11 @@ struct Ctx {
 	float4* kt_q4s = nullptr;           // the targets in Morton order
 	size_t  kt_sort_cap = 0;
 	int*    kt_slot_index = nullptr;    // original index of the target in every slot of every tile
+	bool    kt_src_checked = false;     // the order of the current source has been looked at (once per upload)
+	bool    kt_src_sorted = false;      // ... and it is visited in Morton order through kt_sperm2's second half
+	unsigned long long* kt_skeys = nullptr;
+	int*    kt_sperm2 = nullptr;
+	size_t  kt_ssort_cap = 0;
 	size_t  kt_slot_cap = 0;
 
 	// iteration state

@@ -276,7 +276,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_work); cudaFree(c->kt_mkeys); cudaFree(c->kt_perm2); cudaFree(c->kt_q4s); cudaFree(c->kt_slot_index); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
+	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_work); cudaFree(c->kt_skeys); cudaFree(c->kt_sperm2); cudaFree(c->kt_mkeys); cudaFree(c->kt_perm2); cudaFree(c->kt_q4s); cudaFree(c->kt_slot_index); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
 	cudaFree(c->grid_counts); cudaFree(c->grid_cell_of); cudaFree(c->grid_sums); cudaFree(c->grid_mm);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);
@@ -369,6 +369,7 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 	if (cap > c->n_cap_at_graph || n != c->n) c->graph_gen++;
 	c->n_cap_at_graph = c->n_cap;
 	c->n = n; c->step_state_ready = false;   // the control block caches the global point count
+	c->kt_src_checked = false; c->kt_src_sorted = false;      // K1T looks at the new source's order before its next pass
 	c->n_total_valid = false;
 	const float* src = xyz;
 	if (!on_device && n > 0) {

@@ -12,7 +12,18 @@ import icp_synth
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-D, M = icp_synth.p2p_clouds(W)
+kind = os.environ.get("TC_CLOUD", "saddle")          # saddle (raster order) | volume | sphere (random order: the Morton-ordered tiles)
+if kind == "saddle":
+    D, M = icp_synth.p2p_clouds(W)
+else:
+    rng = np.random.default_rng(99)
+    nf = W * W
+    if kind == "volume":
+        M = rng.uniform(-1.0, 1.0, size=(nf, 3)).astype(np.float32)
+    else:
+        u = rng.normal(size=(nf, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+        M = (u * (2.0 + 0.01 * rng.normal(size=(nf, 1)))).astype(np.float32)
+    D = icp_synth.rigid_move(M, icp_synth.euler_matrix([0.02, -0.02, 0.005]), [0.02, -0.01, 0.015])
 out = {}
 ref_idx = None
 variants = [int(v) for v in os.environ.get("TC_VARIANTS", "0,1,2,3,4").split(",")]
