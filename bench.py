@@ -686,8 +686,10 @@ def main():
     ap.add_argument("--skip-grid", action="store_true", help="do not run the extra whole-registration measurement with the exact grid variant (config 4, N=1)")
     ap.add_argument("--skip-floor", action="store_true", help="do not run the extra k1_filter measurements on non-height-field clouds (config 4, N=1)")
     ap.add_argument("--balance", type=int, default=0, help="N > 1: 1 = deal source blocks in proportion to each GPU's measured matching rate (two extra untimed steps); 0 = even deal (B200s of one box measured within +-1.2 %, so this is off by default)")
-    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
-                    help="how the source is dealt to the ranks (N > 1): blocks of 2048 points round-robin, or contiguous ranges")
+    ap.add_argument("--shard", default="contiguous", choices=["interleaved", "contiguous"],
+                    help="how the source is dealt to the ranks (N > 1): contiguous ranges (default: a rank's sources stay a compact piece of "
+                         "the cloud, which the Morton-ordered matching kernel rewards: 0.91 against 1.10 ms per pass on a 1/8 shard of 1M points), "
+                         "or blocks of 2048 points round-robin (round 1's default: every rank sees the same mix of regions)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

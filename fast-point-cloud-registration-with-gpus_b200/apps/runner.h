@@ -20,7 +20,7 @@ struct Runner {
 		int rc;
 		if (grp) {
 			if ((rc = icpb_group_set_target(grp, target, m)) != ICPB_OK) return rc;
-			return icpb_group_set_source(grp, source, n, 2048);        // blocks of 2048 points dealt round-robin
+			return icpb_group_set_source(grp, source, n, 0);           // contiguous shards: each GPU's sources stay a compact piece of the cloud (what the Morton-ordered matching kernel rewards)
 		}
 		if ((rc = icpb_set_target(ctx, target, m, 0)) != ICPB_OK) return rc;
 		return icpb_set_source(ctx, source, n, 0);

@@ -24,6 +24,16 @@ else:
         u = rng.normal(size=(nf, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
         M = (u * (2.0 + 0.01 * rng.normal(size=(nf, 1)))).astype(np.float32)
     D = icp_synth.rigid_move(M, icp_synth.euler_matrix([0.02, -0.02, 0.005]), [0.02, -0.01, 0.015])
+if os.environ.get("TC_SHARD"):                       # "r/w": the sources rank r of w would get from bench.py (blocks of 2048 dealt round-robin)
+    parts = [int(v) for v in os.environ["TC_SHARD"].split("/")]
+    r_, w_ = parts[0], parts[1]
+    blk = parts[2] if len(parts) > 2 else 2048             # 0: contiguous shards
+    if blk > 0:
+        blocks = np.arange(D.shape[0]) // blk
+        D = np.ascontiguousarray(D[blocks % w_ == r_])
+    else:
+        per = (D.shape[0] + w_ - 1) // w_
+        D = np.ascontiguousarray(D[r_ * per:(r_ + 1) * per])
 out = {}
 ref_idx = None
 variants = [int(v) for v in os.environ.get("TC_VARIANTS", "0,1,2,3,4").split(",")]
