@@ -369,7 +369,7 @@ int icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device)
 	if (cap > c->n_cap_at_graph || n != c->n) c->graph_gen++;
 	c->n_cap_at_graph = c->n_cap;
 	c->n = n; c->step_state_ready = false;   // the control block caches the global point count
-	c->kt_src_checked = false; c->kt_src_sorted = false;      // K1T looks at the new source's order before its next pass
+	c->kt_src_checked = false;                                // K1T looks at the new source's order before its next pass
 	c->n_total_valid = false;
 	const float* src = xyz;
 	if (!on_device && n > 0) {

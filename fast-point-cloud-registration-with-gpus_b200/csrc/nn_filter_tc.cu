@@ -1277,9 +1277,10 @@ int ensure_source_order(Ctx* c)
 {
 	if (c->kt_src_checked) return ICPB_OK;
 	c->kt_src_checked = true;
+	const bool was_sorted = c->kt_src_sorted;          // a captured iteration graph holds the src_perm pointer (or its absence)
 	c->kt_src_sorted = false;
 	const int n = c->n;
-	if (n < 1024 || c->kt_sort_mode == 0 || !c->kf_ready) return ICPB_OK;
+	if (n < 1024 || c->kt_sort_mode == 0 || !c->kf_ready) { if (was_sorted) c->graph_gen++; return ICPB_OK; }
 	if (!c->kt_hmax_d) ICPB_CUDA(c, cudaMalloc((void**)&c->kt_hmax_d, 2 * sizeof(double)));
 	double* step_sum = reinterpret_cast<double*>(c->kt_hmax_d) + 1;
 	const int g = (n + 255) / 256;
@@ -1290,8 +1291,10 @@ int ensure_source_order(Ctx* c)
 	ICPB_CUDA(c, cudaMemcpyAsync(&step_total, step_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
 	const bool scattered = step_total / (double)(n - 1) > 16.0 * (double)c->kf_rq * sqrt(3.14159265358979 / (double)n);
-	if (!(c->kt_sort_mode == 1 || scattered || c->m >= TCG_SORT_MIN)) return ICPB_OK;
+	if (!(c->kt_sort_mode == 1 || scattered || c->m >= TCG_SORT_MIN)) { if (was_sorted) c->graph_gen++; return ICPB_OK; }
+	bool moved = false;
 	if ((size_t)n > c->kt_ssort_cap) {
+		moved = true;
 		cudaFree(c->kt_skeys); cudaFree(c->kt_sperm2); c->kt_skeys = nullptr; c->kt_sperm2 = nullptr; c->kt_ssort_cap = 0;
 		const size_t cap = (size_t)n + (size_t)n / 8 + 1;
 		ICPB_CUDA(c, cudaMalloc((void**)&c->kt_skeys, sizeof(unsigned long long) * 2 * cap));
@@ -1311,7 +1314,7 @@ int ensure_source_order(Ctx* c)
 	ICPB_CUDA(c, cub::DeviceRadixSort::SortPairs(c->kt_cub_tmp, t0, c->kt_skeys, c->kt_skeys + c->kt_ssort_cap, c->kt_sperm2, c->kt_sperm2 + c->kt_ssort_cap, n, 0, 63, c->stream));
 	c->launches += 2;
 	c->kt_src_sorted = true;
-	c->graph_gen++;
+	if (!was_sorted || moved) c->graph_gen++;
 	return ICPB_OK;
 }
 
