@@ -138,6 +138,7 @@ int  launch_finish(Ctx* c);
 int  launch_pack_source(Ctx* c, const float* d_xyz, int n, bool reset_seed);
 int  launch_unpack_source(Ctx* c, float* d_xyz);
 int  launch_pack_target(Ctx* c, const float* d_xyz, int m);
+int  launch_target_same(Ctx* c, const float* d_xyz, int m, int* d_differ);
 int  launch_fp32_peak(Ctx* c, float* d_out, int iters, int blocks);
 
 // ---- NCCL (loaded lazily with dlopen; see dist.cpp) ------------------------------------------------
@@ -258,6 +259,8 @@ struct Ctx {
 	int     kt_nt = 0;
 	int     kt_tpc = 1, kt_built_tpc = 0;   // targets per MMA column: 1, or 2 / 4 = the grouped forms (consecutive targets share a column)
 	int*    kt_fail = nullptr;          // device flag: a bounded mbarrier wait of the pipeline timed out
+	int*    tgt_differ = nullptr;       // device flag of icpb_set_target's "same cloud again?" comparison
+	bool    tgt_packed = false;         // q4 holds a packed target
 	unsigned long long* kt_work = nullptr;   // [0] work counter of the K1T pass, [1] CTAs through (the last one re-arms both)
 	int*    kt_colstart = nullptr;      // grouped form: first target of every column; kt_scan_a / kt_scan_b: scan scratch (run starts, column ids)
 	int*    kt_scan_a = nullptr;

@@ -276,7 +276,7 @@ int icpb_destroy(icpb_ctx* ctx)
 	cudaFree(c->q4); cudaFree(c->qtiles); cudaFree(c->nrm4); cudaFree(c->nbr);
 	cudaFree(c->px); cudaFree(c->py); cudaFree(c->pz); cudaFree(c->keys); cudaFree(c->idx); cudaFree(c->seed); cudaFree(c->dmin);
 	cudaFree(c->stage_xyz); cudaFree(c->st); cudaFree(c->partials); cudaFree(c->errors);
-	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_work); cudaFree(c->kt_skeys); cudaFree(c->kt_sperm2); cudaFree(c->kt_mkeys); cudaFree(c->kt_perm2); cudaFree(c->kt_q4s); cudaFree(c->kt_slot_index); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
+	cudaFree(c->kt_tiles); cudaFree(c->kt_fail); cudaFree(c->kt_work); cudaFree(c->tgt_differ); cudaFree(c->kt_skeys); cudaFree(c->kt_sperm2); cudaFree(c->kt_mkeys); cudaFree(c->kt_perm2); cudaFree(c->kt_q4s); cudaFree(c->kt_slot_index); cudaFree(c->kt_colstart); cudaFree(c->kt_scan_a); cudaFree(c->kt_scan_b); cudaFree(c->kt_cub_tmp); cudaFree(c->kt_hmax_d);
 	cudaFree(c->grid_counts); cudaFree(c->grid_cell_of); cudaFree(c->grid_sums); cudaFree(c->grid_mm);
 	cudaFree(c->grid_cell_start); cudaFree(c->grid_sorted4); cudaFree(c->grid_open_list); cudaFree(c->grid_counters); cudaFree(c->grid_occ); cudaFree(c->kf_tiles7); cudaFree(c->kf_scratch); cudaFree(c->kf_stats); cudaFree(c->kf_work_counter);
 	cudaFree(c->k9.s); cudaFree(c->k9.t); cudaFree(c->k9.e); cudaFree(c->k9.ints); cudaFree(c->k9.dbl);
@@ -330,16 +330,30 @@ int icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device)
 		if ((rc = dev_alloc(c, &c->nrm4, (size_t)0)) != ICPB_OK) return rc;
 		if ((rc = dev_alloc(c, &c->nbr, (size_t)0)) != ICPB_OK) return rc;
 	}
-	if (m != c->m) c->seed_n = -1;      // seeds are indices into the target: only a different size invalidates them
-	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->kt_ready = false; c->step_state_ready = false; c->graph_gen++;
+	const bool same_size = (m == c->m) && c->tgt_packed;
 	const float* src = xyz;
 	if (!on_device) {
 		if ((rc = ensure_stage(c, sizeof(float) * 3 * (size_t)m)) != ICPB_OK) return rc;
 		ICPB_CUDA(c, cudaMemcpyAsync(c->stage_xyz, xyz, sizeof(float) * 3 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
 		src = c->stage_xyz;
 	}
+	if (same_size) {
+		// The same cloud again, bit for bit (a host-driven loop re-uploads its target at every step)? Then everything derived
+		// from it stays: packed copies, filter tiles, grid, normals, policy state, captured graphs.
+		if (!c->tgt_differ) ICPB_CUDA(c, cudaMalloc((void**)&c->tgt_differ, sizeof(int)));
+		int differ = 1;
+		ICPB_CUDA(c, cudaMemsetAsync(c->tgt_differ, 0, sizeof(int), c->stream));
+		if ((rc = launch_target_same(c, src, m, c->tgt_differ)) != ICPB_OK) return rc;
+		ICPB_CUDA(c, cudaMemcpyAsync(&differ, c->tgt_differ, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (!differ) return ICPB_OK;
+	}
+	if (m != c->m) c->seed_n = -1;      // seeds are indices into the target: only a different size invalidates them
+	c->m = m; c->nt = nt; c->have_normals = false; c->knn_k = 0; c->grid_ready = false; c->kf_ready = false; c->kt_ready = false; c->step_state_ready = false; c->graph_gen++;
+	c->tgt_packed = false;
 	if ((rc = launch_pack_target(c, src, m)) != ICPB_OK) return rc;
 	ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->tgt_packed = true;
 	return ICPB_OK;
 }
 

@@ -358,6 +358,17 @@ __global__ void pack_target_kernel(const float* __restrict__ xyz, int m, int m_p
 }
 
 // after a stand-alone matching step: keys -> idx (+ the winning distance)
+// Is the cloud just uploaded bit for bit the target already packed? (a host-driven loop re-uploads an unchanged target at
+// every step; everything derived from it — tiles, grid, normals, policy state — can then stay)
+__global__ void target_same_kernel(const float* __restrict__ xyz, const float4* __restrict__ q4, int m, int* differ)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	const float4 q = q4[j];
+	if (__float_as_uint(xyz[3 * (size_t)j]) != __float_as_uint(q.x) || __float_as_uint(xyz[3 * (size_t)j + 1]) != __float_as_uint(q.y) ||
+	    __float_as_uint(xyz[3 * (size_t)j + 2]) != __float_as_uint(q.z)) *differ = 1;
+}
+
 __global__ void resolve_kernel(const u64* keys, int* idx, int* seed, float* dmin, int n, float sentinel)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,6 +477,13 @@ int launch_pack_target(Ctx* c, const float* d_xyz, int m)
 {
 	const int m_pad = c->nt * K1_TT;
 	pack_target_kernel<<<(m_pad + 255) / 256, 256, 0, c->stream>>>(d_xyz, m, m_pad, c->q4, c->qtiles);
+	c->launches++;
+	ICPB_CUDA(c, cudaGetLastError());
+	return ICPB_OK;
+}
+int launch_target_same(Ctx* c, const float* d_xyz, int m, int* d_differ)
+{
+	target_same_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(d_xyz, c->q4, m, d_differ);
 	c->launches++;
 	ICPB_CUDA(c, cudaGetLastError());
 	return ICPB_OK;
