@@ -155,7 +155,9 @@ int  icpb_group_get_correspondences(icpb_group* g, int* idx_host);    /* in the 
 /* ---- clouds ------------------------------------------------------------------------------- */
 /* `xyz` is AoS float[3*count]; `on_device` != 0 means it already is a device pointer on the
  * context's GPU. Replaces the cudaMemcpy H2D of src/ICP_point_to_point.cu:207-208. The target is
- * re-tiled once here (it never moves during a registration). */
+ * re-tiled once here (it never moves during a registration). Uploading a cloud that is bit for bit the
+ * current target again (a host-driven loop does, at every step) keeps everything derived from it: normals
+ * (they stay valid and in place), the matching tiles and grid, captured graphs. */
 int  icpb_set_target(icpb_ctx* ctx, const float* xyz, int m, int on_device);
 int  icpb_set_source(icpb_ctx* ctx, const float* xyz, int n, int on_device);
 int  icpb_get_source(icpb_ctx* ctx, float* xyz, int on_device);          /* current (transformed) source */
