@@ -188,3 +188,23 @@ def test_knn_through_the_pyramid_equals_the_tiled_scan(ib, orc, golden_dir):
         print("normals at 100k points: pyramid %.3f ms, tiled scan %.3f ms" % (ms, ms_ref))
     finally:
         c.close()
+
+
+def test_same_target_uploaded_again_keeps_its_normals(ib, orc):
+    """icpb_set_target with a cloud that is bit for bit the current target keeps what was derived from it (a host-driven
+    loop re-uploads its target at every step); one differing bit makes it a new target."""
+    D, M = orc.synth_p2p(48)
+    with ib.Context(0) as c:
+        c.set_target(M); c.set_source(D)
+        c.estimate_normals(4)
+        p = ib.default_params(metric=ib.POINT_TO_PLANE, dist_mode=ib.DIST_SQRT, max_iter=4, stop_early=0)
+        e1, r1 = c.run(p)
+        c.set_target(M.copy()); c.set_source(D)                  # identical bits: the normals are still there
+        e2, r2 = c.run(p)
+        assert np.array_equal(e1, e2) and list(r1.R) == list(r2.R)
+        M2 = M.copy(); M2[5, 1] = np.nextafter(M2[5, 1], np.float32(9.0))
+        c.set_target(M2); c.set_source(D)                        # a new target: point-to-plane needs its normals first
+        with pytest.raises(ib.IcpError):
+            c.run(p)
+        c.estimate_normals(4)
+        c.run(p)
