@@ -1397,7 +1397,7 @@ int launch_match_filter_tc(Ctx* c, int dist_mode, float sentinel)
 {
 	int rc;
 	// targets per MMA column: forced by ICPB_KT_VAR (experiments), else chosen by the exact-pass-rate policy (kf_policy_update):
-	// it starts at kt_tpc_auto and halves whenever more than a fifth of the quarter tests end in the exact pass
+	// it starts from the target size and is halved when exact passes cost about as much as the tests and the groups are what asks for them
 	const bool forced = c->kt_variant >= 0;
 	c->kt_tpc = tc_current_tpc(c);
 	if (!c->kt_ready || c->kt_built_tpc != c->kt_tpc) { if ((rc = build_filter_tc_data(c)) != ICPB_OK) return rc; }
