@@ -492,6 +492,14 @@ def run_stream_config(args, env, emit):
         traffic = tj.get("k1_filter_tc" if used_tc else "k1_filter", {}).get(str(args.width or cfg["width"]))
     except Exception:      # noqa: BLE001
         pass
+    # dense TF32 runs at half the dense bf16 rate on B200: MEASURED_PEAKS.json's cuBLAS bf16 figure / 2 (else the nominal 1100)
+    tf32_peak, tf32_peak_source = 1100.0, "nominal dense TF32 (no MEASURED_PEAKS.json)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf32_peak = float(mp["bf16_tflops"]) / 2.0
+        tf32_peak_source = "MEASURED_PEAKS.json bf16_tflops / 2"
+    except Exception:      # noqa: BLE001
+        pass
     if rank == 0:
         fma_per_pair = fcfg["dims_last"] if used_filter else 3
         executed_frac = (achieved / 8.0) * (fma_per_pair * 2.0 if used_filter else 12.0) / fp32_peak
@@ -535,6 +543,8 @@ def run_stream_config(args, env, emit):
                                                         "minimum per sub-tile, the reference's chain on the sub-tiles it cannot exclude)" if used_tc
                                                         else "k1_match (the reference's chain on every pair)"),
                          "tensor": ({"tf32_tflops": achieved / 8.0 * 32.0 / max(1, tc_tpc), "targets_per_column": tc_tpc,
+                                     "tf32_peak_tflops": tf32_peak, "frac_of_tf32_peak": (achieved / 8.0 * 32.0 / max(1, tc_tpc)) / tf32_peak,
+                                     "tf32_peak_source": tf32_peak_source,
                                      "what": "one MMA column stands for targets_per_column consecutive targets (their centroid + a slack term); K = 16 TF32 MACs per "
                                      "(source, column) = 32 FLOP; dense TF32 nominal 1100 TFLOP/s; the kernel is bound by the TMEM read-out + minimum and the accumulator "
                                      "hand-shake, not by the MMA (profiles/r02_k1t_*)"} if used_tc else None),
